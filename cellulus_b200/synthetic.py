@@ -1,0 +1,95 @@
+"""Deterministic synthetic inputs for the embedding-space hot path.
+
+These generators produce the workloads named in SURVEY.md §8(d): loss inputs
+(L1-L3), TTA stacks (T1) and disc/ball embedding scenes (D1/D2).  They are
+pure numpy so the same bytes are produced on the authoring box and on the
+B200 box; neither the oracle nor the CUDA path is involved.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+
+def loss_offsets(batch: int, num_dims: int, out_shape, seed: int = 0) -> np.ndarray:
+    """`offsets ~ N(0,1)` of shape (B, D, *out_shape), fp32."""
+    rng = np.random.default_rng(seed)
+    return rng.standard_normal((batch, num_dims, *out_shape), dtype=np.float32)
+
+
+def tta_stack(num_passes: int, num_dims: int, out_shape, seed: int = 0) -> np.ndarray:
+    """T noisy predictions (T, D, *S) fp32: a smooth field plus per-pass noise."""
+    rng = np.random.default_rng(seed)
+    base = rng.standard_normal((1, num_dims, *out_shape), dtype=np.float32) * 4.0
+    noise = rng.standard_normal((num_passes, num_dims, *out_shape), dtype=np.float32)
+    return (base + 0.25 * noise).astype(np.float32)
+
+
+def blob_scene(
+    shape,
+    num_objects: int,
+    radius: float = 10.0,
+    offset_sigma: float = 0.5,
+    seed: int = 0,
+    dtype=np.float32,
+):
+    """Disc (2D) / ball (3D) scene with object-centric embeddings.
+
+    Returns `(embeddings, centres, instance_ids)`:
+
+    * `embeddings` (D+1, *shape): channel k (k=0 is **x**, the last axis; the
+      reference's channel order, `utils/mean_shift.py:16-32`) holds
+      `centre_k - coordinate_k + N(0, sigma^2)` inside an object and small noise
+      outside; the last channel is the "std" channel: U(0,0.1) inside objects,
+      1+U(0,0.1) outside.
+    * `centres` (K, D) in (x, y[, z]) order.
+    * `instance_ids` int32 (*shape): 0 background, 1..K the painting order.
+    """
+    shape = tuple(int(s) for s in shape)
+    D = len(shape)
+    rng = np.random.default_rng(seed)
+    # centres in array-axis order (z, y, x); keep objects away from the border
+    lo = radius
+    centres_axis = np.stack(
+        [rng.uniform(lo, s - 1 - lo, size=num_objects) for s in shape], axis=1
+    )
+    ids = np.zeros(shape, dtype=np.int32)
+    r = int(np.ceil(radius))
+    for k, c in enumerate(centres_axis):
+        sl = tuple(
+            slice(max(0, int(np.floor(ci)) - r), min(s, int(np.floor(ci)) + r + 2))
+            for ci, s in zip(c, shape)
+        )
+        grids = np.meshgrid(
+            *[np.arange(s.start, s.stop) for s in sl], indexing="ij", sparse=True
+        )
+        d2 = sum((g - ci) ** 2 for g, ci in zip(grids, c))
+        sub = ids[sl]
+        sub[(d2 <= radius * radius) & (sub == 0)] = k + 1
+    emb = np.empty((D + 1, *shape), dtype=dtype)
+    fg = ids > 0
+    coords_axis = np.meshgrid(*[np.arange(s) for s in shape], indexing="ij", sparse=True)
+    centre_lut = np.concatenate([np.zeros((1, D)), centres_axis], axis=0)
+    for ch in range(D):
+        axis = D - 1 - ch  # channel 0 = x = last axis
+        target = centre_lut[:, axis][ids]
+        off = target - coords_axis[axis]
+        off = np.where(fg, off, 0.0)
+        off = off + rng.normal(0.0, offset_sigma, size=shape)
+        emb[ch] = off.astype(dtype)
+    u = rng.uniform(0.0, 0.1, size=shape)
+    emb[D] = np.where(fg, u, 1.0 + u).astype(dtype)
+    centres_xyz = centres_axis[:, ::-1].copy()
+    return emb, centres_xyz, ids
+
+
+def scene_for_points(num_points: int, num_dims: int, radius: float = 10.0, seed: int = 0,
+                     fg_fraction: float = 0.2):
+    """Pick a canvas / object count so a blob scene has ~`num_points` foreground
+    pixels (SURVEY §8d D2 sweep).  Returns `(shape, num_objects)`."""
+    vol = np.pi * radius**2 if num_dims == 2 else 4.0 / 3.0 * np.pi * radius**3
+    num_objects = max(1, int(round(num_points / vol)))
+    total = num_points / fg_fraction
+    side = int(np.ceil(total ** (1.0 / num_dims)))
+    side = max(side, int(4 * radius))
+    return (side,) * num_dims, num_objects

@@ -1,0 +1,28 @@
+"""CPU oracle for the cellulus embedding-space hot path.  TEST INFRASTRUCTURE ONLY.
+
+This package restates, in plain numpy / torch-CPU, the reference algorithm of
+every function on the hot path.  Each function cites the
+reference `file:line` it follows (paths relative to `/root/reference/`, or the
+installed scikit-learn 1.9.0 `sklearn/cluster/_mean_shift.py` for the
+mean-shift arithmetic, which the reference delegates to that library).
+
+Who may import it: `tests/`, `__graft_entry__.smoke()` and `bench.py`'s
+`cpu_baseline` / `--impl reference` legs -- as the checker or the timed CPU
+baseline, never as the product.  Nothing under `cellulus_b200/` imports it and
+the product path has no CPU fallback.
+
+Pinning status (see DESIGN.md "Oracle"):
+
+* loss / gather / pair sampler / TTA aggregate / mean-shift segmentation /
+  greedy centre NMS / nearest-mode predict: **pinned** against outputs of the
+  reference itself, executed in the authoring container by
+  `tests/golden/make_golden.py` (imports `/root/reference` with stubs for the
+  missing third-party I/O libraries) and committed as `tests/golden/*.npz`.
+* `threshold_otsu`, `measure.label` (scikit-image, unpinned dependency of the
+  reference, not installed here, source not under `/root/reference`):
+  **parity unpinned** -- restated from the published algorithm; anchored only
+  on the reference's call sites (`detect.py:88-94`, `utils/misc.py:11-25`) and
+  on `np.histogram` / `scipy.ndimage.label`, which are present.
+"""
+
+ORACLE_IS_TEST_INFRASTRUCTURE = True

@@ -1,0 +1,267 @@
+"""Generate the golden fixtures under tests/golden/ by running THE REFERENCE.
+
+Run in the authoring container only (needs /root/reference, read-only):
+
+    python tests/golden/make_golden.py
+
+The reference is pure Python; its hot-path functions are imported unmodified.
+Third-party I/O libraries that are not installed here (gunpowder, zarr,
+funlib.learn.torch, matplotlib, skimage) are replaced by empty stub modules in
+`sys.modules` purely so the reference modules import -- none of the stubbed
+symbols is executed by the functions we call:
+
+  * `cellulus.criterions.get_loss` / `OCELoss.forward`        (criterions/oce_loss.py)
+  * `UNetModel.select_and_add_coordinates` (static)            (models/unet.py:108-124)
+  * `UNetModel.forward` in infer mode (TTA loop + std_mean)    (models/unet.py:73-100)
+        with a tiny conv as the stubbed backbone class
+  * `ZarrDataset.sample_coordinates` / `sample_offsets_within_radius`
+        on an instance built without `__init__`               (datasets/zarr_dataset.py:177-251)
+  * `mean_shift_segmentation`, `AnchorMeanshift`               (utils/mean_shift.py)
+        loaded by file path (the package __init__ pulls matplotlib)
+  * scikit-learn 1.9.0 `_mean_shift_single_seed` for per-seed (mode, count, iters)
+
+The fixtures cannot be regenerated on the GPU box (no /root/reference there);
+tests only read the committed .npz files.
+"""
+
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, REPO)
+sys.path.insert(0, REF)
+
+from cellulus_b200 import synthetic  # noqa: E402
+
+
+def _stub(name, **attrs):
+    mod = types.ModuleType(name)
+    mod.__dict__.update(attrs)
+    sys.modules[name] = mod
+    return mod
+
+
+class _TinyBackbone(torch.nn.Module):
+    """Stand-in for funlib's UNet *class* so `UNetModel.__init__` runs; a
+    single same-padded conv.  The golden stores the exact predictions it makes."""
+
+    def __init__(self, in_channels, num_fmaps_out, **kwargs):
+        super().__init__()
+        nd = len(kwargs["downsample_factors"][0])
+        conv = torch.nn.Conv2d if nd == 2 else torch.nn.Conv3d
+        self.conv = conv(in_channels, num_fmaps_out, 3, padding=1)
+
+    def forward(self, x):
+        return torch.relu(self.conv(x))
+
+
+def install_stubs():
+    _stub("gunpowder")
+    _stub("zarr")
+    _stub("matplotlib")
+    _stub("matplotlib.pyplot")
+    _stub("funlib")
+    _stub("funlib.learn")
+    _stub("funlib.learn.torch")
+    _stub("funlib.learn.torch.models", UNet=_TinyBackbone)
+
+
+def load_by_path(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_sampler(ZarrDataset, num_spatial_dims, crop, kappa, density):
+    ds = object.__new__(ZarrDataset)
+    ds.num_spatial_dims = num_spatial_dims
+    ds.kappa = kappa
+    ds.density = density
+    ds.output_shape = tuple(int(c - 16) for c in crop)  # zarr_dataset.py:94
+    ds.unbiased_shape = tuple(int(o - 2 * kappa) for o in ds.output_shape)  # :96-98
+    return ds
+
+
+def golden_loss(ZarrDataset, UNetModel, get_loss):
+    out = {}
+    cases = {
+        "2d": dict(nd=2, crop=(60, 60), kappa=10.0, density=0.1, B=2, T=10.0, w=1e-5),
+        "3d": dict(nd=3, crop=(40, 40, 40), kappa=5.0, density=0.5, B=2, T=10.0, w=1e-5),
+        "2d_hot": dict(nd=2, crop=(48, 48), kappa=4.0, density=0.6, B=3, T=2.5, w=1e-2),
+    }
+    for name, c in cases.items():
+        ds = make_sampler(ZarrDataset, c["nd"], c["crop"], c["kappa"], c["density"])
+        np.random.seed(7)
+        anchors, refs = [], []
+        for _ in range(c["B"]):
+            a, r = ds.sample_coordinates()
+            anchors.append(a)
+            refs.append(r)
+        anchors = np.stack(anchors).astype(np.int64)
+        refs = np.stack(refs).astype(np.int64)
+        offsets = synthetic.loss_offsets(c["B"], c["nd"], ds.output_shape, seed=3)
+        t_off = torch.from_numpy(offsets).clone().requires_grad_(True)
+        crit = get_loss(
+            temperature=c["T"], regularizer_weight=c["w"], density=c["density"],
+            num_spatial_dims=c["nd"], device=torch.device("cpu"),
+        )
+        ea = UNetModel.select_and_add_coordinates(t_off, torch.from_numpy(anchors))
+        er = UNetModel.select_and_add_coordinates(t_off, torch.from_numpy(refs))
+        loss, oce, reg = crit(ea, er)
+        loss.backward()
+        out.update({
+            f"{name}_offsets": offsets,
+            f"{name}_anchors": anchors.astype(np.int16),
+            f"{name}_refs": refs.astype(np.int16),
+            f"{name}_params": np.array([c["T"], c["w"], c["kappa"], c["density"]], dtype=np.float64),
+            f"{name}_ea": ea.detach().numpy(),
+            f"{name}_er": er.detach().numpy(),
+            f"{name}_loss": np.array([loss.item(), oce.item(), reg.item()], dtype=np.float64),
+            f"{name}_loss_f32": np.array(
+                [loss.detach().numpy(), oce.detach().numpy(), reg.detach().numpy()], dtype=np.float32),
+            f"{name}_grad": t_off.grad.numpy(),
+        })
+        print(name, "P/sample", anchors.shape[1], "loss", loss.item())
+    np.savez_compressed(os.path.join(HERE, "loss.npz"), **out)
+
+
+def golden_sampler(ZarrDataset):
+    out = {}
+    for name, nd, crop, kappa, density, seed in [
+        ("2d", 2, (76, 76), 10.0, 0.1, 0),
+        ("3d", 3, (48, 48, 48), 6.0, 0.2, 1),
+    ]:
+        ds = make_sampler(ZarrDataset, nd, crop, kappa, density)
+        np.random.seed(seed)
+        a, r = ds.sample_coordinates()
+        out[f"{name}_anchors"] = a.astype(np.int16)
+        out[f"{name}_refs"] = r.astype(np.int16)
+        out[f"{name}_cfg"] = np.array([nd, kappa, density, seed, *crop], dtype=np.float64)
+        out[f"{name}_counts"] = np.array([ds.get_num_anchors(), ds.get_num_references()])
+        print("sampler", name, a.shape, ds.get_num_anchors(), ds.get_num_references())
+    np.savez_compressed(os.path.join(HERE, "sampler.npz"), **out)
+
+
+def golden_tta(UNetModel):
+    out = {}
+    for name, nd, shape in [("2d", 2, (24, 28)), ("3d", 3, (6, 10, 12))]:
+        torch.manual_seed(11)
+        model = UNetModel(
+            in_channels=1, out_channels=nd, num_fmaps=4, fmap_inc_factor=2,
+            features_in_last_layer=4, downsampling_factors=[(2,) * nd], num_spatial_dims=nd,
+        ).eval()
+        n_iter, p = 4, 0.05
+        model.set_infer(p_salt_pepper=p, num_infer_iterations=n_iter, device=torch.device("cpu"))
+        raw = torch.rand(1, 1, *shape)
+        with torch.no_grad():
+            torch.manual_seed(5)
+            ref_out = model(raw)[0]
+            # replay the reference's TTA loop (models/unet.py:78-89) with the same
+            # RNG stream to capture the T predictions it aggregated
+            torch.manual_seed(5)
+            preds = []
+            for val in [0.5, 1.0]:
+                for _ in range(n_iter):
+                    noisy = raw.detach().clone()
+                    rnd = torch.rand(*noisy.shape)
+                    noisy[rnd <= p] = val
+                    preds.append(model.head_forward(model.backbone(noisy))[0].detach())
+            stack = torch.stack(preds, dim=0)
+        out[f"{name}_stack"] = stack.numpy()
+        out[f"{name}_out"] = ref_out.numpy()
+        print("tta", name, stack.shape, ref_out.shape)
+    np.savez_compressed(os.path.join(HERE, "tta.npz"), **out)
+
+
+def golden_mean_shift(ms):
+    from sklearn.cluster._mean_shift import _mean_shift_single_seed
+    from sklearn.neighbors import NearestNeighbors
+    import sklearn
+
+    out = {"sklearn_version": np.array(sklearn.__version__)}
+    cases = [
+        # name, shape, objects, radius, bandwidth, reduction_probability, threshold, int seeds?
+        ("2d_all", (64, 72), 7, 7.0, 4.0, 1.0, 0.5, False),
+        ("2d_red", (96, 96), 12, 8.0, 5.0, 0.3, 0.5, False),
+        ("3d_red", (20, 40, 44), 6, 6.0, 4.0, 0.25, 0.5, False),
+        ("2d_seeds", (64, 64), 6, 7.0, 5.0, 0.5, 0.5, True),
+    ]
+    for name, shape, K, radius, bw, rp, thr, use_seeds in cases:
+        emb, centres, ids = synthetic.blob_scene(shape, K, radius=radius, seed=len(name) + K)
+        D = len(shape)
+        emb64 = emb.astype(np.float64)
+        seeds = None
+        if use_seeds:
+            # integer (x, y) seeds like detect.py:131-132 produces, some far from any object
+            seeds = np.concatenate(
+                [np.round(centres).astype(np.int64), np.array([[1, 1], [shape[1] - 2, 2]])], axis=0)
+        mean_in = emb64[np.newaxis, :D].copy()
+        np.random.seed(123)
+        labels = ms.mean_shift_segmentation(
+            mean_in, emb64[D], bandwidth=bw, min_size=10, reduction_probability=rp,
+            threshold=thr, seeds=seeds)
+        # same call again through AnchorMeanshift to capture the fitted centres
+        mean_in2 = torch.from_numpy(emb64[np.newaxis, :D].copy())
+        if D == 2:
+            mean_in2[:, 1] += torch.arange(shape[0])[None, :, None]
+            mean_in2[:, 0] += torch.arange(shape[1])[None, None, :]
+        else:
+            mean_in2[:, 2] += torch.arange(shape[0])[None, :, None, None]
+            mean_in2[:, 1] += torch.arange(shape[1])[None, None, :, None]
+            mean_in2[:, 0] += torch.arange(shape[2])[None, None, None, :]
+        assert np.array_equal(mean_in2.numpy(), mean_in), "coordinate add mismatch"
+        mask = (emb64[D] < thr)[None]
+        ams = ms.AnchorMeanshift(bw, reduction_probability=rp, cluster_all=False, seeds=seeds)
+        np.random.seed(123)
+        labels2 = ams(mean_in2, mask=mask)[0] + 1
+        assert np.array_equal(labels, labels2)
+        centres_fit = ams.mean_shift.cluster_centers_
+        # per-seed triples straight from scikit-learn's hill climb
+        X = mean_in2[0].permute(*range(1, D + 1), 0)[torch.from_numpy(mask[0])].numpy()
+        np.random.seed(123)
+        fit_mask = np.random.rand(len(X)) < rp if rp < 1.0 else np.ones(len(X), bool)
+        Xr = X[fit_mask]
+        sd = Xr if seeds is None else np.asarray(seeds)
+        nbrs = NearestNeighbors(radius=bw, n_jobs=1).fit(Xr)
+        res = [_mean_shift_single_seed(s, Xr, nbrs, 300) for s in sd]
+        out.update({
+            f"{name}_emb": emb,
+            f"{name}_cfg": np.array([bw, rp, thr], dtype=np.float64),
+            f"{name}_labels": labels.astype(np.int32),
+            f"{name}_centres": centres_fit,
+            f"{name}_fit_mask": fit_mask,
+            f"{name}_modes": np.array([r[0] for r in res], dtype=np.float64),
+            f"{name}_counts": np.array([r[1] for r in res], dtype=np.int64),
+            f"{name}_iters": np.array([r[2] for r in res], dtype=np.int64),
+        })
+        if seeds is not None:
+            out[f"{name}_seeds"] = seeds
+        print("ms", name, "N", len(X), "fit", len(Xr), "K", len(centres_fit), "labels", labels.max())
+    np.savez_compressed(os.path.join(HERE, "mean_shift.npz"), **out)
+
+
+def main():
+    install_stubs()
+    from cellulus.criterions import get_loss
+    from cellulus.models.unet import UNetModel
+    from cellulus.datasets.zarr_dataset import ZarrDataset
+
+    ms = load_by_path("ref_mean_shift", os.path.join(REF, "cellulus/utils/mean_shift.py"))
+    golden_loss(ZarrDataset, UNetModel, get_loss)
+    golden_sampler(ZarrDataset)
+    golden_tta(UNetModel)
+    golden_mean_shift(ms)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,207 @@
+"""CPU: the oracle restatement against the reference's own outputs
+(tests/golden/*.npz, produced by tests/golden/make_golden.py from
+/root/reference) and against scikit-learn, which the reference delegates to."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mean_shift as oms
+from oracle import oce_loss as oloss
+from oracle import otsu as ootsu
+from oracle import sampler as osampler
+from oracle import size_filter as osize
+from oracle import tta as otta
+
+
+@pytest.mark.parametrize("case", ["2d", "3d", "2d_hot"])
+def test_loss_matches_reference(golden, case):
+    g = golden("loss")
+    T, w = g[f"{case}_params"][:2]
+    offsets = torch.from_numpy(g[f"{case}_offsets"])
+    anchors = torch.from_numpy(g[f"{case}_anchors"].astype(np.int64))
+    refs = torch.from_numpy(g[f"{case}_refs"].astype(np.int64))
+    ea = oloss.select_and_add_coordinates(offsets.clone(), anchors)
+    er = oloss.select_and_add_coordinates(offsets.clone(), refs)
+    assert np.array_equal(ea.numpy(), g[f"{case}_ea"])
+    assert np.array_equal(er.numpy(), g[f"{case}_er"])
+    loss, oce, reg, grad = oloss.loss_step(offsets, anchors, refs, T, w)
+    assert np.array_equal(
+        np.array([loss.numpy(), oce.numpy(), reg.numpy()], dtype=np.float32), g[f"{case}_loss_f32"])
+    assert np.array_equal(grad.numpy(), g[f"{case}_grad"])
+
+
+def test_loss_analytic_gradient_float64(golden):
+    # dL/dea = (2/T) exp(-d^2/T) (ea - er) + w ea/||ea||, scattered onto the anchor pixel
+    g = golden("loss")
+    T, w = g["2d_params"][:2]
+    offsets = torch.from_numpy(g["2d_offsets"]).double()
+    anchors = g["2d_anchors"].astype(np.int64)
+    refs = g["2d_refs"].astype(np.int64)
+    _, _, _, grad = oloss.loss_step_float64(offsets, torch.from_numpy(anchors), torch.from_numpy(refs), T, w)
+    B = offsets.shape[0]
+    manual = np.zeros_like(offsets.numpy())
+    off = offsets.numpy()
+    for b in range(B):
+        ax, ay = anchors[b, :, 0], anchors[b, :, 1]
+        rx, ry = refs[b, :, 0], refs[b, :, 1]
+        ea = np.stack([off[b, 0, ay, ax] + ax, off[b, 1, ay, ax] + ay], 1)
+        er = np.stack([off[b, 0, ry, rx] + rx, off[b, 1, ry, rx] + ry], 1)
+        diff = ea - er
+        d2 = (diff**2).sum(1)
+        gr = (2.0 / T) * np.exp(-d2 / T)[:, None] * diff + w * ea / np.linalg.norm(ea, axis=1)[:, None]
+        np.add.at(manual[b, 0], (ay, ax), gr[:, 0])
+        np.add.at(manual[b, 1], (ay, ax), gr[:, 1])
+    np.testing.assert_allclose(manual, grad.numpy(), rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("case", ["2d", "3d"])
+def test_sampler_matches_reference(golden, case):
+    g = golden("sampler")
+    cfg = g[f"{case}_cfg"]
+    nd, kappa, density, seed = int(cfg[0]), cfg[1], cfg[2], int(cfg[3])
+    crop = tuple(int(c) for c in cfg[4:])
+    out_shape = osampler.output_shape_of(crop)
+    np.random.seed(seed)
+    a, r = osampler.sample_coordinates(out_shape, kappa, density, nd)
+    assert np.array_equal(a, g[f"{case}_anchors"].astype(np.int64))
+    assert np.array_equal(r, g[f"{case}_refs"].astype(np.int64))
+    n_a, n_r = g[f"{case}_counts"]
+    assert osampler.num_anchors(density, osampler.unbiased_shape_of(out_shape, kappa)) == n_a
+    assert osampler.num_references(density, kappa) == n_r
+    # structural properties the device sampler is later held to
+    off = r - a
+    assert ((off**2).sum(1) < kappa**2).all() and (np.abs(off).sum(1) > 0).all()
+    assert a.min() >= kappa and (a.max(0) <= np.array(out_shape[:nd]) - kappa).all()
+    assert (a.reshape(n_a, n_r, nd) == a.reshape(n_a, n_r, nd)[:, :1]).all()
+
+
+@pytest.mark.parametrize("case", ["2d", "3d"])
+def test_tta_matches_reference(golden, case):
+    g = golden("tta")
+    out = otta.tta_aggregate(torch.from_numpy(g[f"{case}_stack"]))
+    assert np.array_equal(out.numpy(), g[f"{case}_out"])
+    exact = otta.tta_aggregate_float64(torch.from_numpy(g[f"{case}_stack"]))
+    np.testing.assert_allclose(out.numpy(), exact.numpy(), rtol=2e-5, atol=1e-6)
+
+
+MS_CASES = ["2d_all", "2d_red", "3d_red", "2d_seeds"]
+
+
+def _ms_inputs(g, case):
+    emb = g[f"{case}_emb"].astype(np.float64)
+    bw, rp, thr = g[f"{case}_cfg"]
+    seeds = g[f"{case}_seeds"] if f"{case}_seeds" in g.files else None
+    return emb, bw, rp, thr, seeds
+
+
+@pytest.mark.parametrize("case", MS_CASES)
+def test_mean_shift_port_matches_reference(golden, case):
+    g = golden("mean_shift")
+    emb, bw, rp, thr, seeds = _ms_inputs(g, case)
+    D = emb.shape[0] - 1
+    mean_in = emb[np.newaxis, :D].copy()
+    np.random.seed(123)
+    labels = oms.mean_shift_segmentation(mean_in, emb[D], bw, 10, rp, thr, seeds)
+    assert labels.dtype == np.int32
+    assert np.array_equal(labels, g[f"{case}_labels"])
+    # the in-place coordinate add is part of the contract (utils/mean_shift.py:15-32)
+    assert np.array_equal(mean_in[0], oms.points_from_embedding(emb[:D], np.ones(emb.shape[1:], bool))
+                          .reshape(*emb.shape[1:], D).transpose(D, *range(D)))
+
+
+@pytest.mark.parametrize("case", MS_CASES)
+def test_mean_shift_restatement_matches_sklearn(golden, case):
+    g = golden("mean_shift")
+    emb, bw, rp, thr, seeds = _ms_inputs(g, case)
+    D = emb.shape[0] - 1
+    mask = emb[D] < thr
+    X = oms.points_from_embedding(emb[:D], mask)
+    fit_mask = g[f"{case}_fit_mask"]
+    Xr = X[fit_mask]
+    sd = Xr if seeds is None else seeds.astype(np.float64)
+    modes, counts, iters = oms.mean_shift_modes(Xr, sd, bw)
+    assert np.array_equal(counts, g[f"{case}_counts"])
+    assert np.array_equal(iters, g[f"{case}_iters"])
+    keep = counts > 0
+    np.testing.assert_allclose(modes[keep], g[f"{case}_modes"][keep], rtol=0, atol=1e-9 * bw)
+    centres = oms.nms_centres(modes, counts, bw)
+    np.testing.assert_allclose(centres, g[f"{case}_centres"], rtol=0, atol=1e-9 * bw)
+    labels = oms.predict_labels(X, centres)
+    out = np.zeros(mask.shape, np.int32)
+    out[mask] = labels + 1
+    assert np.array_equal(out, g[f"{case}_labels"])
+
+
+def test_mean_shift_kats():
+    """Behaviours SURVEY §8c verified on the reference: inclusive radius,
+    predict labels orphans, nearest-centre ties -> lowest index."""
+    X = np.array([[0.0, 0.0], [3.0, 4.0], [100.0, 100.0]])
+    modes, counts, iters = oms.mean_shift_modes(X, X[:1], 5.0)
+    assert counts[0] == 2  # the point at distance exactly 5 is inside
+    centres = np.array([[0.0, 0.0], [2.0, 0.0]])
+    lab = oms.predict_labels(np.array([[1.0, 0.0], [50.0, 50.0]]), centres)
+    assert lab[0] == 0  # tie -> lowest index
+    assert lab[1] == 1  # orphan still labelled
+    # seeds with an empty window are dropped
+    modes, counts, _ = oms.mean_shift_modes(X, np.array([[50.0, 50.0], [0.0, 0.0]]), 5.0)
+    assert counts[0] == 0 and len(oms.nms_centres(modes, counts, 5.0)) == 1
+
+
+def test_bin_seeds_match_sklearn():
+    from sklearn.cluster import get_bin_seeds
+
+    rng = np.random.default_rng(0)
+    X = rng.uniform(0, 50, size=(500, 2))
+    mine = oms.get_bin_seeds(X, 7.0)
+    theirs = get_bin_seeds(X, 7.0)
+    assert mine.dtype == theirs.dtype
+    assert np.array_equal(mine, theirs)
+
+
+def test_otsu_restatement():
+    rng = np.random.default_rng(0)
+    img = np.where(rng.random((64, 64)) < 0.3, rng.uniform(0, 0.1, (64, 64)), 1 + rng.uniform(0, 0.1, (64, 64)))
+    t = ootsu.threshold_otsu(img)
+    assert 0.1 < t < 1.0
+    # returns a bin centre of np.histogram(img, 256)
+    _, edges = np.histogram(img.ravel(), 256)
+    centres = (edges[:-1] + edges[1:]) / 2
+    assert t in centres
+    # brute-force between-class variance over the same 255 splits
+    counts, _ = np.histogram(img.ravel(), 256)
+    best, best_i = -1, -1
+    for i in range(255):
+        w1, w2 = counts[: i + 1].sum(), counts[i + 1:].sum()
+        if w1 == 0 or w2 == 0:
+            continue
+        m1 = (counts[: i + 1] * centres[: i + 1]).sum() / w1
+        m2 = (counts[i + 1:] * centres[i + 1:]).sum() / w2
+        v = w1 * w2 * (m1 - m2) ** 2
+        if v > best:
+            best, best_i = v, i
+    assert abs(t - centres[best_i]) <= (edges[1] - edges[0]) * 1.0001
+    const = np.full((4, 4), 0.25)
+    assert ootsu.threshold_otsu(const) == 0.25
+    mask, thr = ootsu.foreground_mask(img, None)
+    assert thr == t and mask.sum() == (img < t).sum()
+
+
+@pytest.mark.parametrize("shape", [(40, 50), (12, 20, 24)])
+def test_size_filter_restatement(shape):
+    rng = np.random.default_rng(1)
+    binary = rng.random(shape) < 0.35
+    lab = osize.label_equal_regions(binary.astype(np.uint16))
+    assert np.array_equal(lab, osize.label_binary_scipy(binary))
+    # multi-valued: equal-value regions, touching different labels stay apart
+    seg = (binary * rng.integers(1, 4, size=shape)).astype(np.uint16)
+    lab2 = osize.label_equal_regions(seg)
+    for v in range(1, 4):
+        per_value = osize.label_binary_scipy(seg == v)
+        a, b = lab2[seg == v], per_value[seg == v]
+        # same partition
+        assert len(np.unique(a)) == len(np.unique(b)) == len(np.unique(np.stack([a, b]), axis=1).T)
+    out = osize.size_filter(seg.copy(), 5)
+    sizes = np.bincount(out.ravel())[1:]
+    assert (sizes >= 5).all()
+    assert osize.size_filter(seg, 0) is seg
