@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""Benchmark of the embedding-space hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Headline line (ONE JSON line on stdout, rank 0): OCELoss fwd+bwd px/s on BASELINE
+config #2 -- offsets (8, 2, 496, 496) fp32, 8 x 702,367 (anchor, reference) pairs,
+int64 coordinate lists as the reference's DataLoader delivers them, kappa 10,
+density 0.1, T 10, w 1e-5.  A "step" is one pass of the fused gather + loss +
+backward over one such batch; with N GPUs every rank runs its own batch (the path
+shards by batch, no data-path collective: weak scaling).  The same line carries
+
+  roofline      achieved algorithmic HBM GB/s of the fused kernel vs the measured peak
+  cpu_baseline  the oracle port of the reference path timed on this box's host cores
+  e2e           the same metric through the public API from pinned HOST buffers
+  detect        secondary metric: mean-shift detection Mpx/s on BASELINE config #3
+                (128 x 256 x 256 volume, 3-D embeddings), with its own cpu_baseline
+
+`--impl reference` times the oracle port (torch CPU, all host threads) on rank 0.
+Nothing here reads /root/reference.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+# ---- BASELINE config #2 ---------------------------------------------
+B, D, OUT = 8, 2, (496, 496)
+KAPPA, DENSITY, TEMP, REGW = 10.0, 0.1, 10.0, 1e-5
+N_ANCHORS = int(DENSITY * (OUT[0] - 2 * KAPPA) * (OUT[1] - 2 * KAPPA))  # 22 657
+N_REFS = int(DENSITY * KAPPA**2 * np.pi)  # 31
+P = N_ANCHORS * N_REFS  # 702 367
+N_PX = B * OUT[0] * OUT[1]  # 1 968 128
+# algorithmic bytes per step: both int64 coordinate lists once, offsets once, dense gradient once
+ALGO_BYTES = B * P * D * 8 * 2 + N_PX * D * 4 + N_PX * D * 4
+WORKLOAD = "configs[1]: OCELoss fwd+bwd, offsets (8,2,496,496) f32, 8x702367 pairs, int64 coords, kappa=10, density=0.1"
+
+# ---- BASELINE config #3 (secondary: detect) ----------------------------------------------
+DET_SHAPE, DET_OBJECTS, DET_RADIUS, DET_BW, DET_THR, DET_RP = (128, 256, 256), 400, 10.0, 7.0, 0.5, 0.1
+
+
+def measured_peak_gbs():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed regions run."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, windows):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if not any(a - 0.05 <= ts <= b + 0.15 for a, b in windows):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except Exception:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:  # timed regions shorter than the sampling period: fall back to every sample taken
+            for ts, line in self.rows:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[0]))
+                    smax.append(float(f[1]))
+                except Exception:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------- reference arm
+def cpu_loss_step_time(batch, steps, warmup, seed=0):
+    """Oracle port of the reference loss slice on the host CPU (torch, all threads)."""
+    from cellulus_b200 import synthetic
+    from oracle import oce_loss as oloss
+    from oracle import sampler as osampler
+
+    np.random.seed(seed)
+    pairs = [osampler.sample_coordinates(OUT, KAPPA, DENSITY, D) for _ in range(batch)]
+    anchors = torch.from_numpy(np.stack([p[0] for p in pairs])).long()
+    refs = torch.from_numpy(np.stack([p[1] for p in pairs])).long()
+    offsets = torch.from_numpy(synthetic.loss_offsets(batch, D, OUT, seed=seed))
+    for _ in range(warmup):
+        oloss.loss_step(offsets, anchors, refs, TEMP, REGW)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oloss.loss_step(offsets, anchors, refs, TEMP, REGW)
+    return (time.perf_counter() - t0) / max(steps, 1)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = torch.get_num_threads()
+    t_one = cpu_loss_step_time(1, 1, 1)
+    budget = 100.0 / max(args.steps + args.warmup, 1)  # whole run within a couple of minutes
+    batch = int(max(1, min(B, budget / max(t_one, 1e-6))))
+    t = cpu_loss_step_time(batch, args.steps, args.warmup)
+    px = batch * OUT[0] * OUT[1]
+    value = px / t
+    sample = f"{batch}/{B} samples of the batch per step ({batch * P} pairs), {args.steps} steps"
+    line = {
+        "impl": "reference", "metric": "OCELoss fwd+bwd px/s", "value": value, "unit": "px/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "px/s", "cores": cores, "kind": "port", "sample": sample,
+                         "pairs_per_s": batch * P / t},
+        "e2e": {"value": value, "unit": "px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------- B200 arm
+def bench_detect(dev, windows):
+    """Secondary metric: threshold -> labels on BASELINE config #3, inputs resident in HBM."""
+    from cellulus_b200 import kernels as K
+    from cellulus_b200 import synthetic
+    from cellulus_b200.detect import detect_embeddings
+
+    emb_np, _, ids = synthetic.blob_scene(DET_SHAPE, DET_OBJECTS, radius=DET_RADIUS, seed=0)
+    emb = torch.from_numpy(emb_np).to(dev)
+    n_vox = int(np.prod(DET_SHAPE))
+    fg = int((ids > 0).sum())
+    kw = dict(bandwidth=DET_BW, threshold=DET_THR, reduction_probability=DET_RP, rng="philox")
+    for _ in range(2):
+        labels, _, _, infos = detect_embeddings(emb, return_info=True, **kw)
+    torch.cuda.synchronize(dev)
+    reps = 5
+    c0 = K.launch_counter["calls"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    e0.record()
+    for _ in range(reps):
+        labels, _, _ = detect_embeddings(emb, **kw)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    windows.append((w0, time.time()))
+    ms = e0.elapsed_time(e1) / reps
+    calls = (K.launch_counter["calls"] - c0) // reps
+    # e2e: pinned host volume in, uint16 labels out
+    host = torch.from_numpy(emb_np).pin_memory()
+    out_host = torch.empty((1, *DET_SHAPE), dtype=torch.uint16).pin_memory()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        d = host.to(dev, non_blocking=True)
+        labels, _, _ = detect_embeddings(d, **kw)
+        out_host.copy_(labels, non_blocking=True)
+        torch.cuda.synchronize(dev)
+    e2e_s = (time.perf_counter() - t0) / 3
+    info = infos[0]
+    return {
+        "metric": "detect Mpx/s (mean-shift)", "value": n_vox / ms / 1e3, "unit": "Mpx/s", "ms_per_volume": ms,
+        "config": {"workload": "configs[2]: 128x256x256 volume, 3-D embeddings, 400 balls r=10, bw=7, threshold=0.5, "
+                               "reduction_probability=0.1, seeds=all fit points",
+                   "foreground_voxels": fg, "fit_points": int(info["n_fit"]), "centres": int(info["k"]),
+                   "method": info["method"]},
+        "e2e": {"value": n_vox / e2e_s / 1e6, "unit": "Mpx/s", "h2d_bytes_per_step": host.numel() * 4,
+                "d2h_bytes_per_step": out_host.numel() * 2},
+        "abi_calls_per_volume": int(calls),
+    }
+
+
+def cpu_detect_baseline():
+    """Oracle port of `mean_shift_segmentation` (scikit-learn MeanShift, hill climb on ONE core as shipped)
+    on a bounded sub-volume of the same scene family."""
+    from cellulus_b200 import synthetic
+    from oracle import mean_shift as oms
+
+    shape, objects = (24, 96, 96), 11  # same object density as config #3
+    emb, _, _ = synthetic.blob_scene(shape, objects, radius=DET_RADIUS, seed=0)
+    emb64 = emb.astype(np.float64)
+    np.random.seed(0)
+    t0 = time.perf_counter()
+    labels = oms.mean_shift_segmentation(emb64[np.newaxis, :3].copy(), emb64[3], DET_BW, 0, DET_RP, DET_THR, None)
+    dt = time.perf_counter() - t0
+    n = int(np.prod(shape))
+    return {"value": n / dt / 1e6, "unit": "Mpx/s", "cores": 1, "kind": "port",
+            "sample": f"{shape[0]}x{shape[1]}x{shape[2]} sub-volume, {objects} balls, {int((labels > 0).sum())} fg voxels, "
+                      f"{dt:.1f} s; sklearn hill climb is single-core (n_jobs=None), predict uses OpenMP"}
+
+
+def run_b200(args):
+    from cellulus_b200 import kernels as K
+    from cellulus_b200.criterions import oce_loss_fused
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist = None
+    if args.gpus != world:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    windows = []
+
+    # inputs resident in HBM: every rank owns its own batch (sharded by batch)
+    torch.manual_seed(rank)
+    offsets = torch.randn(B, D, *OUT, device=dev, requires_grad=True)
+    anchors, refs = K.sample_pairs(B, (OUT[1], OUT[0]), KAPPA, N_ANCHORS, N_REFS, seed=1234 + rank, device=dev,
+                                   dtype=torch.int64)
+
+    def step():
+        offsets.grad = None
+        loss, oce, reg = oce_loss_fused(offsets, anchors, refs, TEMP, REGW)
+        loss.backward()
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize(dev)
+
+    # (1) whole-job throughput: K steps between barriers, device-timed, max over ranks
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    c0 = K.launch_counter["calls"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if dist is not None:
+        dist.barrier()
+    windows.append((w0, time.time()))
+    launches = K.launch_counter["calls"] - c0
+    total_ms = e0.elapsed_time(e1)
+    t_ms = torch.tensor([total_ms], device=dev)
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = t_ms.item() / args.steps
+    value = world * N_PX / (ms_per_step * 1e-3)
+
+    # (2) the dominant kernel alone: events around each fused launch (gradient memset included)
+    k_ms = []
+    for _ in range(min(args.steps, 50)):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        K.oce_loss_fwd_bwd(offsets.detach(), anchors, refs, TEMP, REGW, want_grad=True)
+        b.record()
+        k_ms.append((a, b))
+    torch.cuda.synchronize(dev)
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ms]))
+    peak, peak_src = measured_peak_gbs()
+    achieved = ALGO_BYTES / (k_ms * 1e-3) / 1e9
+
+    # (3) end to end through the public API from pinned host buffers
+    h_off = offsets.detach().cpu().pin_memory()
+    h_anc, h_ref = anchors.cpu().pin_memory(), refs.cpu().pin_memory()
+    e2e_steps = max(3, min(args.steps, 20))
+
+    def e2e_step():
+        o = h_off.to(dev, non_blocking=True).requires_grad_(True)
+        a = h_anc.to(dev, non_blocking=True)
+        r = h_ref.to(dev, non_blocking=True)
+        loss, _, _ = oce_loss_fused(o, a, r, TEMP, REGW)
+        loss.backward()
+        return loss.item()  # device -> host read of the step's result (train.py:180)
+
+    for _ in range(2):
+        e2e_step()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    w0 = time.time()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize(dev)
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=dev)
+    windows.append((w0, time.time()))
+    if dist is not None:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * N_PX / e2e_s.item()
+
+    detect = None
+    cpu_base = None
+    if rank == 0:
+        if not args.skip_detect:
+            detect = bench_detect(dev, windows)
+        if world == 1 and not args.skip_cpu:
+            t_cpu = cpu_loss_step_time(B, 3, 1)
+            cpu_base = {"value": N_PX / t_cpu, "unit": "px/s", "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"full configs[1] batch ({B * P} pairs), 3 steps after 1 warm-up, {t_cpu * 1e3:.0f} ms/step",
+                        "pairs_per_s": B * P / t_cpu}
+            if detect is not None:
+                detect["cpu_baseline"] = cpu_detect_baseline()
+    if dist is not None:
+        dist.barrier()
+    if rank == 0:
+        clocks = sampler.stop(windows)
+        line = {
+            "metric": "OCELoss fwd+bwd px/s", "value": value, "unit": "px/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": B * P, "px_per_step_per_gpu": N_PX,
+                       "l2": "inputs larger than L2 (211 MB streamed per step vs 126 MB L2); no explicit flush",
+                       "sharding": "by batch, one batch per rank, no data-path collective"},
+            "pairs_per_s": world * B * P / (ms_per_step * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "oce_loss_fused_kernel<2,int64,f32,bwd>",
+                         "kernel_ms": k_ms, "algorithmic_bytes_per_launch": ALGO_BYTES,
+                         "note": "duration includes the 15.7 MB gradient memset issued by the same C-ABI call"},
+            "cpu_baseline": cpu_base,
+            "e2e": {"value": e2e_value, "unit": "px/s",
+                    "h2d_bytes_per_step": int(h_off.numel() * 4 + h_anc.numel() * 8 + h_ref.numel() * 8),
+                    "d2h_bytes_per_step": 4, "steps": e2e_steps, "ms_per_step": e2e_s.item() * 1e3},
+            "gpu_launches": int(launches * world),
+            "clocks": clocks,
+            "detect": detect,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--skip-detect", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,105 @@
+"""ctypes binding of `libcellulus_b200.so` (C ABI declared in include/cellulus_b200.h).
+
+The product path has NO CPU fallback: if the library is missing the import of
+any op raises, loudly, with the build command.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libcellulus_b200.so")
+
+OK, EINVAL, EUNSUPPORTED = 0, -1, -2
+F32, BF16, F64, I64, I32, I16, U8, U16 = range(8)
+
+
+class Grid(C.Structure):
+    """`cb200_grid` (include/cellulus_b200.h)."""
+
+    _fields_ = [
+        ("origin", C.c_double * 3),
+        ("cell", C.c_double),
+        ("inv_cell", C.c_double),
+        ("dims", C.c_int32 * 3),
+        ("num_dims", C.c_int32),
+        ("n_cells", C.c_int64),
+    ]
+
+
+class CellulusB200Error(RuntimeError):
+    pass
+
+
+_p, _i, _i64, _f, _d, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_uint64
+_pi64 = C.POINTER(C.c_int64)
+
+# name -> (restype, argtypes); every symbol the header declares
+PROTOTYPES = {
+    "cb200_version": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "cb200_error_string": (C.c_char_p, [_i]),
+    "cb200_oce_loss_workspace_bytes": (_i64, []),
+    "cb200_oce_loss_fwd_bwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _pi64, _i64, _f, _f, _p, _p, _p, _p]),
+    "cb200_scale_inplace": (_i, [_p, _i64, _p, _p]),
+    "cb200_gather_add_coords": (_i, [_p, _i, _p, _i, _i, _i, _pi64, _i64, _p, _p]),
+    "cb200_scatter_add_coords": (_i, [_p, _p, _i, _i, _i, _pi64, _i64, _p, _p]),
+    "cb200_oce_pair_loss": (_i, [_p, _p, _i64, _i, _f, _f, _p, _p, _p, _p]),
+    "cb200_sample_pairs": (_i, [_p, _p, _i, _i, _i, _pi64, _d, _i64, _i, _u64, _u64, _p]),
+    "cb200_tta_aggregate": (_i, [_p, _i, _i, _i64, _p, _p]),
+    "cb200_tta_accumulate": (_i, [_p, _p, _i, _i, _i64, _p]),
+    "cb200_tta_finalize": (_i, [_p, _i, _i, _i64, _p, _p]),
+    "cb200_reduce_workspace_bytes": (_i64, []),
+    "cb200_minmax": (_i, [_p, _i, _i64, _p, _p, _p]),
+    "cb200_histogram": (_i, [_p, _i, _i64, _p, _i, _p, _p]),
+    "cb200_compact_workspace_bytes": (_i64, [_i64]),
+    "cb200_fg_compact": (_i, [_p, _i, _i, _pi64, _d, _p, _p, _i64, _p, _p, _i, _p, _p]),
+    "cb200_select_points": (_i, [_p, _i64, _i64, _i, _p, _p, _i64, _p, _p, _p]),
+    "cb200_bernoulli_flags": (_i, [_p, _i64, _d, _u64, _p]),
+    "cb200_ms_brute_partial_bytes": (_i64, [_i64, _i64, _i]),
+    "cb200_ms_brute_accumulate": (_i, [_p, _i64, _i64, _i, _p, _i64, _p, _i64, _d, _p, _p]),
+    "cb200_ms_update": (_i, [_p, _i64, _i, _p, _p, _p, _i64, _i64, _p, _d, _i, _p, _p, _p]),
+    "cb200_grid_plan": (_i, [C.POINTER(_d), C.POINTER(_d), _i, _d, _i64, C.POINTER(Grid)]),
+    "cb200_grid_build_workspace_bytes": (_i64, [_i64, _i64]),
+    "cb200_grid_build": (_i, [_p, _i64, _i64, C.POINTER(Grid), _p, _i64, _p, _p, _p, _i64, _p]),
+    "cb200_ms_grid_modes": (_i, [_p, _i64, _i64, C.POINTER(Grid), _p, _p, _i64, _i64, _d, _i, _p, _p, _p, _p]),
+    "cb200_nms_workspace_bytes": (_i64, [_i64, _i, _i64]),
+    "cb200_nms_centres": (_i, [_p, _i64, _i, _p, _i64, _d, C.POINTER(Grid), _p, _p, _p, _i64, _p]),
+    "cb200_assign_labels": (_i, [_p, _i64, _i64, _i, _p, _i64, _i, _p, _p, _i, _p]),
+    "cb200_cc_workspace_bytes": (_i64, [_i64]),
+    "cb200_label_components": (_i, [_p, _i, _pi64, _p, _p, _p, _p]),
+    "cb200_size_filter": (_i, [_p, _i, _pi64, _i64, _p, _p, _p, _p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once) and attach the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CellulusB200Error(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built and there is no CPU fallback. "
+            "Run `python -m cellulus_b200.build` (needs nvcc; cross-compiles sm_100a without a GPU)."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here = header and library out of sync
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str) -> None:
+    if code == OK:
+        return
+    msg = load().cb200_error_string(code)
+    raise CellulusB200Error(f"{what} failed: {msg.decode() if msg else code} (code {code})")
+
+
+def spatial_array(shape):
+    return (C.c_int64 * len(shape))(*[int(s) for s in shape])

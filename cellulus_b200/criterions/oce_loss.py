@@ -1,0 +1,152 @@
+"""Object-centric-embedding loss on the B200 kernels.
+
+`OCELoss` keeps the reference's constructor and `forward(anchor_embedding,
+reference_embedding) -> (loss, oce_loss, regularization_loss)` contract
+(`cellulus/criterions/oce_loss.py:5-63`); `oce_loss_fused` replaces the three
+calls of `cellulus/train.py:169-176` (gather, gather, criterion) with ONE
+kernel that also produces the gradient w.r.t. the offsets.
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from cellulus_b200 import kernels as K
+
+
+class _PairLoss(torch.autograd.Function):
+    """criterions/oce_loss.py:53-63 on materialised (.., D) embeddings; gradient
+    flows to the anchor side only (the reference side is `.detach()`ed, :55)."""
+
+    @staticmethod
+    def forward(ctx, anchor_embedding, reference_embedding, temperature, regularization_weight):
+        ctx.set_materialize_grads(False)
+        need = ctx.needs_input_grad[0]
+        out, grad = K.oce_pair_loss(anchor_embedding, reference_embedding, temperature, regularization_weight, need)
+        ctx.args = (temperature, regularization_weight)
+        ctx.in_dtype = anchor_embedding.dtype
+        ctx.save_for_backward(grad, anchor_embedding, reference_embedding)
+        return out[0], out[1], out[2]
+
+    @staticmethod
+    def backward(ctx, g_loss, g_oce, g_reg):
+        grad, ea, er = ctx.saved_tensors
+        T, w = ctx.args
+        if grad is None:
+            return None, None, None, None
+        total = _combine(grad, g_loss, g_oce, g_reg,
+                         lambda ww: K.oce_pair_loss(ea, er, T, ww, True)[1])
+        return total.reshape(ea.shape).to(ctx.in_dtype), None, None, None
+
+
+def _combine(grad, g_loss, g_oce, g_reg, recompute):
+    """d/d(input) of g_loss*loss + g_oce*oce + g_reg*reg from the stored d loss/d(input)."""
+    if g_oce is None and g_reg is None:
+        if g_loss is None:
+            return torch.zeros_like(grad)
+        # common case (loss.backward()): one scale kernel that exits at once when g_loss == 1.
+        # The stored gradient is left untouched so that retain_graph=True keeps working.
+        scale = g_loss.detach().to(torch.float32).reshape(1).contiguous()
+        return K.scale_inplace(grad.clone(), scale)
+    # rare: somebody differentiates oce_loss / regularization_loss on their own
+    g_oce_only = recompute(0.0)  # regulariser off
+    g_reg_only = grad - g_oce_only
+    zero = torch.zeros((), device=grad.device)
+    gl = zero if g_loss is None else g_loss
+    go = zero if g_oce is None else g_oce
+    gr = zero if g_reg is None else g_reg
+    return (gl + go) * g_oce_only + (gl + gr) * g_reg_only
+
+
+class _FusedLoss(torch.autograd.Function):
+    """cellulus/train.py:169-176 in one kernel (cb200_oce_loss_fwd_bwd)."""
+
+    @staticmethod
+    def forward(ctx, offsets, anchor_coordinates, reference_coordinates, temperature, regularization_weight):
+        ctx.set_materialize_grads(False)
+        need = ctx.needs_input_grad[0]
+        out, grad = K.oce_loss_fwd_bwd(offsets, anchor_coordinates, reference_coordinates, temperature,
+                                       regularization_weight, want_grad=need)
+        ctx.args = (temperature, regularization_weight)
+        ctx.in_dtype = offsets.dtype
+        ctx.save_for_backward(grad, offsets, anchor_coordinates, reference_coordinates)
+        ctx.mark_non_differentiable(out)
+        return out[0], out[1], out[2], out
+
+    @staticmethod
+    def backward(ctx, g_loss, g_oce, g_reg, _g_out):
+        grad, offsets, anchors, refs = ctx.saved_tensors
+        T, w = ctx.args
+        if grad is None:
+            return None, None, None, None, None
+        if g_oce is None and g_reg is None and g_loss is not None:
+            # d loss / d offsets was produced by the forward pass; apply the upstream scalar on the
+            # device (the kernel returns immediately when it is exactly 1, as for loss.backward()).
+            if getattr(ctx, "consumed", False):  # second backward through a retained graph
+                grad = K.oce_loss_fwd_bwd(offsets, anchors, refs, T, w, True)[1]
+            ctx.consumed = True
+            total = K.scale_inplace(grad, g_loss.detach().to(torch.float32).reshape(1).contiguous())
+        else:
+            total = _combine(grad, g_loss, g_oce, g_reg,
+                             lambda ww: K.oce_loss_fwd_bwd(offsets, anchors, refs, T, ww, True)[1])
+        return total.to(ctx.in_dtype), None, None, None, None
+
+
+def oce_loss_fused(offsets, anchor_coordinates, reference_coordinates, temperature, regularizer_weight,
+                   return_raw: bool = False):
+    """Fused replacement of
+
+        ea = model.select_and_add_coordinates(offsets, anchor_coordinates)
+        er = model.select_and_add_coordinates(offsets, reference_coordinates)
+        loss, oce_loss, regularization_loss = criterion(ea, er)
+
+    (`cellulus/train.py:169-176`).  `offsets` (B, D, *S) fp32/bf16 on a CUDA device,
+    coordinates (B, P, D) int64/int32/int16 with columns (x, y[, z]).  Returns three
+    zero-dim fp32 tensors; `loss` (and the other two) are differentiable w.r.t. `offsets`.
+    With `return_raw=True` a 4th value is returned: the raw 4-float result whose last entry
+    counts pairs skipped because a coordinate was out of range (the reference would raise
+    IndexError for those; read it with `.item()` when you want that check).
+    """
+    loss, oce, reg, raw = _FusedLoss.apply(offsets, anchor_coordinates, reference_coordinates,
+                                           float(temperature), float(regularizer_weight))
+    if return_raw:
+        return loss, oce, reg, raw
+    return loss, oce, reg
+
+
+class OCELoss(nn.Module):  # type: ignore
+    def __init__(
+        self,
+        temperature: float,
+        regularization_weight: float,
+        density: float,
+        num_spatial_dims: int,
+        device: torch.device,
+    ):
+        """Same constructor as the reference (`criterions/oce_loss.py:6-43`);
+        `density`, `num_spatial_dims` and `device` are stored and unused there too."""
+        super().__init__()
+        self.temperature = temperature
+        self.regularization_weight = regularization_weight
+        self.density = density
+        self.num_spatial_dims = num_spatial_dims
+        self.device = device
+
+    @staticmethod
+    def distance_function(embedding_0, embedding_1):
+        difference = embedding_0 - embedding_1
+        return difference.norm(2, dim=-1)
+
+    def non_linearity(self, distance):
+        return 1 - (-distance.pow(2) / self.temperature).exp()
+
+    def forward(self, anchor_embedding, reference_embedding):
+        """(B, P, D) x 2 -> (loss, oce_loss, regularization_loss), all sums (:53-63)."""
+        return _PairLoss.apply(anchor_embedding, reference_embedding, float(self.temperature),
+                               float(self.regularization_weight))
+
+    def fused(self, offsets, anchor_coordinates, reference_coordinates):
+        """The whole loss slice of `train_iteration` in one kernel."""
+        return oce_loss_fused(offsets, anchor_coordinates, reference_coordinates, self.temperature,
+                              self.regularization_weight)

@@ -1,0 +1,134 @@
+// Order-preserving stream compaction skeleton shared by the detect kernels:
+// count per tile -> single-block scan of the tile counts -> emit in raster order.
+#pragma once
+#include "common.cuh"
+
+namespace cb200 {
+
+// ---------------------------------------------------------------------------
+// order-preserving compaction: count per tile -> scan -> emit
+// ---------------------------------------------------------------------------
+constexpr int CMP_THREADS = 256;
+constexpr int CMP_ITEMS = 8;
+constexpr int CMP_TILE = CMP_THREADS * CMP_ITEMS;
+
+template <class Pred>
+__global__ void __launch_bounds__(CMP_THREADS)
+compact_count_kernel(Pred pred, int64_t n, int* __restrict__ tile_counts) {
+  const int64_t base = (int64_t)blockIdx.x * CMP_TILE;
+  int c = 0;
+#pragma unroll
+  for (int j = 0; j < CMP_ITEMS; ++j) {
+    const int64_t i = base + j * CMP_THREADS + threadIdx.x;
+    c += (i < n && pred(i)) ? 1 : 0;
+  }
+  c = warp_sum(c);
+  __shared__ int s[CMP_THREADS / 32];
+  if (lane_id() == 0) s[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < CMP_THREADS / 32; ++w) t += s[w];
+    tile_counts[blockIdx.x] = t;
+  }
+}
+
+// single-block exclusive scan of the tile counts (a few hundred thousand at most)
+static __global__ void __launch_bounds__(1024)
+compact_scan_kernel(const int* __restrict__ tile_counts, int64_t n_tiles, long long* __restrict__ tile_offsets,
+                    long long* __restrict__ total) {
+  __shared__ long long s_warp[32];
+  __shared__ long long s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n_tiles; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    const long long v = i < n_tiles ? tile_counts[i] : 0;
+    long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long t = __shfl_up_sync(FULL, inc, o);
+      if (lane_id() >= o) inc += t;
+    }
+    if (lane_id() == 31) s_warp[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      long long w = s_warp[threadIdx.x];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(FULL, w, o);
+        if (lane_id() >= o) w += t;
+      }
+      s_warp[threadIdx.x] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const long long warp_off = (threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0;
+    const long long carry = s_carry;
+    if (i < n_tiles) tile_offsets[i] = carry + warp_off + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + warp_off + inc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = s_carry;
+}
+
+template <class Pred, class Emit>
+__global__ void __launch_bounds__(CMP_THREADS)
+compact_emit_kernel(Pred pred, Emit emit, int64_t n, const long long* __restrict__ tile_offsets, int64_t capacity) {
+  const int64_t base = (int64_t)blockIdx.x * CMP_TILE;
+  __shared__ int s_warp[CMP_THREADS / 32];
+  long long running = tile_offsets[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+#pragma unroll 1
+  for (int j = 0; j < CMP_ITEMS; ++j) {
+    const int64_t i = base + j * CMP_THREADS + threadIdx.x;
+    const bool p = (i < n) && pred(i);
+    const unsigned ballot = __ballot_sync(FULL, p);
+    if (lane == 0) s_warp[warp] = __popc(ballot);
+    __syncthreads();
+    int before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < CMP_THREADS / 32; ++w) {
+      const int c = s_warp[w];
+      before += (w < warp) ? c : 0;
+      all += c;
+    }
+    if (p) {
+      const long long dst = running + before + __popc(ballot & ((1u << lane) - 1u));
+      if (dst < capacity) emit(i, dst);
+    }
+    running += all;
+    __syncthreads();
+  }
+}
+
+struct CompactWorkspace {  // layout inside the caller's buffer
+  static int64_t bytes(int64_t n) {
+    const int64_t tiles = (n + CMP_TILE - 1) / CMP_TILE;
+    return tiles * (int64_t)(sizeof(long long) + sizeof(int)) + 64;
+  }
+};
+
+template <class Pred, class Emit>
+static int run_compaction(Pred pred, Emit emit, int64_t n, int64_t capacity, long long* n_out, void* workspace,
+                          cudaStream_t st) {
+  const int64_t tiles = (n + CMP_TILE - 1) / CMP_TILE;
+  if (tiles == 0) {
+    CB200_CUDA_TRY(cudaMemsetAsync(n_out, 0, sizeof(long long), st));
+    return CB200_OK;
+  }
+  if (tiles > INT32_MAX) return CB200_EUNSUPPORTED;
+  long long* tile_offsets = static_cast<long long*>(workspace);
+  int* tile_counts = reinterpret_cast<int*>(tile_offsets + tiles);
+  compact_count_kernel<Pred><<<(int)tiles, CMP_THREADS, 0, st>>>(pred, n, tile_counts);
+  CB200_LAUNCH_CHECK();
+  compact_scan_kernel<<<1, 1024, 0, st>>>(tile_counts, tiles, tile_offsets, n_out);
+  CB200_LAUNCH_CHECK();
+  compact_emit_kernel<Pred, Emit><<<(int)tiles, CMP_THREADS, 0, st>>>(pred, emit, n, tile_offsets, capacity);
+  CB200_LAUNCH_CHECK();
+  return CB200_OK;
+}
+
+
+}  // namespace cb200

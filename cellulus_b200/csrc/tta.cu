@@ -1,0 +1,185 @@
+// Test-time-augmentation aggregate for sm_100a (models/unet.py:90-98).
+//
+// stack (T, C, n) fp32 -> out (C+1, n): per-channel mean over the T passes and
+// the per-channel POPULATION std summed over channels.  Pure streaming: every
+// input byte is read once with 16-byte no-allocate loads, T/UNROLL batches of
+// independent requests in flight per thread; the statistics are carried in
+// registers with Welford's update (the same recurrence torch.std_mean uses),
+// so nothing but the (C+1, n) result is written.
+#include "common.cuh"
+
+namespace cb200 {
+
+constexpr int TTA_THREADS = 256;
+constexpr int TTA_MAXC = 4;
+
+struct Welford4 {
+  float4 mean, m2;
+  __device__ __forceinline__ void init() {
+    mean = make_float4(0.f, 0.f, 0.f, 0.f);
+    m2 = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __device__ __forceinline__ void push(const float4 x, const float inv_count) {
+#define CB200_W(f)                          \
+  {                                         \
+    const float d = x.f - mean.f;           \
+    mean.f = fmaf(d, inv_count, mean.f);    \
+    m2.f = fmaf(d, x.f - mean.f, m2.f);     \
+  }
+    CB200_W(x) CB200_W(y) CB200_W(z) CB200_W(w)
+#undef CB200_W
+  }
+};
+
+// One thread owns 4 consecutive pixels of every channel.
+template <int C>
+__global__ void __launch_bounds__(TTA_THREADS)
+tta_aggregate_kernel(const float* __restrict__ stack, int T, int64_t n, int64_t n4, float* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const float inv_T = 1.0f / (float)T;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    Welford4 w[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) w[c].init();
+    constexpr int U = 8 / C > 0 ? 8 / C : 1;  // passes fetched per batch: ~8 independent 16-byte loads
+    int t = 0;
+    for (; t + U <= T; t += U) {
+      float4 v[U][C];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[u][c] = ld_stream_f4(stack + ((int64_t)(t + u) * C + c) * n + i * 4);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float inv = 1.0f / (float)(t + u + 1);
+#pragma unroll
+        for (int c = 0; c < C; ++c) w[c].push(v[u][c], inv);
+      }
+    }
+    for (; t < T; ++t) {
+      const float inv = 1.0f / (float)(t + 1);
+#pragma unroll
+      for (int c = 0; c < C; ++c) w[c].push(ld_stream_f4(stack + ((int64_t)t * C + c) * n + i * 4), inv);
+    }
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      st_stream_f4(out + (int64_t)c * n + i * 4, w[c].mean);
+      s.x += sqrtf(w[c].m2.x * inv_T);
+      s.y += sqrtf(w[c].m2.y * inv_T);
+      s.z += sqrtf(w[c].m2.z * inv_T);
+      s.w += sqrtf(w[c].m2.w * inv_T);
+    }
+    st_stream_f4(out + (int64_t)C * n + i * 4, s);
+  }
+  // scalar tail (n not a multiple of 4, or unaligned planes): handled by the generic kernel
+}
+
+// Generic scalar fallback: any C <= TTA_MAXC, any n / alignment; `first` = first pixel handled.
+__global__ void __launch_bounds__(TTA_THREADS)
+tta_aggregate_scalar_kernel(const float* __restrict__ stack, int T, int C, int64_t n, int64_t first,
+                            float* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const float inv_T = 1.0f / (float)T;
+  for (int64_t i = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) {
+      float mean = 0.f, m2 = 0.f;
+      for (int t = 0; t < T; ++t) {
+        const float x = ld_stream_f(stack + ((int64_t)t * C + c) * n + i);
+        const float d = x - mean;
+        mean = fmaf(d, 1.0f / (float)(t + 1), mean);
+        m2 = fmaf(d, x - mean, m2);
+      }
+      out[(int64_t)c * n + i] = mean;
+      s += sqrtf(m2 * inv_T);
+    }
+    out[(int64_t)C * n + i] = s;
+  }
+}
+
+// Streaming form: state = [mean (C,n) | M2 (C,n)], one prediction folded in per call.
+__global__ void __launch_bounds__(TTA_THREADS)
+tta_accumulate_kernel(float* __restrict__ state, const float* __restrict__ pred, int t, int64_t cn) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const float inv = 1.0f / (float)(t + 1);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cn; i += stride) {
+    const float x = ld_stream_f(pred + i);
+    float mean = t == 0 ? 0.f : state[i];
+    float m2 = t == 0 ? 0.f : state[cn + i];
+    const float d = x - mean;
+    mean = fmaf(d, inv, mean);
+    m2 = fmaf(d, x - mean, m2);
+    state[i] = mean;
+    state[cn + i] = m2;
+  }
+}
+
+__global__ void __launch_bounds__(TTA_THREADS)
+tta_finalize_kernel(const float* __restrict__ state, int T, int C, int64_t n, float* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const float inv_T = 1.0f / (float)T;
+  const int64_t cn = (int64_t)C * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) {
+      out[(int64_t)c * n + i] = state[(int64_t)c * n + i];
+      s += sqrtf(state[cn + (int64_t)c * n + i] * inv_T);
+    }
+    out[cn + i] = s;
+  }
+}
+
+}  // namespace cb200
+
+using namespace cb200;
+
+extern "C" {
+
+int cb200_tta_aggregate(const float* stack, int num_passes, int channels, int64_t n, float* out, void* stream) {
+  if (!stack || !out || num_passes <= 0 || channels <= 0 || channels > TTA_MAXC || n < 0) return CB200_EINVAL;
+  if (n == 0) return CB200_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec_ok = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(stack) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  int64_t first_scalar = 0;
+  if (vec_ok) {
+    const int64_t n4 = n / 4;
+    const int blocks = grid_for(n4, TTA_THREADS, 1, 16);
+    switch (channels) {
+      case 1: tta_aggregate_kernel<1><<<blocks, TTA_THREADS, 0, st>>>(stack, num_passes, n, n4, out); break;
+      case 2: tta_aggregate_kernel<2><<<blocks, TTA_THREADS, 0, st>>>(stack, num_passes, n, n4, out); break;
+      case 3: tta_aggregate_kernel<3><<<blocks, TTA_THREADS, 0, st>>>(stack, num_passes, n, n4, out); break;
+      default: tta_aggregate_kernel<4><<<blocks, TTA_THREADS, 0, st>>>(stack, num_passes, n, n4, out); break;
+    }
+    CB200_LAUNCH_CHECK();
+    first_scalar = n;
+  }
+  if (first_scalar < n) {
+    tta_aggregate_scalar_kernel<<<grid_for(n - first_scalar, TTA_THREADS, 1, 16), TTA_THREADS, 0, st>>>(
+        stack, num_passes, channels, n, first_scalar, out);
+    CB200_LAUNCH_CHECK();
+  }
+  return CB200_OK;
+}
+
+int cb200_tta_accumulate(float* state, const float* prediction, int t, int channels, int64_t n, void* stream) {
+  if (!state || !prediction || t < 0 || channels <= 0 || n < 0) return CB200_EINVAL;
+  if (n == 0) return CB200_OK;
+  const int64_t cn = (int64_t)channels * n;
+  tta_accumulate_kernel<<<grid_for(cn, TTA_THREADS, 2, 16), TTA_THREADS, 0, (cudaStream_t)stream>>>(state, prediction,
+                                                                                                  t, cn);
+  CB200_LAUNCH_CHECK();
+  return CB200_OK;
+}
+
+int cb200_tta_finalize(const float* state, int num_passes, int channels, int64_t n, float* out, void* stream) {
+  if (!state || !out || num_passes <= 0 || channels <= 0 || n < 0) return CB200_EINVAL;
+  if (n == 0) return CB200_OK;
+  tta_finalize_kernel<<<grid_for(n, TTA_THREADS, 2, 16), TTA_THREADS, 0, (cudaStream_t)stream>>>(state, num_passes,
+                                                                                               channels, n, out);
+  CB200_LAUNCH_CHECK();
+  return CB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,456 @@
+"""Thin torch-tensor wrappers over the C ABI (device pointers + current stream).
+
+torch is used for device memory and streams only; every computation below is
+a call into `libcellulus_b200.so`.  Inputs must live on a CUDA device: there
+is no CPU fallback (a CPU tensor raises).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import Grid, check, spatial_array
+
+_DTYPE_CODE = {
+    torch.float32: _cabi.F32,
+    torch.bfloat16: _cabi.BF16,
+    torch.float64: _cabi.F64,
+    torch.int64: _cabi.I64,
+    torch.int32: _cabi.I32,
+    torch.int16: _cabi.I16,
+    torch.uint8: _cabi.U8,
+    torch.uint16: _cabi.U16,
+}
+
+# count of kernel-launching C-ABI calls made by this process (bench.py reports it)
+launch_counter = {"calls": 0}
+
+
+def _lib():
+    return _cabi.load()
+
+
+def _stream(t: torch.Tensor) -> C.c_void_p:
+    # the C ABI launches on the calling thread's current device, like any CUDA runtime call
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(
+            f"tensor lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+            "wrap the call in `with torch.cuda.device(tensor.device):` (one process per GPU sets it once)")
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise RuntimeError(
+                "cellulus_b200 kernels run on a CUDA device only (no CPU fallback); got "
+                f"{type(t).__name__} on {getattr(t, 'device', None)}"
+            )
+
+
+def _code(t: torch.Tensor, allowed) -> int:
+    if t.dtype not in allowed:
+        raise TypeError(f"unsupported dtype {t.dtype}; expected one of {sorted(str(a) for a in allowed)}")
+    return _DTYPE_CODE[t.dtype]
+
+
+_workspaces = {}
+
+
+def _zero_workspace(kind: str, nbytes: int, device: torch.device) -> torch.Tensor:
+    """Small persistent zero-initialised scratch, one per (kind, device, stream)."""
+    key = (kind, device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 64), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+# --------------------------------------------------------------------------- loss slice
+_COORD_DTYPES = (torch.int64, torch.int32, torch.int16)
+_OFFSET_DTYPES = (torch.float32, torch.bfloat16)
+
+
+def _check_loss_inputs(offsets, coords_list):
+    _require_cuda(offsets, *coords_list)
+    if offsets.ndim not in (4, 5):
+        raise ValueError("offsets must be (B, C, H, W) or (B, C, D, H, W)")
+    B, Cc = offsets.shape[:2]
+    D = offsets.ndim - 2
+    if Cc != D:
+        raise ValueError(f"offsets has {Cc} channels but {D} spatial dims; the embedding is one offset per dim")
+    for c in coords_list:
+        if c.ndim != 3 or c.shape[0] != B or c.shape[2] != D:
+            raise ValueError(f"coordinates must be (B={B}, P, {D}); got {tuple(c.shape)}")
+        if c.shape != coords_list[0].shape or c.dtype != coords_list[0].dtype:
+            raise ValueError("anchor and reference coordinates must have identical shape and dtype")
+    return B, D
+
+
+def oce_loss_fwd_bwd(offsets, anchors, refs, temperature, regularization_weight, want_grad=True):
+    """`cb200_oce_loss_fwd_bwd`: returns `(out4, grad)`; out4 = [loss, oce, reg, n_bad] (fp32, device)."""
+    B, D = _check_loss_inputs(offsets, [anchors, refs])
+    offsets = offsets.contiguous()
+    anchors = anchors.contiguous()
+    refs = refs.contiguous()
+    odt = _code(offsets, _OFFSET_DTYPES)
+    cdt = _code(anchors, _COORD_DTYPES)
+    out = torch.empty(4, dtype=torch.float32, device=offsets.device)
+    grad = torch.empty(offsets.shape, dtype=torch.float32, device=offsets.device) if want_grad else None
+    ws = _zero_workspace("loss", _lib().cb200_oce_loss_workspace_bytes(), offsets.device)
+    rc = _lib().cb200_oce_loss_fwd_bwd(
+        _ptr(offsets), odt, _ptr(anchors), _ptr(refs), cdt, B, D, spatial_array(offsets.shape[2:]),
+        anchors.shape[1], float(temperature), float(regularization_weight), _ptr(grad), _ptr(out), _ptr(ws),
+        _stream(offsets))
+    check(rc, "cb200_oce_loss_fwd_bwd")
+    launch_counter["calls"] += 1
+    return out, grad
+
+
+def scale_inplace(grad: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    _require_cuda(grad, scale)
+    assert grad.dtype == torch.float32 and grad.is_contiguous() and scale.dtype == torch.float32
+    check(_lib().cb200_scale_inplace(_ptr(grad), grad.numel(), _ptr(scale), _stream(grad)), "cb200_scale_inplace")
+    launch_counter["calls"] += 1
+    return grad
+
+
+def gather_add_coords(offsets, coords):
+    B, D = _check_loss_inputs(offsets, [coords])
+    offsets = offsets.contiguous()
+    coords = coords.contiguous()
+    out = torch.empty((B, coords.shape[1], D), dtype=torch.float32, device=offsets.device)
+    rc = _lib().cb200_gather_add_coords(
+        _ptr(offsets), _code(offsets, _OFFSET_DTYPES), _ptr(coords), _code(coords, _COORD_DTYPES), B, D,
+        spatial_array(offsets.shape[2:]), coords.shape[1], _ptr(out), _stream(offsets))
+    check(rc, "cb200_gather_add_coords")
+    launch_counter["calls"] += 1
+    return out
+
+
+def scatter_add_coords(grad_out, coords, offsets_shape):
+    _require_cuda(grad_out, coords)
+    grad_out = grad_out.contiguous().float()
+    coords = coords.contiguous()
+    B, D = offsets_shape[0], len(offsets_shape) - 2
+    grad = torch.empty(tuple(offsets_shape), dtype=torch.float32, device=grad_out.device)
+    rc = _lib().cb200_scatter_add_coords(
+        _ptr(grad_out), _ptr(coords), _code(coords, _COORD_DTYPES), B, D, spatial_array(offsets_shape[2:]),
+        coords.shape[1], _ptr(grad), _stream(grad_out))
+    check(rc, "cb200_scatter_add_coords")
+    launch_counter["calls"] += 1
+    return grad
+
+
+def oce_pair_loss(ea, er, temperature, regularization_weight, want_grad=True):
+    _require_cuda(ea, er)
+    if ea.shape != er.shape or ea.shape[-1] not in (2, 3):
+        raise ValueError("embeddings must both be (..., D) with D in {2, 3}")
+    ea = ea.contiguous().float()
+    er = er.contiguous().float()
+    n = ea.numel() // ea.shape[-1]
+    out = torch.empty(4, dtype=torch.float32, device=ea.device)
+    grad = torch.empty_like(ea) if want_grad else None
+    ws = _zero_workspace("loss", _lib().cb200_oce_loss_workspace_bytes(), ea.device)
+    rc = _lib().cb200_oce_pair_loss(_ptr(ea), _ptr(er), n, ea.shape[-1], float(temperature),
+                                    float(regularization_weight), _ptr(grad), _ptr(out), _ptr(ws), _stream(ea))
+    check(rc, "cb200_oce_pair_loss")
+    launch_counter["calls"] += 1
+    return out, grad
+
+
+def sample_pairs(batch, extent_xyz, kappa, num_anchors, num_references, seed, sequence=0,
+                 dtype=torch.int64, device="cuda"):
+    """`cb200_sample_pairs`: (anchors, refs), each (B, num_anchors*num_references, D)."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("cellulus_b200 kernels run on a CUDA device only (no CPU fallback)")
+    D = len(extent_xyz)
+    P = int(num_anchors) * int(num_references)
+    anchors = torch.empty((batch, P, D), dtype=dtype, device=device)
+    refs = torch.empty_like(anchors)
+    with torch.cuda.device(device):
+        rc = _lib().cb200_sample_pairs(
+            _ptr(anchors), _ptr(refs), _code(anchors, _COORD_DTYPES), batch, D, spatial_array(extent_xyz),
+            float(kappa), int(num_anchors), int(num_references), int(seed) & (2**64 - 1), int(sequence),
+            _stream(anchors))
+    check(rc, "cb200_sample_pairs")
+    launch_counter["calls"] += 1
+    return anchors, refs
+
+
+# --------------------------------------------------------------------------- TTA
+def tta_aggregate(stack: torch.Tensor) -> torch.Tensor:
+    """(T, C, *S) fp32 -> (C+1, *S) fp32 (`models/unet.py:90-98`)."""
+    _require_cuda(stack)
+    if stack.dtype != torch.float32 or stack.ndim < 3:
+        raise TypeError("stack must be fp32 (T, C, *S)")
+    stack = stack.contiguous()
+    T, Cc = stack.shape[:2]
+    spatial = stack.shape[2:]
+    n = int(np.prod(spatial))
+    out = torch.empty((Cc + 1, *spatial), dtype=torch.float32, device=stack.device)
+    check(_lib().cb200_tta_aggregate(_ptr(stack), T, Cc, n, _ptr(out), _stream(stack)), "cb200_tta_aggregate")
+    launch_counter["calls"] += 1
+    return out
+
+
+def tta_accumulate(state, prediction, t):
+    _require_cuda(state, prediction)
+    prediction = prediction.contiguous()
+    Cc = prediction.shape[0]
+    n = prediction.numel() // Cc
+    check(_lib().cb200_tta_accumulate(_ptr(state), _ptr(prediction), int(t), Cc, n, _stream(state)),
+          "cb200_tta_accumulate")
+    launch_counter["calls"] += 1
+
+
+def tta_finalize(state, num_passes, channels, spatial):
+    n = int(np.prod(spatial))
+    out = torch.empty((channels + 1, *spatial), dtype=torch.float32, device=state.device)
+    check(_lib().cb200_tta_finalize(_ptr(state), int(num_passes), channels, n, _ptr(out), _stream(state)),
+          "cb200_tta_finalize")
+    launch_counter["calls"] += 1
+    return out
+
+
+# --------------------------------------------------------------------------- detect preamble
+_FLOAT_DTYPES = (torch.float32, torch.float64)
+
+
+def minmax(x: torch.Tensor) -> torch.Tensor:
+    """{min, max} of x as a 2-element float64 device tensor."""
+    _require_cuda(x)
+    x = x.contiguous()
+    out = torch.empty(2, dtype=torch.float64, device=x.device)
+    ws = _zero_workspace("reduce", _lib().cb200_reduce_workspace_bytes(), x.device)
+    check(_lib().cb200_minmax(_ptr(x), _code(x, _FLOAT_DTYPES), x.numel(), _ptr(out), _ptr(ws), _stream(x)),
+          "cb200_minmax")
+    launch_counter["calls"] += 1
+    return out
+
+
+def histogram(x: torch.Tensor, edges: torch.Tensor) -> torch.Tensor:
+    """np.histogram(x, len(edges)-1, range=(edges[0], edges[-1])) counts, uint64-exact (returned as int64)."""
+    _require_cuda(x, edges)
+    x = x.contiguous()
+    assert edges.dtype == torch.float64 and edges.is_contiguous()
+    nbins = edges.numel() - 1
+    counts = torch.zeros(nbins, dtype=torch.int64, device=x.device)
+    check(_lib().cb200_histogram(_ptr(x), _code(x, _FLOAT_DTYPES), x.numel(), _ptr(edges), nbins, _ptr(counts),
+                                 _stream(x)), "cb200_histogram")
+    launch_counter["calls"] += 1
+    return counts
+
+
+def fg_compact(emb: torch.Tensor, threshold: float, capacity: Optional[int] = None, mask_dtype=None):
+    """Foreground compaction.  Returns `(points (D, capacity) f64 SoA, pix_index (capacity) i32,
+    n_fg (python int), mask or None)`.  One host sync (the count)."""
+    _require_cuda(emb)
+    emb = emb.contiguous()
+    D = emb.shape[0] - 1
+    spatial = emb.shape[1:]
+    if len(spatial) != D or D not in (2, 3):
+        raise ValueError("emb must be (D+1, *S) with D spatial dims, D in {2, 3}")
+    n_pix = int(np.prod(spatial))
+    dev = emb.device
+    ws = torch.empty(_lib().cb200_compact_workspace_bytes(n_pix), dtype=torch.uint8, device=dev)
+    n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+    mask = None
+    mcode = 0
+    if mask_dtype is not None:
+        mask = torch.empty(spatial, dtype=mask_dtype, device=dev)
+        mcode = _code(mask, (torch.uint8, torch.uint16))
+
+    def run(cap):
+        cap_even = max(2, (cap + 1) & ~1)  # even stride: the brute-force kernel moves 16-byte granules
+        pts = torch.empty((D, cap_even), dtype=torch.float64, device=dev)
+        pix = torch.empty(cap_even, dtype=torch.int32, device=dev)
+        rc = _lib().cb200_fg_compact(_ptr(emb), _code(emb, _FLOAT_DTYPES), D, spatial_array(spatial),
+                                     float(threshold), _ptr(pts), _ptr(pix), cap_even, _ptr(n_out), _ptr(mask), mcode,
+                                     _ptr(ws), _stream(emb))
+        check(rc, "cb200_fg_compact")
+        launch_counter["calls"] += 1
+        return pts, pix, int(n_out.item())
+
+    cap = n_pix if capacity is None else int(capacity)
+    pts, pix, n = run(cap)
+    if n > pts.shape[1]:
+        pts, pix, n = run(n)
+    return pts, pix, n, mask
+
+
+def select_points(points: torch.Tensor, n: int, flags: torch.Tensor):
+    """Rows of an SoA point set where flags != 0 (order kept).  Returns `(subset (D, cap) SoA, count)`."""
+    _require_cuda(points, flags)
+    D = points.shape[0]
+    assert flags.dtype == torch.uint8 and flags.numel() >= n
+    dev = points.device
+    cap = max(2, (n + 1) & ~1)
+    dst = torch.empty((D, cap), dtype=torch.float64, device=dev)
+    n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = torch.empty(_lib().cb200_compact_workspace_bytes(max(n, 1)), dtype=torch.uint8, device=dev)
+    rc = _lib().cb200_select_points(_ptr(points), n, points.stride(0), D, _ptr(flags), _ptr(dst), cap, _ptr(n_out),
+                                    _ptr(ws), _stream(points))
+    check(rc, "cb200_select_points")
+    launch_counter["calls"] += 1
+    return dst, int(n_out.item())
+
+
+def bernoulli_flags(n: int, p: float, seed: int, device) -> torch.Tensor:
+    flags = torch.empty(max(n, 1), dtype=torch.uint8, device=device)
+    check(_lib().cb200_bernoulli_flags(_ptr(flags), n, float(p), int(seed) & (2**64 - 1), _stream(flags)),
+          "cb200_bernoulli_flags")
+    launch_counter["calls"] += 1
+    return flags
+
+
+# --------------------------------------------------------------------------- mean-shift
+def plan_grid(lo, hi, bandwidth: float, max_cells: int = 1 << 26) -> Grid:
+    D = len(lo)
+    g = Grid()
+    lo_a = (C.c_double * D)(*[float(v) for v in lo])
+    hi_a = (C.c_double * D)(*[float(v) for v in hi])
+    check(_lib().cb200_grid_plan(lo_a, hi_a, D, float(bandwidth), int(max_cells), C.byref(g)), "cb200_grid_plan")
+    return g
+
+
+def bounding_box(points: torch.Tensor, n: int):
+    """Per-column (min, max) of an SoA point set; one host sync."""
+    D = points.shape[0]
+    mm = torch.stack([minmax(points[k, :n]) for k in range(D)])  # (D, 2)
+    mm = mm.cpu().numpy()
+    return mm[:, 0], mm[:, 1]
+
+
+def grid_build(points: torch.Tensor, n: int, grid: Grid, want_order: bool = False):
+    """Sort an SoA point set by grid cell.  Returns `(sorted SoA (D, cap), cell_start (n_cells+1) i32, order|None)`."""
+    _require_cuda(points)
+    D = points.shape[0]
+    dev = points.device
+    cap = max(2, (n + 1) & ~1)
+    sorted_pts = torch.empty((D, cap), dtype=torch.float64, device=dev)
+    cell_start = torch.empty(grid.n_cells + 1, dtype=torch.int32, device=dev)
+    order = torch.empty(max(n, 1), dtype=torch.int32, device=dev) if want_order else None
+    nbytes = _lib().cb200_grid_build_workspace_bytes(n, grid.n_cells)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    rc = _lib().cb200_grid_build(_ptr(points), n, points.stride(0), C.byref(grid), _ptr(sorted_pts), cap, _ptr(order),
+                                 _ptr(cell_start), _ptr(ws), nbytes, _stream(points))
+    check(rc, "cb200_grid_build")
+    launch_counter["calls"] += 1
+    return sorted_pts, cell_start, order
+
+
+def ms_grid_modes(sorted_pts, n, grid, cell_start, seeds_soa, n_seeds, bandwidth, max_iter=300):
+    """Climb every seed to convergence (grid-hash form).  `seeds_soa` (D, cap) is updated IN PLACE to the modes.
+    Returns `(counts, iters)` int32 device tensors."""
+    dev = sorted_pts.device
+    counts = torch.zeros(max(n_seeds, 1), dtype=torch.int32, device=dev)
+    iters = torch.zeros(max(n_seeds, 1), dtype=torch.int32, device=dev)
+    work = torch.zeros(1, dtype=torch.int32, device=dev)
+    rc = _lib().cb200_ms_grid_modes(_ptr(sorted_pts), n, sorted_pts.stride(0), C.byref(grid), _ptr(cell_start),
+                                    _ptr(seeds_soa), seeds_soa.stride(0), n_seeds, float(bandwidth), int(max_iter),
+                                    _ptr(counts), _ptr(iters), _ptr(work), _stream(sorted_pts))
+    check(rc, "cb200_ms_grid_modes")
+    launch_counter["calls"] += 1
+    return counts, iters
+
+
+def ms_brute_modes(points, n, seeds_soa, n_seeds, bandwidth, max_iter=300):
+    """Climb every seed to convergence (brute-force n-body form); one accumulate + one update launch per
+    iteration over the still-active seeds.  `seeds_soa` is updated in place.  Returns `(counts, iters)`."""
+    dev = points.device
+    D = points.shape[0]
+    counts = torch.zeros(max(n_seeds, 1), dtype=torch.int32, device=dev)
+    iters = torch.zeros(max(n_seeds, 1), dtype=torch.int32, device=dev)
+    if n_seeds == 0 or n == 0:
+        return counts, iters
+    active = torch.arange(n_seeds, dtype=torch.int32, device=dev)
+    nxt = torch.empty_like(active)
+    n_next = torch.zeros(1, dtype=torch.int32, device=dev)
+    n_active = n_seeds
+    partial = torch.empty(_lib().cb200_ms_brute_partial_bytes(n_active, n, D), dtype=torch.uint8, device=dev)
+    st = _stream(points)
+    for _ in range(max_iter + 2):
+        if n_active == 0:
+            break
+        rc = _lib().cb200_ms_brute_accumulate(_ptr(points), n, points.stride(0), D, _ptr(seeds_soa),
+                                              seeds_soa.stride(0), _ptr(active), n_active, float(bandwidth),
+                                              _ptr(partial), st)
+        check(rc, "cb200_ms_brute_accumulate")
+        n_next.zero_()
+        rc = _lib().cb200_ms_update(_ptr(seeds_soa), seeds_soa.stride(0), D, _ptr(counts), _ptr(iters), _ptr(active),
+                                    n_active, n, _ptr(partial), float(bandwidth), int(max_iter), _ptr(nxt),
+                                    _ptr(n_next), st)
+        check(rc, "cb200_ms_update")
+        launch_counter["calls"] += 2
+        n_active = int(n_next.item())
+        active, nxt = nxt, active
+    return counts, iters
+
+
+def nms_centres(modes_soa, counts, n_seeds, bandwidth, grid: Grid):
+    """sklearn:511-547 on the device.  Returns `(centres (D, n_seeds) SoA in priority order, K)`."""
+    dev = modes_soa.device
+    D = modes_soa.shape[0]
+    centres = torch.empty((D, n_seeds), dtype=torch.float64, device=dev)
+    out2 = torch.zeros(2, dtype=torch.int32, device=dev)
+    nbytes = _lib().cb200_nms_workspace_bytes(n_seeds, D, grid.n_cells)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    rc = _lib().cb200_nms_centres(_ptr(modes_soa), modes_soa.stride(0), D, _ptr(counts), n_seeds, float(bandwidth),
+                                  C.byref(grid), _ptr(centres), _ptr(out2), _ptr(ws), nbytes, _stream(modes_soa))
+    check(rc, "cb200_nms_centres")
+    launch_counter["calls"] += 1
+    k, undecided = (int(v) for v in out2.tolist())
+    if undecided:
+        raise _cabi.CellulusB200Error(
+            f"centre suppression did not reach its fix-point ({undecided} undecided after the built-in rounds)")
+    return centres, k
+
+
+def assign_labels(points, n, centres, k, pix_index, labels_out):
+    """labels_out[pix_index[i]] = 1 + nearest centre (ties -> lowest index); labels_out int32 or uint16."""
+    rc = _lib().cb200_assign_labels(_ptr(points), n, points.stride(0), points.shape[0], _ptr(centres),
+                                    centres.stride(0), int(k), _ptr(pix_index), _ptr(labels_out),
+                                    _code(labels_out, (torch.int32, torch.uint16)), _stream(points))
+    check(rc, "cb200_assign_labels")
+    launch_counter["calls"] += 1
+    return labels_out
+
+
+# --------------------------------------------------------------------------- size filter
+def label_components(seg: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    _require_cuda(seg)
+    seg = seg.contiguous().to(torch.int32)
+    labels = torch.empty_like(seg)
+    n_labels = torch.zeros(1, dtype=torch.int32, device=seg.device)
+    ws = torch.empty(_lib().cb200_cc_workspace_bytes(seg.numel()), dtype=torch.uint8, device=seg.device)
+    rc = _lib().cb200_label_components(_ptr(seg), seg.ndim, spatial_array(seg.shape), _ptr(labels), _ptr(n_labels),
+                                       _ptr(ws), _stream(seg))
+    check(rc, "cb200_label_components")
+    launch_counter["calls"] += 1
+    return labels, n_labels
+
+
+def size_filter_(seg: torch.Tensor, min_size: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """In-place on `seg` (int32, contiguous); returns `(relabelled, n_labels)`."""
+    _require_cuda(seg)
+    assert seg.dtype == torch.int32 and seg.is_contiguous()
+    labels = torch.empty_like(seg)
+    n_labels = torch.zeros(1, dtype=torch.int32, device=seg.device)
+    ws = torch.empty(_lib().cb200_cc_workspace_bytes(seg.numel()), dtype=torch.uint8, device=seg.device)
+    rc = _lib().cb200_size_filter(_ptr(seg), seg.ndim, spatial_array(seg.shape), int(min_size), _ptr(labels),
+                                  _ptr(n_labels), _ptr(ws), _stream(seg))
+    check(rc, "cb200_size_filter")
+    launch_counter["calls"] += 1
+    return labels, n_labels

@@ -1,0 +1,274 @@
+/*
+ * cellulus_b200 -- C ABI of the B200-native embedding-space hot path.
+ *
+ * One shared object (cellulus_b200/libcellulus_b200.so), plain C symbols, raw
+ * DEVICE pointers + explicit sizes + a cudaStream_t passed as void*.  No torch
+ * types.  The reference (funkelab/cellulus) is pure Python and has no FFI of
+ * its own, so each entry point cites the reference function it replaces
+ * (paths relative to the reference root; "sklearn:" = scikit-learn 1.9.0
+ * sklearn/cluster/_mean_shift.py, to which the reference delegates).
+ * INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - return value: 0 = ok; CB200_EINVAL (-1) bad argument; CB200_EUNSUPPORTED
+ *     (-2) unsupported dtype/dims; otherwise a positive cudaError_t.
+ *   - nothing here synchronises the stream or allocates device memory; every
+ *     scratch buffer is passed in (sizes from the *_workspace_bytes queries).
+ *   - re-entrant across streams as long as workspaces are not shared.
+ *   - spatial shapes are passed in tensor-axis order ([z,] y, x); coordinate /
+ *     channel columns are in the reference's (x, y[, z]) order: column 0
+ *     indexes the LAST tensor axis (models/unet.py:114-118).
+ */
+#ifndef CELLULUS_B200_H
+#define CELLULUS_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define CB200_API __attribute__((visibility("default")))
+#else
+#define CB200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB200_OK 0
+#define CB200_EINVAL (-1)
+#define CB200_EUNSUPPORTED (-2)
+
+/* element types */
+#define CB200_F32 0
+#define CB200_BF16 1
+#define CB200_F64 2
+#define CB200_I64 3
+#define CB200_I32 4
+#define CB200_I16 5
+#define CB200_U8 6
+#define CB200_U16 7
+
+/* library / build information: returns the sm arch the kernels were built for (100) */
+CB200_API int cb200_version(int* major, int* minor, int* sm_arch);
+/* last CUDA error string for a positive return code */
+CB200_API const char* cb200_error_string(int code);
+
+/* ===================================================================== *
+ *  Loss slice (training)                                                *
+ * ===================================================================== */
+
+/* bytes of scratch needed by cb200_oce_loss_fwd_bwd (accumulators + ticket) */
+CB200_API int64_t cb200_oce_loss_workspace_bytes(void);
+
+/*
+ * Fused neighbour gather + OCE loss forward + backward in ONE pass.
+ * Replaces, in cellulus/train.py:169-178,
+ *     select_and_add_coordinates(offsets, anchors)   models/unet.py:108-124
+ *     select_and_add_coordinates(offsets, refs)      models/unet.py:108-124
+ *     OCELoss.forward(ea, er)                        criterions/oce_loss.py:53-63
+ *     loss.backward()  (gather backward = scatter-add onto the anchor pixel)
+ *
+ *  offsets      (B, D, *spatial) contiguous, CB200_F32 or CB200_BF16
+ *  anchors/refs (B, P, D) contiguous, CB200_I64 (as the reference delivers
+ *               them), CB200_I32 or CB200_I16; columns (x, y[, z])
+ *  grad         (B, D, *spatial) fp32, OVERWRITTEN with d loss / d offsets
+ *               (zero-filled by this call, then accumulated); may be NULL to
+ *               run the forward only
+ *  out          4 floats: loss, oce_loss, regularization_loss, number of
+ *               pairs skipped because a coordinate was out of range
+ *  workspace    cb200_oce_loss_workspace_bytes() bytes, zero-initialised ONCE
+ *               by the caller (the kernel leaves it zeroed again)
+ */
+CB200_API int cb200_oce_loss_fwd_bwd(const void* offsets, int offsets_dtype,
+                           const void* anchors, const void* refs, int coord_dtype,
+                           int batch, int num_dims, const int64_t* spatial /* host, num_dims */,
+                           int64_t pairs_per_sample,
+                           float temperature, float regularization_weight,
+                           float* grad, float* out, void* workspace, void* stream);
+
+/* grad *= *scale (device scalar); returns immediately on the device when *scale == 1.
+ * Used by the autograd shim to apply the upstream gradient of `loss`. */
+CB200_API int cb200_scale_inplace(float* grad, int64_t n, const float* scale, void* stream);
+
+/*
+ * Unfused drop-ins, for callers that keep the reference's three-call shape.
+ *
+ * cb200_gather_add_coords: models/unet.py:108-124 forward.
+ *   out (B, P, D) fp32 = offsets[b, :, coord] + coord
+ * cb200_scatter_add_coords: its backward; grad_offsets (B, D, *spatial) fp32
+ *   is zero-filled then accumulated from grad_out (B, P, D).
+ */
+CB200_API int cb200_gather_add_coords(const void* offsets, int offsets_dtype, const void* coords, int coord_dtype,
+                            int batch, int num_dims, const int64_t* spatial, int64_t pairs_per_sample,
+                            float* out, void* stream);
+CB200_API int cb200_scatter_add_coords(const float* grad_out, const void* coords, int coord_dtype,
+                             int batch, int num_dims, const int64_t* spatial, int64_t pairs_per_sample,
+                             float* grad_offsets, void* stream);
+/*
+ * cb200_oce_pair_loss: criterions/oce_loss.py:53-63 on materialised embeddings.
+ *   ea, er (n_pairs, D) fp32; grad_ea (n_pairs, D) fp32 or NULL; out = 4 floats
+ *   as above; workspace as for cb200_oce_loss_fwd_bwd.
+ */
+CB200_API int cb200_oce_pair_loss(const float* ea, const float* er, int64_t n_pairs, int num_dims,
+                        float temperature, float regularization_weight,
+                        float* grad_ea, float* out, void* workspace, void* stream);
+
+/*
+ * Device pair sampler (Philox4x32-10), the B200-native replacement of
+ * ZarrDataset.sample_coordinates / sample_offsets_within_radius
+ * (datasets/zarr_dataset.py:177-251): anchors uniform in [kappa, extent-kappa]
+ * per column, each repeated num_references times consecutively; offsets
+ * uniform over the integer points of the open ball sum o^2 < kappa^2 minus
+ * the origin.  Same distribution as the reference, different RNG stream.
+ *  extent       host, num_dims ints in COLUMN order (x, y[, z]) -- the
+ *               reference draws column d from output_shape[d] (quirk Q4)
+ *  anchors/refs (B, num_anchors*num_references, D), CB200_I64 / I32 / I16
+ */
+CB200_API int cb200_sample_pairs(void* anchors, void* refs, int coord_dtype, int batch, int num_dims,
+                       const int64_t* extent, double kappa, int64_t num_anchors, int num_references,
+                       uint64_t seed, uint64_t sequence, void* stream);
+
+/* ===================================================================== *
+ *  Detect slice (inference)                                             *
+ * ===================================================================== */
+
+/*
+ * TTA aggregate: models/unet.py:90-98.
+ *   stack (T, C, n) fp32 -> out (C+1, n) fp32: per-channel mean over T, then
+ *   the per-channel POPULATION std summed over channels.
+ */
+CB200_API int cb200_tta_aggregate(const float* stack, int num_passes, int channels, int64_t n, float* out, void* stream);
+/* Streaming form for an on-device TTA loop (no T-deep stack in HBM):
+ *   state (2*C, n) fp32 = running mean, running M2 (Welford); pass index t is 0-based. */
+CB200_API int cb200_tta_accumulate(float* state, const float* prediction, int t, int channels, int64_t n, void* stream);
+CB200_API int cb200_tta_finalize(const float* state, int num_passes, int channels, int64_t n, float* out, void* stream);
+
+/*
+ * Foreground threshold, detect.py:88-94 (+ skimage threshold_otsu, np.histogram).
+ * cb200_minmax: out2 = {min, max} as doubles.            workspace: cb200_reduce_workspace_bytes()
+ * cb200_histogram: np.histogram(x, nbins, range=(edges[0], edges[nbins])) with
+ *   numpy's exact uniform-bin index arithmetic incl. the +-1 edge corrections;
+ *   edges = np.linspace(min, max, nbins+1) (device, doubles); counts (nbins) uint64, accumulated.
+ */
+CB200_API int64_t cb200_reduce_workspace_bytes(void);
+CB200_API int cb200_minmax(const void* x, int dtype, int64_t n, double* out2, void* workspace, void* stream);
+CB200_API int cb200_histogram(const void* x, int dtype, int64_t n, const double* edges, int nbins,
+                    unsigned long long* counts, void* stream);
+
+/*
+ * Foreground compaction, utils/mean_shift.py:15-36,85,94 (+ detect.py:94):
+ *   mask = std < threshold (compared in float64); foreground pixels, in raster
+ *   order, become points X[k][i] = emb[k][pix] + coordinate_k (float64, SoA:
+ *   points + k*capacity), pix_index[i] = linear pixel index (int32: n_pix < 2^31).
+ *   emb (D+1, *spatial) CB200_F32 / CB200_F64, channel D = std.
+ *   mask_out: optional (n_pix) CB200_U8/CB200_U16 0/1 image (binary-segmentation, detect.py:95)
+ *   n_out: device int64, number of foreground pixels (written before points are).
+ *   If the count exceeds `capacity`, nothing beyond capacity is written and
+ *   *n_out still holds the true count (call again with a larger buffer).
+ *   workspace: cb200_compact_workspace_bytes(n_pix)
+ */
+CB200_API int64_t cb200_compact_workspace_bytes(int64_t n_pix);
+CB200_API int cb200_fg_compact(const void* emb, int dtype, int num_dims, const int64_t* spatial, double threshold,
+                     double* points, int32_t* pix_index, int64_t capacity, long long* n_out,
+                     void* mask_out, int mask_dtype, void* workspace, void* stream);
+
+/* Row subset of an SoA point set: dst[k][j] = src[k][i] for the j-th i with flags[i] != 0
+ * (the `X[np.random.rand(N) < p]` of utils/mean_shift.py:68-70; flags from the host RNG for
+ * parity, or from cb200_bernoulli_flags).  n_out: device int64. */
+CB200_API int cb200_select_points(const double* src, int64_t n, int64_t src_stride, int num_dims, const uint8_t* flags,
+                        double* dst, int64_t dst_stride, long long* n_out, void* workspace, void* stream);
+CB200_API int cb200_bernoulli_flags(uint8_t* flags, int64_t n, double p, uint64_t seed, void* stream);
+
+/*
+ * Flat-kernel mean-shift hill climb, sklearn:108-128, for every seed:
+ *   loop { nbrs = {x : sum_k (m_k - x_k)^2 <= bw^2}; none -> stop;
+ *          m = mean(nbrs); stop if ||m - m_old|| <= 1e-3 bw or it == max_iter; ++it }
+ * All arithmetic float64, distance evaluated as the KD-tree does (sequential
+ * mul/add, no FMA) so the in/out decisions are those of the reference.
+ *
+ * Brute-force n-body form: one iteration over the ACTIVE seeds per call.
+ *   points SoA (D x n, stride pts_stride), means SoA (D x n_seeds, stride seed_stride)
+ *   active: indices of seeds still climbing (n_active of them)
+ *   partial: scratch of cb200_ms_brute_partial_bytes(n_active, n, num_dims) bytes
+ * cb200_ms_brute_accumulate fills the scratch; cb200_ms_update finishes the iteration:
+ * updates means/counts/iters, appends still-active seeds to next_active, *n_next (device int).
+ */
+CB200_API int64_t cb200_ms_brute_partial_bytes(int64_t n_active, int64_t n_points, int num_dims);
+CB200_API int cb200_ms_brute_accumulate(const double* points, int64_t n_points, int64_t pts_stride, int num_dims,
+                              const double* means, int64_t seed_stride, const int* active, int64_t n_active,
+                              double bandwidth, void* partial, void* stream);
+CB200_API int cb200_ms_update(double* means, int64_t seed_stride, int num_dims, int* counts, int* iters,
+                    const int* active, int64_t n_active, int64_t n_points, const void* partial,
+                    double bandwidth, int max_iter, int* next_active, int* n_next, void* stream);
+
+/*
+ * Grid-hash pruned form: cells of edge >= bandwidth; each warp climbs one seed
+ * to convergence inside a single launch, visiting only the 3^D neighbour cells.
+ *   cb200_grid_plan: host-side helper, fills `grid` (origin, cell edge, dims) from a bounding box.
+ *   cb200_grid_build: cell id per point -> sort -> points_sorted SoA + cell_start (n_cells+1 ints).
+ *   cb200_ms_grid_modes: modes (D x n_seeds SoA, in: seeds, out: modes), counts, iters.
+ */
+typedef struct cb200_grid {
+  double origin[3];
+  double cell;      /* edge length, >= bandwidth */
+  double inv_cell;
+  int32_t dims[3];  /* cells per column (x, y, z); unused = 1 */
+  int32_t num_dims;
+  int64_t n_cells;
+} cb200_grid;
+
+CB200_API int cb200_grid_plan(const double* lo, const double* hi, int num_dims, double bandwidth,
+                    int64_t max_cells, cb200_grid* grid /* host out */);
+CB200_API int64_t cb200_grid_build_workspace_bytes(int64_t n_points, int64_t n_cells);
+CB200_API int cb200_grid_build(const double* points, int64_t n_points, int64_t pts_stride, const cb200_grid* grid,
+                     double* points_sorted, int64_t sorted_stride, int* order /* n_points, may be NULL */,
+                     int* cell_start /* n_cells + 1 */, void* workspace, int64_t workspace_bytes, void* stream);
+CB200_API int cb200_ms_grid_modes(const double* points_sorted, int64_t n_points, int64_t sorted_stride,
+                        const cb200_grid* grid, const int* cell_start,
+                        double* means, int64_t seed_stride, int64_t n_seeds,
+                        double bandwidth, int max_iter, int* counts, int* iters,
+                        int* work_counter /* device int, zero */, void* stream);
+
+/*
+ * Centre post-processing, sklearn:511-547: drop empty seeds, order by
+ * (count, coords) descending, merge exact duplicates, greedy suppression of
+ * every centre within `bandwidth` (inclusive) of an earlier survivor --
+ * reproduced exactly as the lexicographically-first maximal independent set.
+ *   centres_out SoA (D x n_seeds capacity, stride = n_seeds), in priority order.
+ *   n_centres_and_undecided[0] = K; [1] = centres still undecided after the built-in
+ *   rounds (0 in practice; if not, call again -- the result is only final when it is 0).
+ */
+CB200_API int64_t cb200_nms_workspace_bytes(int64_t n_seeds, int num_dims, int64_t n_cells);
+CB200_API int cb200_nms_centres(const double* modes, int64_t seed_stride, int num_dims, const int* counts, int64_t n_seeds,
+                      double bandwidth, const cb200_grid* grid /* covers every mode with count > 0 */,
+                      double* centres_out, int* n_centres_and_undecided /* device int[2] */,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * Label assignment, sklearn:563-579 (`predict` = nearest centre, ties -> lowest
+ * index, orphans labelled too) fused with the scatter of utils/mean_shift.py:101-104,57:
+ *   labels_out[pix_index[i]] = 1 + argmin_k ||X_i - c_k||  (label volume pre-zeroed by caller)
+ *   label_dtype CB200_I32 (mean_shift_segmentation's return) or CB200_U16 (detect.py:30,161).
+ *   pix_index may be NULL: labels are then written densely, labels_out[i].
+ */
+CB200_API int cb200_assign_labels(const double* points, int64_t n_points, int64_t pts_stride, int num_dims,
+                        const double* centres, int64_t centre_stride, int n_centres,
+                        const int32_t* pix_index, void* labels_out, int label_dtype, void* stream);
+
+/*
+ * Connected-component size filter, utils/misc.py:11-25 (skimage.measure.label:
+ * full connectivity, equal-valued regions, 0 = background, raster-order ids).
+ *   cb200_label_components: labels_out int32 (n_pix); *n_labels device int.
+ *   cb200_size_filter: in-place zeroing of components smaller than min_size in
+ *   `seg` (int32), then relabel into labels_out.
+ */
+CB200_API int64_t cb200_cc_workspace_bytes(int64_t n_pix);
+CB200_API int cb200_label_components(const int32_t* seg, int num_dims, const int64_t* spatial,
+                           int32_t* labels_out, int* n_labels, void* workspace, void* stream);
+CB200_API int cb200_size_filter(int32_t* seg, int num_dims, const int64_t* spatial, int64_t min_size,
+                      int32_t* labels_out, int* n_labels, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CELLULUS_B200_H */

@@ -1,0 +1,494 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle on the same seeded
+inputs, and against the committed reference outputs (tests/golden/*.npz).
+
+Tolerances (BASELINE.json north_star): loss and gradients within 1e-5 relative (fp32);
+converged mean-shift modes within 1e-3 x bandwidth; labels equal up to permutation with
+ARI >= 0.999; foreground masks, histograms and size filtering bit-exact.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from cellulus_b200 import synthetic  # noqa: E402
+from oracle import mean_shift as oms  # noqa: E402
+from oracle import oce_loss as oloss  # noqa: E402
+from oracle import otsu as ootsu  # noqa: E402
+from oracle import sampler as osampler  # noqa: E402
+from oracle import size_filter as osize  # noqa: E402
+from oracle import tta as otta  # noqa: E402
+
+LOSS_RTOL = 1e-5
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def ari(a, b):
+    """Adjusted Rand index of two labelings (numpy, contingency-table form)."""
+    a, b = np.asarray(a).ravel(), np.asarray(b).ravel()
+    _, ai = np.unique(a, return_inverse=True)
+    _, bi = np.unique(b, return_inverse=True)
+    table = np.zeros((ai.max() + 1, bi.max() + 1), dtype=np.int64)
+    np.add.at(table, (ai, bi), 1)
+    comb = lambda x: x * (x - 1) / 2.0  # noqa: E731
+    s = comb(table).sum()
+    sa, sb = comb(table.sum(1)).sum(), comb(table.sum(0)).sum()
+    n = comb(len(a))
+    expected = sa * sb / n
+    denom = 0.5 * (sa + sb) - expected
+    return 1.0 if denom == 0 else (s - expected) / denom
+
+
+# ----------------------------------------------------------------------------- loss slice
+@pytest.mark.parametrize("case", ["2d", "3d", "2d_hot"])
+def test_fused_loss_matches_reference_golden(golden, case):
+    from cellulus_b200.criterions import oce_loss_fused
+
+    g = golden("loss")
+    T, w = g[f"{case}_params"][:2]
+    offsets = torch.from_numpy(g[f"{case}_offsets"]).to(_dev()).requires_grad_(True)
+    anchors = torch.from_numpy(g[f"{case}_anchors"].astype(np.int64)).to(_dev())
+    refs = torch.from_numpy(g[f"{case}_refs"].astype(np.int64)).to(_dev())
+    loss, oce, reg, raw = oce_loss_fused(offsets, anchors, refs, T, w, return_raw=True)
+    loss.backward()
+    ref = g[f"{case}_loss"]
+    assert abs(loss.item() - ref[0]) <= LOSS_RTOL * abs(ref[0])
+    assert abs(oce.item() - ref[1]) <= LOSS_RTOL * abs(ref[1])
+    assert abs(reg.item() - ref[2]) <= LOSS_RTOL * abs(ref[2])
+    assert raw[3].item() == 0
+    assert _rel(offsets.grad.cpu().numpy(), g[f"{case}_grad"]) <= LOSS_RTOL
+    # and at least as close to exact arithmetic as the fp32 reference itself
+    exact = oloss.loss_step_float64(torch.from_numpy(g[f"{case}_offsets"]), anchors.cpu(), refs.cpu(), T, w)
+    assert abs(loss.item() - exact[0].item()) <= LOSS_RTOL * abs(exact[0].item())
+    assert _rel(offsets.grad.cpu().numpy(), exact[3].numpy()) <= LOSS_RTOL
+
+
+@pytest.mark.parametrize("nd,coord_dtype", [(2, torch.int64), (2, torch.int32), (2, torch.int16), (3, torch.int64),
+                                            (3, torch.int16)])
+def test_fused_loss_matches_oracle_seeded(nd, coord_dtype):
+    from cellulus_b200.criterions import oce_loss_fused
+
+    crop = (140, 140) if nd == 2 else (48, 48, 48)
+    kappa, density, B = (10.0, 0.1, 3) if nd == 2 else (6.0, 0.4, 2)
+    out_shape = osampler.output_shape_of(crop)
+    np.random.seed(0)
+    pairs = [osampler.sample_coordinates(out_shape, kappa, density, nd) for _ in range(B)]
+    anchors = torch.from_numpy(np.stack([p[0] for p in pairs])).long()
+    refs = torch.from_numpy(np.stack([p[1] for p in pairs])).long()
+    offsets = torch.from_numpy(synthetic.loss_offsets(B, nd, out_shape, seed=1))
+    l_ref, o_ref, r_ref, g_ref = oloss.loss_step(offsets, anchors, refs, 10.0, 1e-5)
+    off_d = offsets.to(_dev()).requires_grad_(True)
+    loss, oce, reg = oce_loss_fused(off_d, anchors.to(_dev()).to(coord_dtype), refs.to(_dev()).to(coord_dtype),
+                                    10.0, 1e-5)
+    (2.0 * loss).backward()  # a non-unit upstream gradient exercises the device-side scale
+    assert abs(loss.item() - l_ref.item()) <= LOSS_RTOL * abs(l_ref.item())
+    assert abs(oce.item() - o_ref.item()) <= LOSS_RTOL * abs(o_ref.item())
+    assert abs(reg.item() - r_ref.item()) <= LOSS_RTOL * abs(r_ref.item())
+    assert _rel(off_d.grad.cpu().numpy(), 2.0 * g_ref.numpy()) <= LOSS_RTOL
+
+
+def test_unfused_drop_in_matches_reference_golden(golden):
+    """The reference's three-call shape: gather, gather, criterion (train.py:169-176)."""
+    from cellulus_b200.criterions import get_loss
+    from cellulus_b200.models import UNetModel
+
+    g = golden("loss")
+    for case in ["2d", "3d"]:
+        T, w = g[f"{case}_params"][:2]
+        offsets = torch.from_numpy(g[f"{case}_offsets"]).to(_dev()).requires_grad_(True)
+        anchors = torch.from_numpy(g[f"{case}_anchors"].astype(np.int64)).to(_dev())
+        refs = torch.from_numpy(g[f"{case}_refs"].astype(np.int64)).to(_dev())
+        crit = get_loss(temperature=T, regularizer_weight=w, density=0.1, num_spatial_dims=offsets.ndim - 2,
+                        device=_dev())
+        ea = UNetModel.select_and_add_coordinates(offsets, anchors)
+        er = UNetModel.select_and_add_coordinates(offsets, refs)
+        assert np.array_equal(ea.detach().cpu().numpy(), g[f"{case}_ea"])  # gather + add is bit-exact
+        assert np.array_equal(er.detach().cpu().numpy(), g[f"{case}_er"])
+        loss, oce, reg = crit(ea, er)
+        loss.backward()
+        ref = g[f"{case}_loss"]
+        assert abs(loss.item() - ref[0]) <= LOSS_RTOL * abs(ref[0])
+        assert abs(oce.item() - ref[1]) <= LOSS_RTOL * abs(ref[1])
+        assert _rel(offsets.grad.cpu().numpy(), g[f"{case}_grad"]) <= LOSS_RTOL
+
+
+def test_fused_loss_edge_cases():
+    from cellulus_b200.criterions import oce_loss_fused
+
+    dev = _dev()
+    offsets = torch.randn(2, 2, 16, 20, device=dev, requires_grad=True)
+    # empty pair list -> zero loss, zero gradient
+    empty = torch.zeros((2, 0, 2), dtype=torch.int64, device=dev)
+    loss, oce, reg = oce_loss_fused(offsets, empty, empty, 10.0, 1e-5)
+    loss.backward()
+    assert loss.item() == 0.0 and offsets.grad.abs().max().item() == 0.0
+    # ragged tail (P not a multiple of 32), duplicate anchors, anchor == reference (d = 0, norm grad 0)
+    P = 45
+    a = torch.stack([torch.randint(0, 20, (2, P)), torch.randint(0, 16, (2, P))], -1).to(dev)
+    r = a.clone()
+    r[:, ::2, 0] = (r[:, ::2, 0] + 3) % 20
+    a[:, 5:20] = a[:, 5:6]
+    r[:, 5:20] = r[:, 5:6]
+    off = offsets.detach().clone().requires_grad_(True)
+    loss, _, _ = oce_loss_fused(off, a, r, 3.0, 1e-2)
+    loss.backward()
+    l_ref, _, _, g_ref = oloss.loss_step(offsets.detach().cpu(), a.cpu(), r.cpu(), 3.0, 1e-2)
+    assert abs(loss.item() - l_ref.item()) <= LOSS_RTOL * abs(l_ref.item())
+    assert _rel(off.grad.cpu().numpy(), g_ref.numpy()) <= LOSS_RTOL
+    # out-of-range coordinates are counted, not dereferenced
+    bad = a.clone()
+    bad[0, 0, 0] = 20
+    bad[1, 3, 1] = -17
+    _, _, _, raw = oce_loss_fused(offsets.detach(), bad, r, 3.0, 1e-2, return_raw=True)
+    assert raw[3].item() == 2.0
+    # negative indices wrap once, as torch advanced indexing does
+    neg = a.clone()
+    neg[0, 1, 0] -= 20
+    l_neg, _, _ = oce_loss_fused(offsets.detach(), neg, r, 3.0, 1e-2)
+    l_ref2, _, _, _ = oloss.loss_step(offsets.detach().cpu(), neg.cpu(), r.cpu(), 3.0, 1e-2)
+    assert abs(l_neg.item() - l_ref2.item()) <= LOSS_RTOL * abs(l_ref2.item())
+
+
+def test_fused_loss_bf16_offsets():
+    from cellulus_b200.criterions import oce_loss_fused
+
+    dev = _dev()
+    np.random.seed(3)
+    out_shape = (60, 60)
+    a, r = osampler.sample_coordinates(out_shape, 10.0, 0.1, 2)
+    anchors = torch.from_numpy(a)[None].to(dev)
+    refs = torch.from_numpy(r)[None].to(dev)
+    off_bf16 = torch.randn(1, 2, *out_shape, device=dev).to(torch.bfloat16).requires_grad_(True)
+    loss, _, _ = oce_loss_fused(off_bf16, anchors, refs, 10.0, 1e-5)
+    loss.backward()
+    # oracle on the SAME bf16-rounded values, computed in fp32
+    l_ref, _, _, g_ref = oloss.loss_step(off_bf16.detach().float().cpu(), anchors.cpu(), refs.cpu(), 10.0, 1e-5)
+    assert abs(loss.item() - l_ref.item()) <= LOSS_RTOL * abs(l_ref.item())
+    assert off_bf16.grad.dtype == torch.bfloat16
+    assert _rel(off_bf16.grad.float().cpu().numpy(), g_ref.numpy()) <= 2 ** -8  # bf16 rounding of the result
+
+
+def test_loss_linearity_property_full_size():
+    """Size-independent property at BASELINE config #2 size: with w = 0 the loss of a pair list is the sum of
+    the losses of its halves, and the gradient likewise (no oracle needed at 5.6 M pairs)."""
+    from cellulus_b200 import kernels as K
+
+    dev = _dev()
+    B, S = 8, (496, 496)
+    unb = (S[0] - 20, S[1] - 20)
+    na, nr = int(0.1 * unb[0] * unb[1]), 31
+    anchors, refs = K.sample_pairs(B, (S[1], S[0]), 10.0, na, nr, seed=1, device=dev)
+    offsets = torch.randn(B, 2, *S, device=dev)
+    out_all, g_all = K.oce_loss_fwd_bwd(offsets, anchors, refs, 10.0, 0.0)
+    h = anchors.shape[1] // 2
+    out_a, g_a = K.oce_loss_fwd_bwd(offsets, anchors[:, :h].contiguous(), refs[:, :h].contiguous(), 10.0, 0.0)
+    out_b, g_b = K.oce_loss_fwd_bwd(offsets, anchors[:, h:].contiguous(), refs[:, h:].contiguous(), 10.0, 0.0)
+    assert abs(out_all[0].item() - (out_a[0].item() + out_b[0].item())) <= 1e-5 * abs(out_all[0].item())
+    assert _rel(g_all.cpu().numpy(), (g_a + g_b).cpu().numpy()) <= 1e-5
+    assert out_all[3].item() == 0
+
+
+def test_device_sampler_distribution():
+    """Same distribution as zarr_dataset.py:177-251 (different RNG stream): bounds, run structure,
+    strict open ball minus origin, uniformity over the admissible offsets."""
+    from cellulus_b200 import kernels as K
+
+    for nd, ext, kappa in [(2, (236, 236), 10.0), (3, (64, 48, 40), 5.0)]:
+        na, nr = 5000, 31
+        a, r = K.sample_pairs(2, ext, kappa, na, nr, seed=7, device=_dev(), dtype=torch.int64)
+        a, r = a.cpu().numpy(), r.cpu().numpy()
+        assert a.shape == (2, na * nr, nd)
+        runs = a.reshape(2, na, nr, nd)
+        assert (runs == runs[:, :, :1]).all()  # np.repeat structure
+        for k in range(nd):
+            col = runs[:, :, 0, k]
+            assert col.min() >= int(kappa) and col.max() <= ext[k] - int(kappa)
+            assert col.min() == int(kappa) and col.max() == ext[k] - int(kappa)  # inclusive range is reached
+        off = (r - a).reshape(-1, nd)
+        assert ((off**2).sum(1) < kappa**2).all() and (np.abs(off).sum(1) > 0).all()
+        # uniform over the admissible offsets: chi-square against the flat distribution
+        k_int = int(kappa)
+        grid = np.stack(np.meshgrid(*[np.arange(-k_int, k_int + 1)] * nd, indexing="ij"), -1).reshape(-1, nd)
+        ok = ((grid**2).sum(1) < kappa**2) & (np.abs(grid).sum(1) > 0)
+        n_adm = ok.sum()
+        codes = ((off + k_int) * (2 * k_int + 1) ** np.arange(nd)).sum(1)
+        counts = np.bincount(codes, minlength=(2 * k_int + 1) ** nd)
+        counts = counts[counts > 0]
+        assert len(counts) == n_adm
+        expected = len(off) / n_adm
+        chi2 = ((counts - expected) ** 2 / expected).sum()
+        assert chi2 < n_adm + 6 * np.sqrt(2 * n_adm)
+        # different seeds / sequences give different streams; same seed reproduces
+        a2, _ = K.sample_pairs(2, ext, kappa, na, nr, seed=7, device=_dev())
+        a3, _ = K.sample_pairs(2, ext, kappa, na, nr, seed=8, device=_dev())
+        assert np.array_equal(a2.cpu().numpy(), a) and not np.array_equal(a3.cpu().numpy(), a)
+
+
+# ----------------------------------------------------------------------------- TTA
+@pytest.mark.parametrize("case", ["2d", "3d"])
+def test_tta_matches_reference_golden(golden, case):
+    from cellulus_b200.models import TTAAccumulator, tta_aggregate
+
+    g = golden("tta")
+    stack = torch.from_numpy(g[f"{case}_stack"]).to(_dev())
+    out = tta_aggregate(stack).cpu().numpy()
+    ref = g[f"{case}_out"]
+    exact = otta.tta_aggregate_float64(torch.from_numpy(g[f"{case}_stack"])).numpy()
+    scale = np.abs(exact).max()
+    assert np.abs(out - ref).max() <= 1e-5 * scale
+    assert np.abs(out - exact).max() <= max(np.abs(ref - exact).max() * 4, 1e-6 * scale)
+    acc = TTAAccumulator(stack.shape[1], stack.shape[2:], _dev())
+    for t in range(stack.shape[0]):
+        acc.add(stack[t])
+    assert np.abs(acc.result().cpu().numpy() - ref).max() <= 1e-5 * scale
+
+
+@pytest.mark.parametrize("shape", [(32, 2, 100, 104), (6, 3, 7, 9, 11), (5, 1, 33)])
+def test_tta_matches_oracle_seeded(shape):
+    from cellulus_b200.models import tta_aggregate
+
+    stack = torch.from_numpy(synthetic.tta_stack(shape[0], shape[1], shape[2:], seed=2))
+    ref = otta.tta_aggregate(stack).numpy()
+    out = tta_aggregate(stack.to(_dev())).cpu().numpy()
+    assert out.shape == ref.shape
+    assert np.abs(out - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+# ----------------------------------------------------------------------------- detect preamble
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_histogram_and_otsu_exact(dtype):
+    from cellulus_b200 import kernels as K
+    from cellulus_b200.detect import threshold_otsu
+
+    emb, _, _ = synthetic.blob_scene((150, 170), 25, radius=9.0, seed=4)
+    std = emb[2].astype(dtype)
+    std.ravel()[::97] = std.max()  # values exactly on the last edge
+    std.ravel()[5::89] = std.min()
+    d = torch.from_numpy(std).to(_dev())
+    mm = K.minmax(d).cpu().numpy()
+    assert mm[0] == std.min() and mm[1] == std.max()
+    counts_ref, edges = np.histogram(std.astype(np.float64).ravel(), 256)
+    counts = K.histogram(d, torch.from_numpy(edges).to(_dev())).cpu().numpy()
+    assert np.array_equal(counts, counts_ref)
+    t = threshold_otsu(d)
+    assert t == float(ootsu.threshold_otsu(std.astype(np.float64)))
+    const = torch.full((8, 8), 0.25, device=_dev())
+    assert threshold_otsu(const) == 0.25
+
+
+@pytest.mark.parametrize("shape,dtype", [((70, 90), np.float32), ((9, 40, 50), np.float64), ((5, 7), np.float32)])
+def test_foreground_compaction_exact(shape, dtype):
+    from cellulus_b200 import kernels as K
+
+    emb, _, _ = synthetic.blob_scene(shape, 6, radius=4.0 if min(shape) < 20 else 7.0, seed=5, dtype=dtype)
+    D = len(shape)
+    thr = 0.5
+    pts, pix, n, mask = K.fg_compact(torch.from_numpy(emb).to(_dev()), thr, mask_dtype=torch.uint16)
+    ref_mask = emb[D].astype(np.float64) < thr
+    X = oms.points_from_embedding(emb[:D], ref_mask)
+    assert n == ref_mask.sum()
+    assert np.array_equal(mask.cpu().numpy().astype(bool), ref_mask)  # integer foreground mask: exact
+    assert np.array_equal(pts[:, :n].cpu().numpy().T, X)  # float64 points: exact
+    assert np.array_equal(pix[:n].cpu().numpy(), np.flatnonzero(ref_mask.ravel()))
+    # nothing / everything foreground
+    _, _, n0, _ = K.fg_compact(torch.from_numpy(emb).to(_dev()), -1.0)
+    _, _, n1, _ = K.fg_compact(torch.from_numpy(emb).to(_dev()), 10.0)
+    assert n0 == 0 and n1 == ref_mask.size
+
+
+# ----------------------------------------------------------------------------- mean-shift
+MS_CASES = ["2d_all", "2d_red", "3d_red", "2d_seeds"]
+
+
+def _golden_points(g, case):
+    emb = g[f"{case}_emb"]
+    bw, rp, thr = g[f"{case}_cfg"]
+    D = emb.shape[0] - 1
+    mask = emb[D].astype(np.float64) < thr
+    X = oms.points_from_embedding(emb[:D], mask)
+    seeds = g[f"{case}_seeds"] if f"{case}_seeds" in g.files else None
+    return emb, X, mask, bw, rp, thr, seeds
+
+
+def _soa(X, dev):
+    n, D = X.shape
+    cap = max(2, (n + 1) & ~1)
+    t = torch.zeros((D, cap), dtype=torch.float64, device=dev)
+    t[:, :n] = torch.from_numpy(np.ascontiguousarray(X.T)).to(dev)
+    return t
+
+
+@pytest.mark.parametrize("method", ["brute", "grid"])
+@pytest.mark.parametrize("case", MS_CASES)
+def test_mean_shift_modes_match_sklearn_golden(golden, case, method):
+    """Per-seed (mode, count, iterations) against scikit-learn's own hill climb."""
+    from cellulus_b200 import kernels as K
+
+    g = golden("mean_shift")
+    _, X, _, bw, _, _, seeds = _golden_points(g, case)
+    Xr = X[g[f"{case}_fit_mask"]]
+    sd = Xr if seeds is None else seeds.astype(np.float64)
+    pts = _soa(Xr, _dev())
+    modes = _soa(sd, _dev())
+    if method == "brute":
+        counts, iters = K.ms_brute_modes(pts, len(Xr), modes, len(sd), bw)
+    else:
+        lo, hi = K.bounding_box(pts, len(Xr))
+        grid = K.plan_grid(lo, hi, bw)
+        sorted_pts, cell_start, _ = K.grid_build(pts, len(Xr), grid)
+        counts, iters = K.ms_grid_modes(sorted_pts, len(Xr), grid, cell_start, modes, len(sd), bw)
+    counts = counts[: len(sd)].cpu().numpy()
+    iters = iters[: len(sd)].cpu().numpy()
+    m = modes[:, : len(sd)].cpu().numpy().T
+    assert np.array_equal(counts, g[f"{case}_counts"])  # identical neighbour sets at the last step
+    assert np.array_equal(iters, g[f"{case}_iters"])  # identical trajectories
+    keep = counts > 0
+    assert np.abs(m[keep] - g[f"{case}_modes"][keep]).max() <= 1e-3 * bw  # the stated bar ...
+    assert np.abs(m[keep] - g[f"{case}_modes"][keep]).max() <= 1e-9 * bw  # ... met with 6 orders to spare
+
+
+@pytest.mark.parametrize("method", ["brute", "grid"])
+@pytest.mark.parametrize("case", MS_CASES)
+def test_mean_shift_segmentation_drop_in_matches_reference(golden, case, method):
+    from cellulus_b200.utils.mean_shift import mean_shift_segmentation
+
+    g = golden("mean_shift")
+    emb, _, _, bw, rp, thr, seeds = _golden_points(g, case)
+    D = emb.shape[0] - 1
+    emb64 = emb.astype(np.float64)
+    mean_in = emb64[np.newaxis, :D].copy()
+    ref_in = emb64[np.newaxis, :D].copy()
+    np.random.seed(123)
+    labels = mean_shift_segmentation(mean_in, emb64[D], bw, 10, rp, thr, seeds, method=method)
+    assert labels.dtype == np.int32 and labels.shape == emb.shape[1:]
+    ref = g[f"{case}_labels"]
+    assert np.array_equal(labels > 0, ref > 0)  # foreground mask: exact
+    assert ari(labels, ref) >= 0.999
+    assert np.array_equal(labels, ref)  # in fact identical, numbering included
+    # side effect of the reference: coordinates added in place (utils/mean_shift.py:15-32)
+    np.random.seed(123)
+    oms.mean_shift_segmentation(ref_in, emb64[D], bw, 10, rp, thr, seeds)
+    assert np.array_equal(mean_in, ref_in)
+
+
+@pytest.mark.parametrize("case", ["2d_red", "3d_red"])
+def test_centres_match_sklearn_golden(golden, case):
+    from cellulus_b200.utils.mean_shift import cluster_points_device
+
+    g = golden("mean_shift")
+    _, X, _, bw, _, _, seeds = _golden_points(g, case)
+    Xr = X[g[f"{case}_fit_mask"]]
+    pts = _soa(X, _dev())
+    fit = _soa(Xr, _dev())
+    for method in ["brute", "grid"]:
+        centres, k, _ = cluster_points_device(pts, len(X), fit, len(Xr), bw, seeds=seeds, method=method)
+        ref = g[f"{case}_centres"]
+        assert k == len(ref)
+        assert np.abs(centres[:, :k].cpu().numpy().T - ref).max() <= 1e-9 * bw  # same centres, same ORDER
+
+
+def test_mean_shift_matches_oracle_larger_scene():
+    """A scene the numpy oracle still finishes in seconds; grid and brute kernels agree with it exactly."""
+    from cellulus_b200.utils.mean_shift import segment_embeddings_device
+
+    emb, _, _ = synthetic.blob_scene((160, 160), 40, radius=8.0, seed=9)
+    bw, thr, rp = 5.0, 0.5, 0.2
+    D = 2
+    mask = emb[D].astype(np.float64) < thr
+    X = oms.points_from_embedding(emb[:D], mask)
+    np.random.seed(5)
+    fit_mask = np.random.rand(len(X)) < rp
+    ref_labels, ref_centres = oms.segment_points(X, fit_mask, bw)
+    ref = np.zeros(mask.shape, np.int32)
+    ref[mask] = ref_labels + 1
+    for method in ["brute", "grid"]:
+        np.random.seed(5)
+        labels, info = segment_embeddings_device(torch.from_numpy(emb).to(_dev()), bw, thr, rp, method=method)
+        assert info["k"] == len(ref_centres)
+        assert np.abs(info["centres"].cpu().numpy().T - ref_centres).max() <= 1e-3 * bw
+        assert ari(labels.cpu().numpy(), ref) >= 0.999
+        assert np.array_equal(labels.cpu().numpy() > 0, ref > 0)
+
+
+def test_mean_shift_kats_and_edges():
+    """Known answers verified on the reference: inclusive radius, orphans labelled by predict,
+    ties -> lowest index, empty-window seeds dropped, empty mask -> all background."""
+    from cellulus_b200 import kernels as K
+    from cellulus_b200.utils.mean_shift import cluster_points_device, segment_embeddings_device
+
+    dev = _dev()
+    X = np.array([[0.0, 0.0], [3.0, 4.0], [100.0, 100.0]])
+    for method in ["brute", "grid"]:
+        pts = _soa(X, dev)
+        seeds = np.array([[0.0, 0.0], [50.0, 50.0]])
+        centres, k, info = cluster_points_device(pts, 3, pts, 3, 5.0, seeds=seeds, method=method)
+        counts = info["counts"].cpu().numpy()
+        assert counts[0] == 2 and counts[1] == 0  # distance exactly 5 is inside; far seed has an empty window
+        assert k == 1
+        assert np.allclose(centres[:, 0].cpu().numpy(), [1.5, 2.0])
+        labels = torch.zeros(3, dtype=torch.int32, device=dev)
+        K.assign_labels(pts, 3, centres, k, None, labels)
+        assert labels.cpu().tolist() == [1, 1, 1]  # the orphan at (100, 100) is labelled too
+    cen = _soa(np.array([[0.0, 0.0], [2.0, 0.0]]), dev)
+    q = _soa(np.array([[1.0, 0.0], [1.5, 0.0]]), dev)
+    labels = torch.zeros(2, dtype=torch.int32, device=dev)
+    K.assign_labels(q, 2, cen, 2, None, labels)
+    assert labels.cpu().tolist() == [1, 2]  # tie -> lowest index
+    emb = np.ones((3, 12, 12), np.float32)
+    labels, info = segment_embeddings_device(torch.from_numpy(emb).to(dev), 3.0, 0.5, 1.0)
+    assert info["n_fg"] == 0 and labels.abs().max().item() == 0
+    with pytest.raises(ValueError, match="No point was within bandwidth"):
+        pts = _soa(X, dev)
+        cluster_points_device(pts, 3, pts, 3, 5.0, seeds=np.array([[50.0, 50.0]]), method="grid")
+
+
+def test_detect_full_pipeline_3d_properties():
+    """BASELINE config #3 shape (128 x 256 x 256, 3-D embeddings): no oracle at this size; size-independent
+    properties instead -- idempotent, every object recovered, labels constant inside an object."""
+    from cellulus_b200.detect import detect_embeddings
+
+    shape = (128, 256, 256)
+    emb, centres, ids = synthetic.blob_scene(shape, 400, radius=10.0, seed=0)
+    d = torch.from_numpy(emb).to(_dev())
+    np.random.seed(0)
+    labels, thr, mask, infos = detect_embeddings(d, bandwidth=7.0, threshold=0.5, reduction_probability=0.1,
+                                                 return_info=True)
+    np.random.seed(0)
+    labels2, _, _ = detect_embeddings(d, bandwidth=7.0, threshold=0.5, reduction_probability=0.1)
+    assert torch.equal(labels, labels2)  # deterministic
+    lab = labels[0].cpu().numpy()
+    assert lab.dtype == np.uint16
+    assert np.array_equal(lab > 0, ids > 0)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), ids > 0)
+    assert ari(lab[ids > 0], ids[ids > 0]) >= 0.99  # vs the generating ground truth (objects may touch)
+    assert abs(infos[0]["k"] - len(np.unique(ids[ids > 0]))) <= 0.05 * len(centres)
+
+
+# ----------------------------------------------------------------------------- size filter
+@pytest.mark.parametrize("shape", [(64, 80), (10, 30, 34), (1, 9), (300, 300)])
+def test_size_filter_exact(shape):
+    from cellulus_b200 import kernels as K
+    from cellulus_b200.utils.misc import size_filter
+
+    rng = np.random.default_rng(3)
+    binary = rng.random(shape) < 0.4
+    seg = (binary * rng.integers(1, 5, size=shape)).astype(np.uint16)
+    lab, n = K.label_components(torch.from_numpy(seg.astype(np.int32)).to(_dev()))
+    ref_lab = osize.label_equal_regions(seg)
+    assert np.array_equal(lab.cpu().numpy(), ref_lab)  # same regions AND same raster-order numbering
+    assert n.item() == ref_lab.max()
+    for min_size in [0, 3, 12]:
+        a, b = seg.copy(), seg.copy()
+        out = size_filter(a, min_size)
+        ref = osize.size_filter(b, min_size)
+        assert np.array_equal(a, b)  # in-place removal set: exact
+        assert np.array_equal(np.asarray(out), np.asarray(ref))
