@@ -10,10 +10,11 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libcellulus_b200.so")
+LIB_PATH = os.environ.get("CELLULUS_B200_LIB") or os.path.join(PKG, "libcellulus_b200.so")  # override: A/B builds
 
 OK, EINVAL, EUNSUPPORTED = 0, -1, -2
 F32, BF16, F64, I64, I32, I16, U8, U16 = range(8)
+LAYOUT_PLANAR, LAYOUT_CHANNELS_LAST = 0, 1
 
 
 class Grid(C.Structure):
@@ -41,7 +42,7 @@ PROTOTYPES = {
     "cb200_version": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "cb200_error_string": (C.c_char_p, [_i]),
     "cb200_oce_loss_workspace_bytes": (_i64, []),
-    "cb200_oce_loss_fwd_bwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _pi64, _i64, _f, _f, _p, _p, _p, _p]),
+    "cb200_oce_loss_fwd_bwd": (_i, [_p, _i, _i, _p, _p, _i, _i, _i, _pi64, _i64, _f, _f, _p, _p, _p, _p]),
     "cb200_scale_inplace": (_i, [_p, _i64, _p, _p]),
     "cb200_gather_add_coords": (_i, [_p, _i, _p, _i, _i, _i, _pi64, _i64, _p, _p]),
     "cb200_scatter_add_coords": (_i, [_p, _p, _i, _i, _i, _pi64, _i64, _p, _p]),

@@ -54,19 +54,23 @@ def _digest() -> str:
 
 
 def is_fresh() -> bool:
-    stamp = os.path.join(BUILD, "digest")
+    stamp = LIB + ".digest"
     return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == _digest()
 
 
-def build(force: bool = False, verbose: bool = True) -> str:
-    if not force and is_fresh():
+def build(force: bool = False, verbose: bool = True, extra_flags=(), out: str | None = None) -> str:
+    """`extra_flags` / `out` build a tuning variant (e.g. -DCB200_LOSS_UNROLL=4) next to the real library."""
+    variant = bool(extra_flags) or out is not None
+    if not variant and not force and is_fresh():
         return LIB
-    os.makedirs(BUILD, exist_ok=True)
+    build_dir = BUILD if not variant else os.path.join(BUILD, "variant_" + hashlib.sha1(" ".join(extra_flags).encode()).hexdigest()[:8])
+    os.makedirs(build_dir, exist_ok=True)
     nvcc = _nvcc()
+    lib_out = out or LIB
 
     def compile_one(src):
-        obj = os.path.join(BUILD, src[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(build_dir, src[:-3] + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -74,15 +78,16 @@ def build(force: bool = False, verbose: bool = True) -> str:
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", lib_out, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    with open(os.path.join(BUILD, "digest"), "w") as fh:
-        fh.write(_digest())
+    if not variant:
+        with open(LIB + ".digest", "w") as fh:
+            fh.write(_digest())
     if verbose:
-        print(f"built {LIB} from {len(objs)} translation units", file=sys.stderr)
-    return LIB
+        print(f"built {lib_out} from {len(objs)} translation units", file=sys.stderr)
+    return lib_out
 
 
 if __name__ == "__main__":

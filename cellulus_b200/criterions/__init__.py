@@ -1,4 +1,4 @@
-from cellulus_b200.criterions.oce_loss import OCELoss, oce_loss_fused  # noqa: F401
+from cellulus_b200.criterions.oce_loss import GraphedLossStep, OCELoss, oce_loss_fused  # noqa: F401
 
 
 def get_loss(

@@ -115,6 +115,44 @@ def oce_loss_fused(offsets, anchor_coordinates, reference_coordinates, temperatu
     return loss, oce, reg
 
 
+class GraphedLossStep:
+    """One fused loss step (zero-fill + gather + loss + backward) captured in a CUDA graph.
+
+    The step is two tiny launches; replaying them as a graph takes the host (python, ctypes, the
+    caching allocator) out of the loop, which is what a launch-bound inner loop wants on B200.
+    Buffers are static: write new data into `.offsets` / `.anchors` / `.refs` (or pass tensors that
+    are already final), call `replay()`, read `.loss`, `.oce_loss`, `.regularization_loss`, `.grad`
+    (`d loss / d offsets`, in the memory layout of `offsets`).
+    """
+
+    def __init__(self, offsets, anchor_coordinates, reference_coordinates, temperature, regularizer_weight):
+        self.offsets = offsets.detach()
+        self.anchors = anchor_coordinates
+        self.refs = reference_coordinates
+        self.temperature = float(temperature)
+        self.regularizer_weight = float(regularizer_weight)
+        dev = self.offsets.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):  # warm-up outside the capture (workspace allocation, occupancy query)
+                self._run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.raw, self.grad = self._run()
+        self.loss, self.oce_loss, self.regularization_loss = self.raw[0], self.raw[1], self.raw[2]
+
+    def _run(self):
+        return K.oce_loss_fwd_bwd(self.offsets, self.anchors, self.refs, self.temperature, self.regularizer_weight,
+                                  want_grad=True)
+
+    def replay(self):
+        self.graph.replay()
+        K.launch_counter["calls"] += 1
+        return self.loss
+
+
 class OCELoss(nn.Module):  # type: ignore
     def __init__(
         self,

@@ -75,13 +75,21 @@ __device__ __forceinline__ int pixel_of(const int (&c)[D], const Shape<D>& s) {
   return (c[2] * s.ext[1] + c[1]) * s.ext[0] + c[0];
 }
 
+#ifndef CB200_LOSS_UNROLL
+#define CB200_LOSS_UNROLL 1
+#endif
+#ifndef CB200_LOSS_MIN_BLOCKS
+#define CB200_LOSS_MIN_BLOCKS 6  // <= 40 registers: 48 resident warps per SM (measured best, tools/loss_sweep.py)
+#endif
 constexpr int LOSS_THREADS = 256;
-constexpr int LOSS_UNROLL = 4;
+constexpr int LOSS_UNROLL = CB200_LOSS_UNROLL;
+constexpr int LOSS_MIN_BLOCKS = CB200_LOSS_MIN_BLOCKS;
 
+constexpr int LOSS_MAX_WARPS = 16;
 __device__ __forceinline__ void block_reduce_to_workspace(float oce, float nrm, int bad, LossWorkspace* ws,
                                                           float w, float* out) {
-  __shared__ double s_acc[2][LOSS_THREADS / 32];
-  __shared__ int s_bad[LOSS_THREADS / 32];
+  __shared__ double s_acc[2][LOSS_MAX_WARPS];
+  __shared__ int s_bad[LOSS_MAX_WARPS];
   __shared__ bool s_last;
   double a = warp_sum((double)oce), b = warp_sum((double)nrm);
   int c = warp_sum(bad);
@@ -95,8 +103,7 @@ __device__ __forceinline__ void block_reduce_to_workspace(float oce, float nrm, 
   if (threadIdx.x == 0) {
     double ta = 0, tb = 0;
     int tc = 0;
-#pragma unroll
-    for (int i = 0; i < LOSS_THREADS / 32; ++i) {
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
       ta += s_acc[0][i];
       tb += s_acc[1][i];
       tc += s_bad[i];
@@ -106,7 +113,7 @@ __device__ __forceinline__ void block_reduce_to_workspace(float oce, float nrm, 
     if (tc) atomicAdd(&ws->bad, (unsigned long long)tc);
     __threadfence();
     const unsigned t = atomicAdd(&ws->ticket, 1u);
-    s_last = (t == gridDim.x - 1);
+    s_last = (t == gridDim.x * gridDim.y - 1);
   }
   __syncthreads();
   if (s_last && threadIdx.x == 0) {
@@ -127,120 +134,245 @@ __device__ __forceinline__ void block_reduce_to_workspace(float oce, float nrm, 
   }
 }
 
-template <int D, typename CT, typename OT, bool BWD>
-__global__ void __launch_bounds__(LOSS_THREADS)
+// ---- raw coordinate registers: what the load returns, converted only at first use, so that the
+// software prefetch of the NEXT iteration's coordinates never stalls on its own loads ----------
+template <int D, typename CT>
+struct RawCoord;
+template <>
+struct RawCoord<2, long long> {
+  longlong2 v;
+  __device__ __forceinline__ void load(const long long* base, unsigned pair) { v = ld_stream_ll2(base + (size_t)pair * 2); }
+  __device__ __forceinline__ void zero() { v.x = v.y = 0; }
+  __device__ __forceinline__ int get(int k) const { return (int)(k == 0 ? v.x : v.y); }
+};
+template <>
+struct RawCoord<2, int> {
+  int2 v;
+  __device__ __forceinline__ void load(const int* base, unsigned pair) { v = __ldg(reinterpret_cast<const int2*>(base) + pair); }
+  __device__ __forceinline__ void zero() { v.x = v.y = 0; }
+  __device__ __forceinline__ int get(int k) const { return k == 0 ? v.x : v.y; }
+};
+template <>
+struct RawCoord<2, short> {
+  short2 v;
+  __device__ __forceinline__ void load(const short* base, unsigned pair) { v = __ldg(reinterpret_cast<const short2*>(base) + pair); }
+  __device__ __forceinline__ void zero() { v.x = v.y = 0; }
+  __device__ __forceinline__ int get(int k) const { return k == 0 ? v.x : v.y; }
+};
+template <typename CT>
+struct RawCoord<3, CT> {
+  CT v[3];
+  __device__ __forceinline__ void load(const CT* base, unsigned pair) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if constexpr (sizeof(CT) == 8) v[k] = (CT)ld_stream_ll(base + (size_t)pair * 3 + k);
+      else v[k] = __ldg(base + (size_t)pair * 3 + k);
+    }
+  }
+  __device__ __forceinline__ void zero() { v[0] = v[1] = v[2] = 0; }
+  __device__ __forceinline__ int get(int k) const { return (int)v[k]; }
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// pixel gather: PLANAR = (B, D, *S) contiguous; interleaved = channels-last (B, *S, D) contiguous
+template <int D, typename OT, bool IL>
+__device__ __forceinline__ void gather_pixel(const OT* __restrict__ base, int npix, int pix, float (&o)[D]) {
+  if constexpr (!IL) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) o[k] = load_as_float<OT>(base, k * npix + pix);
+  } else if constexpr (D == 2 && sizeof(OT) == 4) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(base) + pix);
+    o[0] = v.x;
+    o[1] = v.y;
+  } else if constexpr (D == 2 && sizeof(OT) == 2) {
+    const __nv_bfloat162 v = __ldg(reinterpret_cast<const __nv_bfloat162*>(base) + pix);
+    o[0] = __low2float(v);
+    o[1] = __high2float(v);
+  } else {
+#pragma unroll
+    for (int k = 0; k < D; ++k) o[k] = load_as_float<OT>(base, pix * D + k);
+  }
+}
+
+template <int D, bool IL>
+__device__ __forceinline__ void scatter_pixel(float* __restrict__ gbase, int npix, int pix, const float (&g)[D]) {
+  if constexpr (!IL) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) atomicAdd(gbase + (k * npix + pix), g[k]);
+  } else if constexpr (D == 2) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gbase + pix * 2), "f"(g[0]), "f"(g[1]) : "memory");
+  } else {
+#pragma unroll
+    for (int k = 0; k < D; ++k) atomicAdd(gbase + (pix * D + k), g[k]);
+  }
+}
+
+// ---- per-chunk work shared by both kernels --------------------------------------------------------
+// U chunks of 32 pairs: range-check (fast path: one unsigned compare per coordinate; the rare negative
+// index takes the wrapping slow path, as torch advanced indexing would), issue all gathers, then the
+// pair terms, the segmented warp sum of the gradients and one reduction per run of equal anchors.
+template <int D, typename OT, bool BWD, bool IL, int U>
+__device__ __forceinline__ void process_chunks(int (&ca)[U][D], int (&cr)[U][D], bool (&live)[U],
+                                               const OT* __restrict__ off_b, float* __restrict__ grad_b,
+                                               const Shape<D>& shape, float neg_log2e_over_t, float two_over_t,
+                                               float w, unsigned lane, float& acc_oce, float& acc_nrm, int& bad) {
+  float oa[U][D], orf[U][D];
+  int pix_a[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+      ok = ok && ((unsigned)ca[u][k] < (unsigned)shape.ext[k]) && ((unsigned)cr[u][k] < (unsigned)shape.ext[k]);
+    int pa, pr;
+    if (__builtin_expect(__any_sync(FULL, live[u] && !ok), 0)) {
+      int wa[D], wr[D];
+      ok = wrap_and_check<D>(ca[u], wa, shape) & wrap_and_check<D>(cr[u], wr, shape);
+      pa = pixel_of<D>(wa, shape);
+      pr = pixel_of<D>(wr, shape);
+    } else {
+      pa = pixel_of<D>(ca[u], shape);
+      pr = pixel_of<D>(cr[u], shape);
+    }
+    if (live[u] && !ok) ++bad;
+    live[u] = live[u] && ok;
+    pix_a[u] = live[u] ? pa : -1 - u;  // dead lanes never merge with a live neighbour
+    if (live[u]) {
+      gather_pixel<D, OT, IL>(off_b, (int)shape.npix, pa, oa[u]);
+      gather_pixel<D, OT, IL>(off_b, (int)shape.npix, pr, orf[u]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < D; ++k) oa[u][k] = orf[u][k] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    float g[D], diff[D], ea[D];
+    float d2 = 0.f, n2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      ea[k] = __fadd_rn(oa[u][k], (float)ca[u][k]);  // selection += coordinate (models/unet.py:120)
+      const float er = __fadd_rn(orf[u][k], (float)cr[u][k]);
+      diff[k] = ea[k] - er;
+      d2 = fmaf(diff[k], diff[k], d2);
+      n2 = fmaf(ea[k], ea[k], n2);
+    }
+    const float e = ex2_approx(d2 * neg_log2e_over_t);   // exp(-d^2 / T)
+    const float rs = n2 > 0.f ? rsqrt_approx(n2) : 0.f;  // 1 / ||ea||, 0 at the origin (torch's norm backward)
+    if (live[u]) {
+      acc_oce += 1.0f - e;
+      acc_nrm = fmaf(n2, rs, acc_nrm);  // ||ea||
+    }
+    if constexpr (BWD) {
+      const float ge = two_over_t * e;
+      const float gr = w * rs;
+#pragma unroll
+      for (int k = 0; k < D; ++k) g[k] = live[u] ? fmaf(ge, diff[k], gr * ea[k]) : 0.f;
+      // segmented sum over runs of equal anchor pixel; only run heads touch memory
+      const int key = pix_a[u];
+      const int prev = __shfl_up_sync(FULL, key, 1);
+      const bool head = (lane == 0) || (prev != key);
+      const unsigned heads = __ballot_sync(FULL, head);
+      const unsigned above = heads & (0xfffffffeu << lane);
+      const unsigned limit = above ? (unsigned)(__ffs(above) - 1) : 32u;
+#pragma unroll
+      for (unsigned o = 1; o < 32; o <<= 1) {
+        const bool take = lane + o < limit;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          const float v = __shfl_down_sync(FULL, g[k], o);
+          if (take) g[k] += v;
+        }
+      }
+      if (head && live[u]) scatter_pixel<D, IL>(grad_b, (int)shape.npix, key, g);
+    }
+  }
+}
+
+// ---- the fused kernel: direct streaming loads, register double buffer ------------------------------
+// One warp owns LOSS_UNROLL chunks of 32 consecutive pairs of ONE sample (blockIdx.y) per iteration.
+// Iteration i+1's coordinates are fetched before iteration i's gathers are issued, so the HBM latency
+// of the lists hides behind the L2 gathers and the math.
+template <int D, typename CT, typename OT, bool BWD, bool IL>
+__global__ void __launch_bounds__(LOSS_THREADS, LOSS_MIN_BLOCKS)
 oce_loss_fused_kernel(const OT* __restrict__ offsets, const CT* __restrict__ anchors, const CT* __restrict__ refs,
-                      int batch, int64_t P, Shape<D> shape, float inv_t, float w, float* __restrict__ grad,
-                      LossWorkspace* ws, float* out) {
-  const int lane = lane_id();
-  const int warps_per_block = LOSS_THREADS / 32;
-  const int64_t chunks_per_sample = (P + 31) >> 5;
-  const int64_t n_chunks = chunks_per_sample * batch;
-  const int64_t warp_gid = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  const int64_t warp_stride = (int64_t)gridDim.x * warps_per_block;
-  const float two_inv_t = 2.0f * inv_t;
+                      unsigned P, unsigned chunks_per_sample, Shape<D> shape, float neg_log2e_over_t, float two_over_t,
+                      float w, float* __restrict__ grad, LossWorkspace* ws, float* out) {
+  const unsigned lane = lane_id();
+  const unsigned b = blockIdx.y;
+  const unsigned warp_stride = gridDim.x * (LOSS_THREADS / 32) * LOSS_UNROLL;
+  const CT* __restrict__ a_base = anchors + (size_t)b * P * D;
+  const CT* __restrict__ r_base = refs + (size_t)b * P * D;
+  const OT* __restrict__ off_b = offsets + (size_t)b * D * shape.npix;
+  float* __restrict__ grad_b = BWD ? grad + (size_t)b * D * shape.npix : nullptr;
 
   float acc_oce = 0.f, acc_nrm = 0.f;
   int bad = 0;
 
-  for (int64_t chunk0 = warp_gid * LOSS_UNROLL; chunk0 < n_chunks; chunk0 += warp_stride * LOSS_UNROLL) {
+  RawCoord<D, CT> na[LOSS_UNROLL], nr[LOSS_UNROLL];
+  auto fetch = [&](unsigned c0) {
+#pragma unroll
+    for (int u = 0; u < LOSS_UNROLL; ++u) {
+      const unsigned p = ((c0 + u) << 5) + lane;
+      if (p < P) {
+        na[u].load(a_base, p);
+        nr[u].load(r_base, p);
+      } else {
+        na[u].zero();
+        nr[u].zero();
+      }
+    }
+  };
+
+  unsigned c0 = (blockIdx.x * (LOSS_THREADS / 32) + (threadIdx.x >> 5)) * LOSS_UNROLL;
+  if (c0 < chunks_per_sample) fetch(c0);
+  for (; c0 < chunks_per_sample; c0 += warp_stride) {
     int ca[LOSS_UNROLL][D], cr[LOSS_UNROLL][D];
-    int b[LOSS_UNROLL];
     bool live[LOSS_UNROLL];
-    // ---- phase 1: coordinate loads (2 * UNROLL independent 16-byte requests in flight) ----
 #pragma unroll
     for (int u = 0; u < LOSS_UNROLL; ++u) {
-      const int64_t chunk = chunk0 + u;
-      const int bb = (int)(chunk / chunks_per_sample);
-      const int64_t p = ((chunk - (int64_t)bb * chunks_per_sample) << 5) + lane;
-      b[u] = bb;
-      live[u] = (chunk < n_chunks) && (p < P);
-      if (live[u]) {
-        const int64_t pair = (int64_t)bb * P + p;
-        load_coord<D, CT>(anchors, pair, ca[u]);
-        load_coord<D, CT>(refs, pair, cr[u]);
-      } else {
-#pragma unroll
-        for (int k = 0; k < D; ++k) ca[u][k] = cr[u][k] = 0;
-      }
-    }
-    // ---- phase 2: pixel gathers (L2-resident offsets) ----
-    float oa[LOSS_UNROLL][D], orf[LOSS_UNROLL][D];
-    int pix_a[LOSS_UNROLL];
-#pragma unroll
-    for (int u = 0; u < LOSS_UNROLL; ++u) {
-      int wa[D], wr[D];
-      if (live[u]) {
-        const bool ok = wrap_and_check<D>(ca[u], wa, shape) & wrap_and_check<D>(cr[u], wr, shape);
-        if (!ok) {
-          live[u] = false;
-          ++bad;
-        }
-      }
-      pix_a[u] = -1 - u;  // dead lanes never merge with a live neighbour
-      if (live[u]) {
-        const int pa = pixel_of<D>(wa, shape);
-        const int pr = pixel_of<D>(wr, shape);
-        const int64_t base = (int64_t)b[u] * D * shape.npix;
-        pix_a[u] = pa;
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-          oa[u][k] = load_as_float<OT>(offsets, base + k * shape.npix + pa);
-          orf[u][k] = load_as_float<OT>(offsets, base + k * shape.npix + pr);
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < D; ++k) oa[u][k] = orf[u][k] = 0.f;
-      }
-    }
-    // ---- phase 3: pair terms, segmented warp reduction, scatter ----
-#pragma unroll
-    for (int u = 0; u < LOSS_UNROLL; ++u) {
-      float g[D];
-      float d2 = 0.f, n2 = 0.f, diff[D], ea[D];
+      live[u] = (((c0 + u) << 5) + lane) < P;
 #pragma unroll
       for (int k = 0; k < D; ++k) {
-        ea[k] = __fadd_rn(oa[u][k], (float)ca[u][k]);  // selection += coordinate (models/unet.py:120)
-        const float er = __fadd_rn(orf[u][k], (float)cr[u][k]);
-        diff[k] = ea[k] - er;
-        d2 = fmaf(diff[k], diff[k], d2);
-        n2 = fmaf(ea[k], ea[k], n2);
-      }
-      const float e = expf(-d2 * inv_t);
-      const float nrm = sqrtf(n2);
-      if (live[u]) {
-        acc_oce += 1.0f - e;
-        acc_nrm += nrm;
-      }
-      if constexpr (BWD) {
-        const float ge = two_inv_t * e;
-        const float gr = nrm > 0.f ? w / nrm : 0.f;
-#pragma unroll
-        for (int k = 0; k < D; ++k) g[k] = live[u] ? fmaf(ge, diff[k], gr * ea[k]) : 0.f;
-        // runs of equal anchor pixel (same sample: a chunk never straddles samples)
-        const int key = pix_a[u];
-        const int prev = __shfl_up_sync(FULL, key, 1);
-        const bool head = (lane == 0) || (prev != key);
-        const unsigned heads = __ballot_sync(FULL, head);
-        const unsigned above = (lane == 31) ? 0u : (heads & (0xfffffffeu << lane));
-        const int limit = above ? (__ffs(above) - 1) : 32;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-#pragma unroll
-          for (int k = 0; k < D; ++k) {
-            const float v = __shfl_down_sync(FULL, g[k], o);
-            if (lane + o < limit) g[k] += v;
-          }
-        }
-        if (head && live[u]) {
-          float* gp = grad + (int64_t)b[u] * D * shape.npix + key;
-#pragma unroll
-          for (int k = 0; k < D; ++k) atomicAdd(gp + k * shape.npix, g[k]);
-        }
+        ca[u][k] = na[u].get(k);
+        cr[u][k] = nr[u].get(k);
       }
     }
+    if (c0 + warp_stride < chunks_per_sample) fetch(c0 + warp_stride);  // prefetch the next iteration
+    process_chunks<D, OT, BWD, IL, LOSS_UNROLL>(ca, cr, live, off_b, grad_b, shape, neg_log2e_over_t, two_over_t, w,
+                                                lane, acc_oce, acc_nrm, bad);
   }
   block_reduce_to_workspace(acc_oce, acc_nrm, bad, ws, w, out);
+}
+
+// zero-fill of the gradient tensor (16-byte stores, one wave)
+__global__ void __launch_bounds__(256) zero_fill_kernel(float4* __restrict__ p, int64_t n4, float* __restrict__ tail,
+                                                        int n_tail) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) p[i] = z;
+  if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) tail[threadIdx.x] = 0.f;
+}
+static int zero_fill(float* p, int64_t n, cudaStream_t st) {
+  if (n <= 0) return CB200_OK;
+  if (reinterpret_cast<uintptr_t>(p) & 15) {
+    CB200_CUDA_TRY(cudaMemsetAsync(p, 0, sizeof(float) * (size_t)n, st));
+    return CB200_OK;
+  }
+  const int64_t n4 = n / 4;
+  zero_fill_kernel<<<grid_for(n4, 256, 4, 8), 256, 0, st>>>(reinterpret_cast<float4*>(p), n4, p + n4 * 4, (int)(n - n4 * 4));
+  CB200_LAUNCH_CHECK();
+  return CB200_OK;
 }
 
 // grad *= *scale, skipping all work when the upstream gradient is exactly 1
@@ -370,53 +502,78 @@ static bool make_shape(const int64_t* spatial, Shape<D>& s) {
     s.ext[k] = (int)e;
     npix *= e;
   }
-  if (npix > INT32_MAX) return false;  // pixel indices are 32-bit per sample
+  if (npix * D > INT32_MAX) return false;  // element offsets are 32-bit per sample
   s.npix = npix;
   return true;
 }
 
-template <int D, typename CT, typename OT>
-static int launch_fused(const void* offsets, const void* anchors, const void* refs, int batch, const int64_t* spatial,
-                        int64_t P, float T, float w, float* grad, float* out, void* workspace, cudaStream_t st) {
-  Shape<D> shape;
-  if (!make_shape<D>(spatial, shape)) return CB200_EINVAL;
-  const int64_t n_chunks = ((P + 31) >> 5) * batch;
-  const int warps = LOSS_THREADS / 32;
-  int64_t blocks = (n_chunks + (int64_t)warps * LOSS_UNROLL - 1) / ((int64_t)warps * LOSS_UNROLL);
-  const int64_t cap = (int64_t)CB200_SM_COUNT * 8;  // persistent: 8 CTAs of 256 threads per SM
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  auto* ws = static_cast<LossWorkspace*>(workspace);
-  if (grad) {
-    CB200_CUDA_TRY(cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)batch * D * shape.npix, st));
-    oce_loss_fused_kernel<D, CT, OT, true><<<(int)blocks, LOSS_THREADS, 0, st>>>(
-        (const OT*)offsets, (const CT*)anchors, (const CT*)refs, batch, P, shape, 1.0f / T, w, grad, ws, out);
-  } else {
-    oce_loss_fused_kernel<D, CT, OT, false><<<(int)blocks, LOSS_THREADS, 0, st>>>(
-        (const OT*)offsets, (const CT*)anchors, (const CT*)refs, batch, P, shape, 1.0f / T, w, nullptr, ws, out);
+template <int D, typename CT, typename OT, bool BWD, bool IL>
+static int launch_fused_variant(const void* offsets, const void* anchors, const void* refs, int batch,
+                                const Shape<D>& shape, int64_t P, float T, float w, float* grad, float* out,
+                                LossWorkspace* ws, cudaStream_t st) {
+  auto kernel = oce_loss_fused_kernel<D, CT, OT, BWD, IL>;
+  // persistent grid: exactly the CTAs that are co-resident (one wave), split evenly over the samples
+  static int occupancy = 0;  // per template instantiation
+  if (occupancy == 0) {
+    int occ = 0;
+    CB200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, LOSS_THREADS, 0));
+    occupancy = occ > 0 ? occ : 1;
   }
+  const unsigned cps = (unsigned)((P + 31) >> 5);
+  const unsigned per_block = (LOSS_THREADS / 32) * LOSS_UNROLL;
+  unsigned blocks_x = (unsigned)((CB200_SM_COUNT * occupancy) / batch);  // floor: never spill into a second wave
+  const unsigned needed = (cps + per_block - 1) / per_block;
+  if (blocks_x > needed) blocks_x = needed;
+  if (blocks_x < 1) blocks_x = 1;
+  const float log2e = 1.4426950408889634f;
+  kernel<<<dim3(blocks_x, (unsigned)batch), LOSS_THREADS, 0, st>>>(
+      (const OT*)offsets, (const CT*)anchors, (const CT*)refs, (unsigned)P, cps, shape, -log2e / T, 2.0f / T, w, grad,
+      ws, out);
   CB200_LAUNCH_CHECK();
   return CB200_OK;
 }
 
+template <int D, typename CT, typename OT>
+static int launch_fused(const void* offsets, int layout, const void* anchors, const void* refs, int batch,
+                        const int64_t* spatial, int64_t P, float T, float w, float* grad, float* out, void* workspace,
+                        cudaStream_t st) {
+  Shape<D> shape;
+  if (!make_shape<D>(spatial, shape)) return CB200_EINVAL;
+  if (P >= ((int64_t)1 << 31) - 64 || batch > 65535) return CB200_EUNSUPPORTED;
+  auto* ws = static_cast<LossWorkspace*>(workspace);
+  if (grad) {
+    const int rc = zero_fill(grad, (int64_t)batch * D * shape.npix, st);
+    if (rc != CB200_OK) return rc;
+  }
+  const bool il = layout == CB200_LAYOUT_CHANNELS_LAST;
+  if (il && D == 2 && (reinterpret_cast<uintptr_t>(offsets) % (2 * sizeof(OT)) || reinterpret_cast<uintptr_t>(grad) % 8))
+    return CB200_EINVAL;  // vector gathers / vector reductions need pixel-aligned bases
+#define CB200_FUSED(BWD, IL) \
+  launch_fused_variant<D, CT, OT, BWD, IL>(offsets, anchors, refs, batch, shape, P, T, w, grad, out, ws, st)
+  if (grad) return il ? CB200_FUSED(true, true) : CB200_FUSED(true, false);
+  return il ? CB200_FUSED(false, true) : CB200_FUSED(false, false);
+#undef CB200_FUSED
+}
+
 template <int D, typename CT>
-static int dispatch_offsets(const void* offsets, int odt, const void* a, const void* r, int batch,
+static int dispatch_offsets(const void* offsets, int odt, int layout, const void* a, const void* r, int batch,
                             const int64_t* spatial, int64_t P, float T, float w, float* grad, float* out, void* ws,
                             cudaStream_t st) {
-  if (odt == CB200_F32) return launch_fused<D, CT, float>(offsets, a, r, batch, spatial, P, T, w, grad, out, ws, st);
+  if (odt == CB200_F32)
+    return launch_fused<D, CT, float>(offsets, layout, a, r, batch, spatial, P, T, w, grad, out, ws, st);
   if (odt == CB200_BF16)
-    return launch_fused<D, CT, __nv_bfloat16>(offsets, a, r, batch, spatial, P, T, w, grad, out, ws, st);
+    return launch_fused<D, CT, __nv_bfloat16>(offsets, layout, a, r, batch, spatial, P, T, w, grad, out, ws, st);
   return CB200_EUNSUPPORTED;
 }
 
 template <int D>
-static int dispatch_coords(const void* offsets, int odt, const void* a, const void* r, int cdt, int batch,
+static int dispatch_coords(const void* offsets, int odt, int layout, const void* a, const void* r, int cdt, int batch,
                            const int64_t* spatial, int64_t P, float T, float w, float* grad, float* out, void* ws,
                            cudaStream_t st) {
   switch (cdt) {
-    case CB200_I64: return dispatch_offsets<D, long long>(offsets, odt, a, r, batch, spatial, P, T, w, grad, out, ws, st);
-    case CB200_I32: return dispatch_offsets<D, int>(offsets, odt, a, r, batch, spatial, P, T, w, grad, out, ws, st);
-    case CB200_I16: return dispatch_offsets<D, short>(offsets, odt, a, r, batch, spatial, P, T, w, grad, out, ws, st);
+    case CB200_I64: return dispatch_offsets<D, long long>(offsets, odt, layout, a, r, batch, spatial, P, T, w, grad, out, ws, st);
+    case CB200_I32: return dispatch_offsets<D, int>(offsets, odt, layout, a, r, batch, spatial, P, T, w, grad, out, ws, st);
+    case CB200_I16: return dispatch_offsets<D, short>(offsets, odt, layout, a, r, batch, spatial, P, T, w, grad, out, ws, st);
   }
   return CB200_EUNSUPPORTED;
 }
@@ -465,19 +622,21 @@ extern "C" {
 
 int64_t cb200_oce_loss_workspace_bytes(void) { return (int64_t)sizeof(LossWorkspace); }
 
-int cb200_oce_loss_fwd_bwd(const void* offsets, int offsets_dtype, const void* anchors, const void* refs,
-                           int coord_dtype, int batch, int num_dims, const int64_t* spatial, int64_t pairs_per_sample,
+
+int cb200_oce_loss_fwd_bwd(const void* offsets, int offsets_dtype, int offsets_layout, const void* anchors,
+                           const void* refs, int coord_dtype, int batch, int num_dims, const int64_t* spatial, int64_t pairs_per_sample,
                            float temperature, float regularization_weight, float* grad, float* out, void* workspace,
                            void* stream) {
-  if (!offsets || !anchors || !refs || !spatial || !out || !workspace) return CB200_EINVAL;
+  if (!offsets || !spatial || !out || !workspace) return CB200_EINVAL;
   if (batch <= 0 || pairs_per_sample < 0 || !(temperature != 0.f)) return CB200_EINVAL;
+  if (pairs_per_sample > 0 && (!anchors || !refs)) return CB200_EINVAL;  // an empty list may be a null pointer
   if (!coords_aligned(anchors, coord_dtype, num_dims) || !coords_aligned(refs, coord_dtype, num_dims)) return CB200_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   if (num_dims == 2)
-    return dispatch_coords<2>(offsets, offsets_dtype, anchors, refs, coord_dtype, batch, spatial, pairs_per_sample,
+    return dispatch_coords<2>(offsets, offsets_dtype, offsets_layout, anchors, refs, coord_dtype, batch, spatial, pairs_per_sample,
                               temperature, regularization_weight, grad, out, workspace, st);
   if (num_dims == 3)
-    return dispatch_coords<3>(offsets, offsets_dtype, anchors, refs, coord_dtype, batch, spatial, pairs_per_sample,
+    return dispatch_coords<3>(offsets, offsets_dtype, offsets_layout, anchors, refs, coord_dtype, batch, spatial, pairs_per_sample,
                               temperature, regularization_weight, grad, out, workspace, st);
   return CB200_EUNSUPPORTED;
 }
@@ -493,7 +652,9 @@ int cb200_scale_inplace(float* grad, int64_t n, const float* scale, void* stream
 
 int cb200_gather_add_coords(const void* offsets, int offsets_dtype, const void* coords, int coord_dtype, int batch,
                             int num_dims, const int64_t* spatial, int64_t pairs_per_sample, float* out, void* stream) {
-  if (!offsets || !coords || !spatial || !out || batch <= 0 || pairs_per_sample < 0) return CB200_EINVAL;
+  if (!offsets || !spatial || batch <= 0 || pairs_per_sample < 0) return CB200_EINVAL;
+  if (pairs_per_sample == 0) return CB200_OK;
+  if (!coords || !out) return CB200_EINVAL;
   if (!coords_aligned(coords, coord_dtype, num_dims)) return CB200_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
 #define CB200_GATHER(DD)                                                                                          \
@@ -511,7 +672,8 @@ int cb200_gather_add_coords(const void* offsets, int offsets_dtype, const void* 
 
 int cb200_scatter_add_coords(const float* grad_out, const void* coords, int coord_dtype, int batch, int num_dims,
                              const int64_t* spatial, int64_t pairs_per_sample, float* grad_offsets, void* stream) {
-  if (!grad_out || !coords || !spatial || !grad_offsets || batch <= 0 || pairs_per_sample < 0) return CB200_EINVAL;
+  if (!spatial || !grad_offsets || batch <= 0 || pairs_per_sample < 0) return CB200_EINVAL;
+  if (pairs_per_sample > 0 && (!grad_out || !coords)) return CB200_EINVAL;
   if (!coords_aligned(coords, coord_dtype, num_dims)) return CB200_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
 #define CB200_SCATTER(DD)                                                                                     \
@@ -529,7 +691,8 @@ int cb200_scatter_add_coords(const float* grad_out, const void* coords, int coor
 
 int cb200_oce_pair_loss(const float* ea, const float* er, int64_t n_pairs, int num_dims, float temperature,
                         float regularization_weight, float* grad_ea, float* out, void* workspace, void* stream) {
-  if (!ea || !er || !out || !workspace || n_pairs < 0 || !(temperature != 0.f)) return CB200_EINVAL;
+  if (!out || !workspace || n_pairs < 0 || !(temperature != 0.f)) return CB200_EINVAL;
+  if (n_pairs > 0 && (!ea || !er)) return CB200_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   auto* ws = static_cast<LossWorkspace*>(workspace);
   const int blocks = grid_for(n_pairs, LOSS_THREADS, 4);

@@ -97,19 +97,30 @@ def _check_loss_inputs(offsets, coords_list):
     return B, D
 
 
+def _offsets_layout(offsets):
+    """Planar (contiguous NCHW/NCDHW) or channels-last, both zero-copy; anything else is made contiguous."""
+    if offsets.is_contiguous():
+        return offsets, _cabi.LAYOUT_PLANAR
+    cl = torch.channels_last if offsets.ndim == 4 else torch.channels_last_3d
+    if offsets.is_contiguous(memory_format=cl):
+        return offsets, _cabi.LAYOUT_CHANNELS_LAST
+    return offsets.contiguous(), _cabi.LAYOUT_PLANAR
+
+
 def oce_loss_fwd_bwd(offsets, anchors, refs, temperature, regularization_weight, want_grad=True):
     """`cb200_oce_loss_fwd_bwd`: returns `(out4, grad)`; out4 = [loss, oce, reg, n_bad] (fp32, device)."""
     B, D = _check_loss_inputs(offsets, [anchors, refs])
-    offsets = offsets.contiguous()
+    offsets, layout = _offsets_layout(offsets)
     anchors = anchors.contiguous()
     refs = refs.contiguous()
     odt = _code(offsets, _OFFSET_DTYPES)
     cdt = _code(anchors, _COORD_DTYPES)
     out = torch.empty(4, dtype=torch.float32, device=offsets.device)
-    grad = torch.empty(offsets.shape, dtype=torch.float32, device=offsets.device) if want_grad else None
+    # the gradient is produced in the memory layout of `offsets` (empty_like preserves channels_last)
+    grad = torch.empty_like(offsets, dtype=torch.float32) if want_grad else None
     ws = _zero_workspace("loss", _lib().cb200_oce_loss_workspace_bytes(), offsets.device)
     rc = _lib().cb200_oce_loss_fwd_bwd(
-        _ptr(offsets), odt, _ptr(anchors), _ptr(refs), cdt, B, D, spatial_array(offsets.shape[2:]),
+        _ptr(offsets), odt, layout, _ptr(anchors), _ptr(refs), cdt, B, D, spatial_array(offsets.shape[2:]),
         anchors.shape[1], float(temperature), float(regularization_weight), _ptr(grad), _ptr(out), _ptr(ws),
         _stream(offsets))
     check(rc, "cb200_oce_loss_fwd_bwd")
@@ -119,7 +130,9 @@ def oce_loss_fwd_bwd(offsets, anchors, refs, temperature, regularization_weight,
 
 def scale_inplace(grad: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
     _require_cuda(grad, scale)
-    assert grad.dtype == torch.float32 and grad.is_contiguous() and scale.dtype == torch.float32
+    dense = grad.is_contiguous() or (grad.ndim in (4, 5) and grad.is_contiguous(
+        memory_format=torch.channels_last if grad.ndim == 4 else torch.channels_last_3d))
+    assert grad.dtype == torch.float32 and dense and scale.dtype == torch.float32
     check(_lib().cb200_scale_inplace(_ptr(grad), grad.numel(), _ptr(scale), _stream(grad)), "cb200_scale_inplace")
     launch_counter["calls"] += 1
     return grad

@@ -48,6 +48,10 @@ extern "C" {
 #define CB200_U8 6
 #define CB200_U16 7
 
+/* memory layout of a (B, D, *spatial) tensor */
+#define CB200_LAYOUT_PLANAR 0
+#define CB200_LAYOUT_CHANNELS_LAST 1
+
 /* library / build information: returns the sm arch the kernels were built for (100) */
 CB200_API int cb200_version(int* major, int* minor, int* sm_arch);
 /* last CUDA error string for a positive return code */
@@ -68,10 +72,13 @@ CB200_API int64_t cb200_oce_loss_workspace_bytes(void);
  *     OCELoss.forward(ea, er)                        criterions/oce_loss.py:53-63
  *     loss.backward()  (gather backward = scatter-add onto the anchor pixel)
  *
- *  offsets      (B, D, *spatial) contiguous, CB200_F32 or CB200_BF16
+ *  offsets      CB200_F32 or CB200_BF16; offsets_layout says how the (B, D, *spatial) tensor lies in memory:
+ *               CB200_LAYOUT_PLANAR = contiguous NCHW / NCDHW (what the reference's model emits),
+ *               CB200_LAYOUT_CHANNELS_LAST = contiguous (B, *spatial, D) (torch channels_last): one
+ *               vector load fetches a whole embedding, which halves the gather traffic
  *  anchors/refs (B, P, D) contiguous, CB200_I64 (as the reference delivers
  *               them), CB200_I32 or CB200_I16; columns (x, y[, z])
- *  grad         (B, D, *spatial) fp32, OVERWRITTEN with d loss / d offsets
+ *  grad         fp32, same layout as offsets, OVERWRITTEN with d loss / d offsets
  *               (zero-filled by this call, then accumulated); may be NULL to
  *               run the forward only
  *  out          4 floats: loss, oce_loss, regularization_loss, number of
@@ -79,7 +86,7 @@ CB200_API int64_t cb200_oce_loss_workspace_bytes(void);
  *  workspace    cb200_oce_loss_workspace_bytes() bytes, zero-initialised ONCE
  *               by the caller (the kernel leaves it zeroed again)
  */
-CB200_API int cb200_oce_loss_fwd_bwd(const void* offsets, int offsets_dtype,
+CB200_API int cb200_oce_loss_fwd_bwd(const void* offsets, int offsets_dtype, int offsets_layout,
                            const void* anchors, const void* refs, int coord_dtype,
                            int batch, int num_dims, const int64_t* spatial /* host, num_dims */,
                            int64_t pairs_per_sample,

@@ -1,0 +1,36 @@
+"""Small driver for ncu captures: a few fused-loss steps (config #2) and one detect volume (config #3)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from cellulus_b200 import kernels as K  # noqa: E402
+from cellulus_b200 import synthetic  # noqa: E402
+from cellulus_b200.detect import detect_embeddings  # noqa: E402
+from cellulus_b200.models import tta_aggregate  # noqa: E402
+
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+dev = torch.device("cuda:0")
+torch.cuda.set_device(dev)
+if what in ("all", "loss"):
+    offsets = torch.randn(bench.B, bench.D, *bench.OUT, device=dev)
+    anchors, refs = K.sample_pairs(bench.B, (bench.OUT[1], bench.OUT[0]), bench.KAPPA, bench.N_ANCHORS, bench.N_REFS,
+                                   seed=1, device=dev)
+    for _ in range(4):
+        K.oce_loss_fwd_bwd(offsets, anchors, refs, bench.TEMP, bench.REGW)
+    torch.cuda.synchronize()
+if what in ("all", "tta"):
+    stack = torch.randn(32, 2, 496, 496, device=dev)
+    for _ in range(3):
+        tta_aggregate(stack)
+    torch.cuda.synchronize()
+if what in ("all", "detect"):
+    emb, _, _ = synthetic.blob_scene(bench.DET_SHAPE, bench.DET_OBJECTS, radius=bench.DET_RADIUS, seed=0)
+    d = torch.from_numpy(emb).to(dev)
+    for _ in range(2):
+        detect_embeddings(d, bandwidth=bench.DET_BW, threshold=bench.DET_THR, reduction_probability=bench.DET_RP,
+                          rng="philox")
+    torch.cuda.synchronize()
