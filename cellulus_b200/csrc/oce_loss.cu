@@ -75,9 +75,7 @@ __device__ __forceinline__ int pixel_of(const int (&c)[D], const Shape<D>& s) {
   return (c[2] * s.ext[1] + c[1]) * s.ext[0] + c[0];
 }
 
-#ifndef CB200_LOSS_UNROLL
 #define CB200_LOSS_UNROLL 1
-#endif
 #ifndef CB200_LOSS_MIN_BLOCKS
 #define CB200_LOSS_MIN_BLOCKS 6  // <= 40 registers: 48 resident warps per SM (measured best, tools/loss_sweep.py)
 #endif
@@ -217,92 +215,98 @@ __device__ __forceinline__ void scatter_pixel(float* __restrict__ gbase, int npi
   }
 }
 
-// ---- per-chunk work shared by both kernels --------------------------------------------------------
-// U chunks of 32 pairs: range-check (fast path: one unsigned compare per coordinate; the rare negative
-// index takes the wrapping slow path, as torch advanced indexing would), issue all gathers, then the
-// pair terms, the segmented warp sum of the gradients and one reduction per run of equal anchors.
-template <int D, typename OT, bool BWD, bool IL, int U>
-__device__ __forceinline__ void process_chunks(int (&ca)[U][D], int (&cr)[U][D], bool (&live)[U],
-                                               const OT* __restrict__ off_b, float* __restrict__ grad_b,
-                                               const Shape<D>& shape, float neg_log2e_over_t, float two_over_t,
-                                               float w, unsigned lane, float& acc_oce, float& acc_nrm, int& bad) {
-  float oa[U][D], orf[U][D];
-  int pix_a[U];
+// ---- one chunk = 32 consecutive pairs of one sample, one pair per lane -----------------------------
+template <int D>
+struct Chunk {
+  int ca[D], cr[D];  // anchor / reference coordinates as delivered
+  float oa[D], orf[D];  // gathered offsets
+  int pix_a;            // anchor pixel (run key); negative for dead lanes
+  bool live;
+};
+
+// Stage 1: range-check (fast path: one unsigned compare per coordinate; the rare negative index takes the
+// wrapping slow path, as torch advanced indexing would) and ISSUE the gathers.  Nothing here waits.
+template <int D, typename OT, bool IL>
+__device__ __forceinline__ void chunk_gather(Chunk<D>& c, const OT* __restrict__ off_b, const Shape<D>& shape,
+                                             int& bad) {
+  bool ok = true;
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    bool ok = true;
-#pragma unroll
-    for (int k = 0; k < D; ++k)
-      ok = ok && ((unsigned)ca[u][k] < (unsigned)shape.ext[k]) && ((unsigned)cr[u][k] < (unsigned)shape.ext[k]);
-    int pa, pr;
-    if (__builtin_expect(__any_sync(FULL, live[u] && !ok), 0)) {
-      int wa[D], wr[D];
-      ok = wrap_and_check<D>(ca[u], wa, shape) & wrap_and_check<D>(cr[u], wr, shape);
-      pa = pixel_of<D>(wa, shape);
-      pr = pixel_of<D>(wr, shape);
-    } else {
-      pa = pixel_of<D>(ca[u], shape);
-      pr = pixel_of<D>(cr[u], shape);
-    }
-    if (live[u] && !ok) ++bad;
-    live[u] = live[u] && ok;
-    pix_a[u] = live[u] ? pa : -1 - u;  // dead lanes never merge with a live neighbour
-    if (live[u]) {
-      gather_pixel<D, OT, IL>(off_b, (int)shape.npix, pa, oa[u]);
-      gather_pixel<D, OT, IL>(off_b, (int)shape.npix, pr, orf[u]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < D; ++k) oa[u][k] = orf[u][k] = 0.f;
-    }
+  for (int k = 0; k < D; ++k)
+    ok = ok && ((unsigned)c.ca[k] < (unsigned)shape.ext[k]) && ((unsigned)c.cr[k] < (unsigned)shape.ext[k]);
+  int pa, pr;
+  if (__builtin_expect(__any_sync(FULL, c.live && !ok), 0)) {
+    int wa[D], wr[D];
+    ok = wrap_and_check<D>(c.ca, wa, shape) & wrap_and_check<D>(c.cr, wr, shape);
+    pa = pixel_of<D>(wa, shape);
+    pr = pixel_of<D>(wr, shape);
+    if (c.live && !ok) ++bad;
+  } else {
+    pa = pixel_of<D>(c.ca, shape);
+    pr = pixel_of<D>(c.cr, shape);
   }
+  c.live = c.live && ok;
+  c.pix_a = c.live ? pa : -1;  // dead lanes never merge with a live neighbour
+  if (c.live) {
+    gather_pixel<D, OT, IL>(off_b, (int)shape.npix, pa, c.oa);
+    gather_pixel<D, OT, IL>(off_b, (int)shape.npix, pr, c.orf);
+  } else {
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    float g[D], diff[D], ea[D];
-    float d2 = 0.f, n2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-      ea[k] = __fadd_rn(oa[u][k], (float)ca[u][k]);  // selection += coordinate (models/unet.py:120)
-      const float er = __fadd_rn(orf[u][k], (float)cr[u][k]);
-      diff[k] = ea[k] - er;
-      d2 = fmaf(diff[k], diff[k], d2);
-      n2 = fmaf(ea[k], ea[k], n2);
-    }
-    const float e = ex2_approx(d2 * neg_log2e_over_t);   // exp(-d^2 / T)
-    const float rs = n2 > 0.f ? rsqrt_approx(n2) : 0.f;  // 1 / ||ea||, 0 at the origin (torch's norm backward)
-    if (live[u]) {
-      acc_oce += 1.0f - e;
-      acc_nrm = fmaf(n2, rs, acc_nrm);  // ||ea||
-    }
-    if constexpr (BWD) {
-      const float ge = two_over_t * e;
-      const float gr = w * rs;
-#pragma unroll
-      for (int k = 0; k < D; ++k) g[k] = live[u] ? fmaf(ge, diff[k], gr * ea[k]) : 0.f;
-      // segmented sum over runs of equal anchor pixel; only run heads touch memory
-      const int key = pix_a[u];
-      const int prev = __shfl_up_sync(FULL, key, 1);
-      const bool head = (lane == 0) || (prev != key);
-      const unsigned heads = __ballot_sync(FULL, head);
-      const unsigned above = heads & (0xfffffffeu << lane);
-      const unsigned limit = above ? (unsigned)(__ffs(above) - 1) : 32u;
-#pragma unroll
-      for (unsigned o = 1; o < 32; o <<= 1) {
-        const bool take = lane + o < limit;
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-          const float v = __shfl_down_sync(FULL, g[k], o);
-          if (take) g[k] += v;
-        }
-      }
-      if (head && live[u]) scatter_pixel<D, IL>(grad_b, (int)shape.npix, key, g);
-    }
+    for (int k = 0; k < D; ++k) c.oa[k] = c.orf[k] = 0.f;
   }
 }
 
-// ---- the fused kernel: direct streaming loads, register double buffer ------------------------------
-// One warp owns LOSS_UNROLL chunks of 32 consecutive pairs of ONE sample (blockIdx.y) per iteration.
-// Iteration i+1's coordinates are fetched before iteration i's gathers are issued, so the HBM latency
-// of the lists hides behind the L2 gathers and the math.
+// Stage 2: the pair terms, the segmented warp sum of the gradients over runs of equal anchor pixel, and
+// one reduction per run.
+template <int D, bool BWD, bool IL>
+__device__ __forceinline__ void chunk_finish(const Chunk<D>& c, float* __restrict__ grad_b, const Shape<D>& shape,
+                                             float neg_log2e_over_t, float two_over_t, float w, unsigned lane,
+                                             float& acc_oce, float& acc_nrm) {
+  float g[D], diff[D], ea[D];
+  float d2 = 0.f, n2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    ea[k] = __fadd_rn(c.oa[k], (float)c.ca[k]);  // selection += coordinate (models/unet.py:120)
+    const float er = __fadd_rn(c.orf[k], (float)c.cr[k]);
+    diff[k] = ea[k] - er;
+    d2 = fmaf(diff[k], diff[k], d2);
+    n2 = fmaf(ea[k], ea[k], n2);
+  }
+  const float e = ex2_approx(d2 * neg_log2e_over_t);   // exp(-d^2 / T)
+  const float rs = n2 > 0.f ? rsqrt_approx(n2) : 0.f;  // 1 / ||ea||, 0 at the origin (torch's norm backward)
+  if (c.live) {
+    acc_oce += 1.0f - e;
+    acc_nrm = fmaf(n2, rs, acc_nrm);  // ||ea||
+  }
+  if constexpr (BWD) {
+    const float ge = two_over_t * e;
+    const float gr = w * rs;
+#pragma unroll
+    for (int k = 0; k < D; ++k) g[k] = c.live ? fmaf(ge, diff[k], gr * ea[k]) : 0.f;
+    const int key = c.pix_a;
+    const int prev = __shfl_up_sync(FULL, key, 1);
+    const bool head = (lane == 0) || (prev != key);
+    const unsigned heads = __ballot_sync(FULL, head);
+    const unsigned above = heads & (0xfffffffeu << lane);
+    const unsigned limit = above ? (unsigned)(__ffs(above) - 1) : 32u;
+#pragma unroll
+    for (unsigned o = 1; o < 32; o <<= 1) {
+      const bool take = lane + o < limit;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        const float v = __shfl_down_sync(FULL, g[k], o);
+        if (take) g[k] += v;
+      }
+    }
+    if (head && c.live) scatter_pixel<D, IL>(grad_b, (int)shape.npix, key, g);
+  }
+}
+
+// ---- the fused kernel ------------------------------------------------------------------------------
+// One warp owns one chunk per iteration.  The coordinates of the chunk after next are always in flight from
+// HBM (streaming 16-byte loads into a raw register buffer that is converted only when taken), so the list
+// latency hides behind the gathers and the math; the L2 gather latency is covered by the 48 resident warps
+// per SM.  (Issuing the next chunk's gathers before the current chunk's math, and a warp-specialised
+// cp.async.bulk ring for the lists, were both built and measured SLOWER: see profiles/README.md.)
 template <int D, typename CT, typename OT, bool BWD, bool IL>
 __global__ void __launch_bounds__(LOSS_THREADS, LOSS_MIN_BLOCKS)
 oce_loss_fused_kernel(const OT* __restrict__ offsets, const CT* __restrict__ anchors, const CT* __restrict__ refs,
@@ -310,7 +314,7 @@ oce_loss_fused_kernel(const OT* __restrict__ offsets, const CT* __restrict__ anc
                       float w, float* __restrict__ grad, LossWorkspace* ws, float* out) {
   const unsigned lane = lane_id();
   const unsigned b = blockIdx.y;
-  const unsigned warp_stride = gridDim.x * (LOSS_THREADS / 32) * LOSS_UNROLL;
+  const unsigned stride = gridDim.x * (LOSS_THREADS / 32);
   const CT* __restrict__ a_base = anchors + (size_t)b * P * D;
   const CT* __restrict__ r_base = refs + (size_t)b * P * D;
   const OT* __restrict__ off_b = offsets + (size_t)b * D * shape.npix;
@@ -319,48 +323,57 @@ oce_loss_fused_kernel(const OT* __restrict__ offsets, const CT* __restrict__ anc
   float acc_oce = 0.f, acc_nrm = 0.f;
   int bad = 0;
 
-  RawCoord<D, CT> na[LOSS_UNROLL], nr[LOSS_UNROLL];
-  auto fetch = [&](unsigned c0) {
+  RawCoord<D, CT> na, nr;  // coordinates of the chunk after next, as loaded
+  auto fetch = [&](unsigned c) {
+    const unsigned p = (c << 5) + lane;
+    if (c < chunks_per_sample && p < P) {
+      na.load(a_base, p);
+      nr.load(r_base, p);
+    } else {
+      na.zero();
+      nr.zero();
+    }
+  };
+  auto take = [&](Chunk<D>& ch, unsigned c) {
+    ch.live = c < chunks_per_sample && ((c << 5) + lane) < P;
 #pragma unroll
-    for (int u = 0; u < LOSS_UNROLL; ++u) {
-      const unsigned p = ((c0 + u) << 5) + lane;
-      if (p < P) {
-        na[u].load(a_base, p);
-        nr[u].load(r_base, p);
-      } else {
-        na[u].zero();
-        nr[u].zero();
-      }
+    for (int k = 0; k < D; ++k) {
+      ch.ca[k] = na.get(k);
+      ch.cr[k] = nr.get(k);
     }
   };
 
-  unsigned c0 = (blockIdx.x * (LOSS_THREADS / 32) + (threadIdx.x >> 5)) * LOSS_UNROLL;
-  if (c0 < chunks_per_sample) fetch(c0);
-  for (; c0 < chunks_per_sample; c0 += warp_stride) {
-    int ca[LOSS_UNROLL][D], cr[LOSS_UNROLL][D];
-    bool live[LOSS_UNROLL];
-#pragma unroll
-    for (int u = 0; u < LOSS_UNROLL; ++u) {
-      live[u] = (((c0 + u) << 5) + lane) < P;
-#pragma unroll
-      for (int k = 0; k < D; ++k) {
-        ca[u][k] = na[u].get(k);
-        cr[u][k] = nr[u].get(k);
-      }
+  unsigned c0 = blockIdx.x * (LOSS_THREADS / 32) + (threadIdx.x >> 5);
+  if (c0 < chunks_per_sample) {
+    Chunk<D> cur, nxt;
+    fetch(c0);
+    take(cur, c0);
+    fetch(c0 + stride);
+    chunk_gather<D, OT, IL>(cur, off_b, shape, bad);
+    for (; c0 < chunks_per_sample; c0 += stride) {
+      chunk_finish<D, BWD, IL>(cur, grad_b, shape, neg_log2e_over_t, two_over_t, w, lane, acc_oce, acc_nrm);
+      take(nxt, c0 + stride);
+      fetch(c0 + 2 * stride);
+      if (c0 + stride < chunks_per_sample) chunk_gather<D, OT, IL>(nxt, off_b, shape, bad);
+      cur = nxt;
     }
-    if (c0 + warp_stride < chunks_per_sample) fetch(c0 + warp_stride);  // prefetch the next iteration
-    process_chunks<D, OT, BWD, IL, LOSS_UNROLL>(ca, cr, live, off_b, grad_b, shape, neg_log2e_over_t, two_over_t, w,
-                                                lane, acc_oce, acc_nrm, bad);
   }
   block_reduce_to_workspace(acc_oce, acc_nrm, bad, ws, w, out);
 }
 
-// zero-fill of the gradient tensor (16-byte stores, one wave)
+// zero-fill of the gradient tensor: 4 independent 16-byte stores per thread per trip, one wave
 __global__ void __launch_bounds__(256) zero_fill_kernel(float4* __restrict__ p, int64_t n4, float* __restrict__ tail,
                                                         int n_tail) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) p[i] = z;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    p[i] = z;
+    p[i + stride] = z;
+    p[i + 2 * stride] = z;
+    p[i + 3 * stride] = z;
+  }
+  for (; i < n4; i += stride) p[i] = z;
   if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) tail[threadIdx.x] = 0.f;
 }
 static int zero_fill(float* p, int64_t n, cudaStream_t st) {
@@ -370,7 +383,7 @@ static int zero_fill(float* p, int64_t n, cudaStream_t st) {
     return CB200_OK;
   }
   const int64_t n4 = n / 4;
-  zero_fill_kernel<<<grid_for(n4, 256, 4, 8), 256, 0, st>>>(reinterpret_cast<float4*>(p), n4, p + n4 * 4, (int)(n - n4 * 4));
+  zero_fill_kernel<<<grid_for(n4, 256, 4, 4), 256, 0, st>>>(reinterpret_cast<float4*>(p), n4, p + n4 * 4, (int)(n - n4 * 4));
   CB200_LAUNCH_CHECK();
   return CB200_OK;
 }

@@ -10,7 +10,7 @@
 
 namespace cb200 {
 
-constexpr int TTA_THREADS = 256;
+constexpr int TTA_THREADS = 128;
 constexpr int TTA_MAXC = 4;
 
 struct Welford4 {
@@ -31,35 +31,43 @@ struct Welford4 {
   }
 };
 
-// One thread owns 4 consecutive pixels of every channel.
+// One thread owns 4 consecutive pixels of every channel.  The T passes are consumed in batches of U; batch
+// b+1 is loaded (U*C independent 16-byte requests) BEFORE batch b is folded into the Welford state, so the
+// HBM stream never drains even when the block being aggregated is small (a 496x496 scan block is only 61 k
+// threads -- 20 % occupancy -- and must live on memory-level parallelism, not on warps).
 template <int C>
 __global__ void __launch_bounds__(TTA_THREADS)
 tta_aggregate_kernel(const float* __restrict__ stack, int T, int64_t n, int64_t n4, float* __restrict__ out) {
+  constexpr int U = 8 / C > 0 ? 8 / C : 1;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const float inv_T = 1.0f / (float)T;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     Welford4 w[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) w[c].init();
-    constexpr int U = 8 / C > 0 ? 8 / C : 1;  // passes fetched per batch: ~8 independent 16-byte loads
-    int t = 0;
-    for (; t + U <= T; t += U) {
-      float4 v[U][C];
+    float4 cur[U][C], nxt[U][C];
+    auto load = [&](float4 (&v)[U][C], int t0) {
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int c = 0; c < C; ++c) v[u][c] = ld_stream_f4(stack + ((int64_t)(t + u) * C + c) * n + i * 4);
+        for (int c = 0; c < C; ++c)
+          if (t0 + u < T) v[u][c] = ld_stream_f4(stack + ((int64_t)(t0 + u) * C + c) * n + i * 4);
+    };
+    load(cur, 0);
+    for (int t = 0; t < T; t += U) {
+      if (t + U < T) load(nxt, t + U);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const float inv = 1.0f / (float)(t + u + 1);
+        if (t + u < T) {
+          const float inv = 1.0f / (float)(t + u + 1);
 #pragma unroll
-        for (int c = 0; c < C; ++c) w[c].push(v[u][c], inv);
+          for (int c = 0; c < C; ++c) w[c].push(cur[u][c], inv);
+        }
       }
-    }
-    for (; t < T; ++t) {
-      const float inv = 1.0f / (float)(t + 1);
 #pragma unroll
-      for (int c = 0; c < C; ++c) w[c].push(ld_stream_f4(stack + ((int64_t)t * C + c) * n + i * 4), inv);
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int c = 0; c < C; ++c) cur[u][c] = nxt[u][c];
     }
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -72,7 +80,6 @@ tta_aggregate_kernel(const float* __restrict__ stack, int T, int64_t n, int64_t 
     }
     st_stream_f4(out + (int64_t)C * n + i * 4, s);
   }
-  // scalar tail (n not a multiple of 4, or unaligned planes): handled by the generic kernel
 }
 
 // Generic scalar fallback: any C <= TTA_MAXC, any n / alignment; `first` = first pixel handled.

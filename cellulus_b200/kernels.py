@@ -412,30 +412,50 @@ def ms_brute_modes(points, n, seeds_soa, n_seeds, bandwidth, max_iter=300):
     return counts, iters
 
 
-def nms_centres(modes_soa, counts, n_seeds, bandwidth, grid: Grid):
-    """sklearn:511-547 on the device.  Returns `(centres (D, n_seeds) SoA in priority order, K)`."""
+def nms_centres(modes_soa, counts, n_seeds, bandwidth, grid: Grid, rounds_per_call: int = 4):
+    """sklearn:511-547 on the device.  Returns `(centres (D, cap) SoA in `cluster_centers_` order, K)`.
+    One host sync per call of `rounds_per_call` rounds (the fix-point takes 2-3 rounds in practice)."""
     dev = modes_soa.device
     D = modes_soa.shape[0]
-    centres = torch.empty((D, n_seeds), dtype=torch.float64, device=dev)
     out2 = torch.zeros(2, dtype=torch.int32, device=dev)
-    nbytes = _lib().cb200_nms_workspace_bytes(n_seeds, D, grid.n_cells)
+    nbytes = _lib().cb200_nms_workspace_bytes(n_seeds, C.byref(grid), float(bandwidth))
+    if nbytes < 0:
+        raise _cabi.CellulusB200Error("the bounding box of the modes is too large for the suppression grid")
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    rc = _lib().cb200_nms_centres(_ptr(modes_soa), modes_soa.stride(0), D, _ptr(counts), n_seeds, float(bandwidth),
-                                  C.byref(grid), _ptr(centres), _ptr(out2), _ptr(ws), nbytes, _stream(modes_soa))
-    check(rc, "cb200_nms_centres")
-    launch_counter["calls"] += 1
-    k, undecided = (int(v) for v in out2.tolist())
-    if undecided:
-        raise _cabi.CellulusB200Error(
-            f"centre suppression did not reach its fix-point ({undecided} undecided after the built-in rounds)")
+    resume = 0
+    for _ in range(64):
+        rc = _lib().cb200_nms_suppress(_ptr(modes_soa), modes_soa.stride(0), D, _ptr(counts), n_seeds,
+                                       float(bandwidth), C.byref(grid), int(rounds_per_call), resume, _ptr(out2),
+                                       _ptr(ws), nbytes, _stream(modes_soa))
+        check(rc, "cb200_nms_suppress")
+        launch_counter["calls"] += 1
+        k, undecided = (int(x) for x in out2.tolist())
+        if undecided == 0:
+            break
+        resume = 1
+    else:
+        raise _cabi.CellulusB200Error("centre suppression did not reach its fix-point")
+    cap = max(2, (k + 1) & ~1)
+    centres = torch.zeros((D, cap), dtype=torch.float64, device=dev)
+    if k:
+        rc = _lib().cb200_nms_emit(_ptr(modes_soa), modes_soa.stride(0), D, _ptr(counts), n_seeds, float(bandwidth),
+                                   C.byref(grid), k, _ptr(centres), cap, _ptr(ws), nbytes, _stream(modes_soa))
+        check(rc, "cb200_nms_emit")
+        launch_counter["calls"] += 1
     return centres, k
 
 
-def assign_labels(points, n, centres, k, pix_index, labels_out):
-    """labels_out[pix_index[i]] = 1 + nearest centre (ties -> lowest index); labels_out int32 or uint16."""
+def assign_labels(points, n, centres, k, pix_index, labels_out, grid: Optional[Grid] = None):
+    """labels_out[pix_index[i]] = 1 + nearest centre (ties -> lowest index); labels_out int32 or uint16.
+    With `grid` (cells of edge >= bandwidth covering the centres) the search is pruned to 3^D cells."""
+    ws = None
+    if grid is not None:
+        nbytes = _lib().cb200_assign_workspace_bytes(n, int(k), grid.n_cells)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=points.device)
     rc = _lib().cb200_assign_labels(_ptr(points), n, points.stride(0), points.shape[0], _ptr(centres),
-                                    centres.stride(0), int(k), _ptr(pix_index), _ptr(labels_out),
-                                    _code(labels_out, (torch.int32, torch.uint16)), _stream(points))
+                                    centres.stride(0), int(k), C.byref(grid) if grid is not None else None,
+                                    _ptr(pix_index), _ptr(labels_out),
+                                    _code(labels_out, (torch.int32, torch.uint16)), _ptr(ws), _stream(points))
     check(rc, "cb200_assign_labels")
     launch_counter["calls"] += 1
     return labels_out

@@ -1,0 +1,181 @@
+"""Multi-GPU sharding of the hot path (one process per GPU, `torch.distributed`).
+
+The path shards three ways, none of which needs a collective on the data path
+except the last:
+
+* training: by batch -- the loss kernel is rank-local (the loss is a plain sum over samples,
+  `criterions/oce_loss.py:58-62`); only the U-Net's parameter gradients are all-reduced (DDP).
+* inference over many samples / scan blocks: independent units (`detect.py:82`, `predict.py:129`),
+  dealt round-robin or in contiguous ranges -> `shard_items`, `shard_round_robin`, `scan_blocks`.
+* ONE huge volume: seeds are independent given the full point set (sklearn `_mean_shift.py:506-509`).
+  Each rank compacts its slab, the point sets are all-gathered, every rank climbs its slice of the
+  seeds, the converged (mode, count) lists are all-gathered, centre suppression is replicated
+  (deterministic) and labels are assigned per slab -> `sharded_mean_shift`.
+
+The functions take the compute steps as callables so the same composition runs on the CUDA kernels
+(NCCL) and, in the CPU tests, on the oracle (gloo, world_size 2).
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_items(n_items: int, rank: int, world: int) -> range:
+    """Contiguous balanced range of `n_items` units for `rank` (the first n % world ranks get one more)."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return range(lo, lo + base + (1 if rank < extra else 0))
+
+
+def shard_round_robin(n_items: int, rank: int, world: int) -> range:
+    """Units rank, rank + world, ... (scan blocks of similar cost are dealt like cards)."""
+    return range(rank, n_items, world)
+
+
+def scan_blocks(spatial: Sequence[int], block: Sequence[int]) -> List[Tuple[int, ...]]:
+    """Offsets of the output blocks a gunpowder `Scan` visits (`predict.py:62-93,129`): strides of the
+    block size, the last block of every axis shifted INWARD (not shrunk) so that it ends at the border.
+    A block larger than the volume is clamped to offset 0."""
+    axes = []
+    for s, b in zip(spatial, block):
+        if b >= s:
+            axes.append([0])
+            continue
+        offs = list(range(0, s - b + 1, b))
+        if offs[-1] + b < s:
+            offs.append(s - b)
+        axes.append(offs)
+    out = [()]
+    for offs in axes:
+        out = [o + (v,) for o in out for v in offs]
+    return out
+
+
+def _world(group) -> Tuple[int, int]:
+    if not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def all_gather_columns(local: torch.Tensor, n_local: int, group=None) -> Tuple[torch.Tensor, List[int]]:
+    """All-gather of a ragged SoA array: `local` is (R, >= n_local); returns ((R, sum n), counts per rank),
+    rank-major.  Works on CPU tensors over gloo and CUDA tensors over NCCL (pads to the largest shard)."""
+    rank, world = _world(group)
+    if world == 1:
+        return local[:, :n_local].contiguous(), [n_local]
+    counts_t = torch.zeros(world, dtype=torch.int64, device=local.device)
+    counts_t[rank] = n_local
+    dist.all_reduce(counts_t, group=group)
+    counts = [int(c) for c in counts_t.tolist()]
+    width = max(max(counts), 1)
+    send = torch.zeros((local.shape[0], width), dtype=local.dtype, device=local.device)
+    send[:, :n_local] = local[:, :n_local]
+    recv = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(recv, send, group=group)
+    return torch.cat([r[:, :c] for r, c in zip(recv, counts)], dim=1).contiguous(), counts
+
+
+@dataclass
+class MeanShiftOps:
+    """The compute steps `sharded_mean_shift` composes (CUDA kernels in production, oracle in CPU tests).
+
+    climb(points (D,n), seeds (D,s), bandwidth)           -> (modes (D,s), counts (s,), iters (s,))
+    suppress(modes (D,s), counts (s,), bandwidth, points)  -> centres (D,k) in priority order
+    assign(points (D,n), centres (D,k))                    -> labels (n,) int, 1 + nearest centre
+    """
+
+    climb: Callable
+    suppress: Callable
+    assign: Callable
+
+
+def sharded_mean_shift(local_points: torch.Tensor, n_local: int, bandwidth: float, ops: MeanShiftOps,
+                       local_fit_flags: Optional[torch.Tensor] = None, group=None):
+    """Mean-shift of one point set that is spread over the ranks (slab order = rank order).
+
+    local_points (D, >= n_local) float64 SoA: this rank's foreground points in raster order.
+    local_fit_flags (n_local,) uint8/bool or None: which of them take part in `fit` (the
+    `reduction_probability` subset, `utils/mean_shift.py:68-70`).
+    Returns `(labels_local (n_local,), centres (D, k))`; identical to running the single-GPU pipeline on
+    the concatenated point set.
+    """
+    rank, world = _world(group)
+    D = local_points.shape[0]
+    if local_fit_flags is None:
+        fit_local, n_fit_local = local_points[:, :n_local], n_local
+    else:
+        keep = local_fit_flags[:n_local].to(torch.bool)
+        fit_local = local_points[:, :n_local][:, keep]
+        n_fit_local = int(keep.sum())
+    # exchange 1: every rank needs the whole fit set (N x D doubles; O(ms) over NVSwitch)
+    fit_all, _ = all_gather_columns(fit_local.contiguous(), n_fit_local, group)
+    n_fit = fit_all.shape[1]
+    if n_fit == 0:
+        raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required by MeanShift.")
+    # seeds = all fit points (sklearn:491-496), split evenly; raster order keeps neighbours together
+    mine = shard_items(n_fit, rank, world)
+    seeds = fit_all[:, mine.start:mine.stop].contiguous()
+    modes, counts, _ = ops.climb(fit_all, seeds, bandwidth)
+    # exchange 2: converged (mode, count) of every seed, in global seed order
+    packed = torch.cat([modes[:, :len(mine)], counts[:len(mine)].to(modes.dtype)[None]], dim=0)
+    packed_all, _ = all_gather_columns(packed.contiguous(), len(mine), group)
+    modes_all = packed_all[:D].contiguous()
+    counts_all = packed_all[D].round().to(torch.int32).contiguous()
+    # centre suppression is deterministic: replicate it instead of broadcasting its result
+    centres = ops.suppress(modes_all, counts_all, bandwidth, fit_all)
+    labels = ops.assign(local_points[:, :n_local].contiguous(), centres)
+    return labels, centres
+
+
+def cuda_ops(method: str = "auto") -> MeanShiftOps:
+    """`MeanShiftOps` on the B200 kernels."""
+    from cellulus_b200 import kernels as K
+    from cellulus_b200.utils import mean_shift as MS
+
+    def pad(t):  # kernels want an even stride (16-byte bulk copies)
+        n = t.shape[1]
+        cap = max(2, (n + 1) & ~1)
+        if t.stride(0) == cap and t.is_contiguous():
+            return t
+        out = torch.zeros((t.shape[0], cap), dtype=torch.float64, device=t.device)
+        out[:, :n] = t
+        return out
+
+    def climb(points, seeds, bandwidth):
+        n, s = points.shape[1], seeds.shape[1]
+        pts, sd = pad(points), pad(seeds)
+        use = method
+        if use == "auto":
+            use = "brute" if n * s <= MS._BRUTE_PAIR_LIMIT else "grid"
+        if use == "grid":
+            lo, hi = K.bounding_box(pts, n)
+            grid = K.plan_grid(lo, hi, bandwidth)
+            sorted_pts, cell_start, _ = K.grid_build(pts, n, grid)
+            counts, iters = K.ms_grid_modes(sorted_pts, n, grid, cell_start, sd, s, bandwidth)
+        else:
+            counts, iters = K.ms_brute_modes(pts, n, sd, s, bandwidth)
+        return sd[:, :s], counts[:s], iters[:s]
+
+    def suppress(modes, counts, bandwidth, points):
+        n = points.shape[1]
+        lo, hi = K.bounding_box(pad(points), n)
+        grid = K.plan_grid(lo, hi, bandwidth)
+        m = pad(modes)
+        centres, k = K.nms_centres(m, counts.contiguous(), modes.shape[1], bandwidth, grid)
+        if k == 0:
+            raise ValueError("No point was within bandwidth=%f of any seed." % bandwidth)
+        return centres[:, :k].contiguous()
+
+    def assign(points, centres):
+        n = points.shape[1]
+        labels = torch.zeros(max(n, 1), dtype=torch.int32, device=points.device)
+        if n:
+            K.assign_labels(pad(points), n, pad(centres), centres.shape[1], None, labels)
+        return labels[:n]
+
+    return MeanShiftOps(climb, suppress, assign)

@@ -60,13 +60,13 @@ def cluster_points_device(points, n, fit_points, n_fit, bandwidth, seeds=None, m
             "No point was within bandwidth=%f of any seed. Try a different seeding strategy "
             "                             or increase the bandwidth." % bandwidth)
     info = {"method": method, "n_seeds": n_seeds, "n_fit": n_fit, "modes": seeds_soa, "counts": counts,
-            "iters": iters, "grid_cells": int(grid.n_cells)}
+            "iters": iters, "grid_cells": int(grid.n_cells), "grid": grid}
     return centres, k, info
 
 
 def segment_embeddings_device(emb, bandwidth, threshold, reduction_probability=1.0, seeds=None, rng="numpy",
                               fit_flags=None, method="auto", label_dtype=torch.int32, want_mask=False,
-                              philox_seed=0):
+                              philox_seed=0, assign="grid"):
     """threshold -> foreground points -> fit subset -> modes -> centres -> labels, all on the device.
 
     emb: (D+1, *S) CUDA tensor (fp32/fp64), channel D = std.  Returns `(labels (*S), info)`;
@@ -97,7 +97,8 @@ def segment_embeddings_device(emb, bandwidth, threshold, reduction_probability=1
     else:
         fit_pts, n_fit = pts, n
     centres, k, cinfo = cluster_points_device(pts, n, fit_pts, n_fit, bandwidth, seeds=seeds, method=method)
-    K.assign_labels(pts, n, centres, k, pix, labels)  # predict on ALL foreground (:74), scatter, +1
+    # predict on ALL foreground (:74), scatter, +1; pruned nearest-centre search over the same cell grid
+    K.assign_labels(pts, n, centres, k, pix, labels, grid=cinfo["grid"] if assign == "grid" else None)
     info.update(cinfo)
     info.update({"k": k, "centres": centres[:, :k]})
     return labels, info

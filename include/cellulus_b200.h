@@ -240,16 +240,26 @@ CB200_API int cb200_ms_grid_modes(const double* points_sorted, int64_t n_points,
  * Centre post-processing, sklearn:511-547: drop empty seeds, order by
  * (count, coords) descending, merge exact duplicates, greedy suppression of
  * every centre within `bandwidth` (inclusive) of an earlier survivor --
- * reproduced exactly as the lexicographically-first maximal independent set.
- *   centres_out SoA (D x n_seeds capacity, stride = n_seeds), in priority order.
- *   n_centres_and_undecided[0] = K; [1] = centres still undecided after the built-in
- *   rounds (0 in practice; if not, call again -- the result is only final when it is 0).
+ * reproduced exactly as the lexicographically-first maximal independent set
+ * (parallel rounds; priority = sklearn's sort key evaluated pairwise).
+ *
+ * cb200_nms_suppress: runs `rounds` (1..16) rounds over a FINE grid hash of the modes (edge bw/2:
+ *   modes sharing a cell are always within the bandwidth, so only the best live mode of a
+ *   cell can survive next -- one warp per non-empty cell per round).
+ *   grid must cover every mode with count > 0 (the bounding box of the fit points does);
+ *   resume = 0 starts from scratch, resume = 1 continues on the same workspace;
+ *   n_keep_and_undecided (device int[2]): [0] = survivors so far, [1] = modes still
+ *   undecided -- the result is final when [1] == 0 (2-3 rounds in practice).
+ * cb200_nms_emit: writes the n_keep survivors in sklearn's `cluster_centers_` order
+ *   into centres_out SoA (D x centre_stride).  n_keep is the host copy of [0].
  */
-CB200_API int64_t cb200_nms_workspace_bytes(int64_t n_seeds, int num_dims, int64_t n_cells);
-CB200_API int cb200_nms_centres(const double* modes, int64_t seed_stride, int num_dims, const int* counts, int64_t n_seeds,
-                      double bandwidth, const cb200_grid* grid /* covers every mode with count > 0 */,
-                      double* centres_out, int* n_centres_and_undecided /* device int[2] */,
-                      void* workspace, int64_t workspace_bytes, void* stream);
+CB200_API int64_t cb200_nms_workspace_bytes(int64_t n_seeds, const cb200_grid* grid, double bandwidth);
+CB200_API int cb200_nms_suppress(const double* modes, int64_t seed_stride, int num_dims, const int* counts, int64_t n_seeds,
+                       double bandwidth, const cb200_grid* grid, int rounds, int resume,
+                       int* n_keep_and_undecided, void* workspace, int64_t workspace_bytes, void* stream);
+CB200_API int cb200_nms_emit(const double* modes, int64_t seed_stride, int num_dims, const int* counts, int64_t n_seeds,
+                   double bandwidth, const cb200_grid* grid, int n_keep, double* centres_out, int64_t centre_stride,
+                   void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
  * Label assignment, sklearn:563-579 (`predict` = nearest centre, ties -> lowest
@@ -257,10 +267,15 @@ CB200_API int cb200_nms_centres(const double* modes, int64_t seed_stride, int nu
  *   labels_out[pix_index[i]] = 1 + argmin_k ||X_i - c_k||  (label volume pre-zeroed by caller)
  *   label_dtype CB200_I32 (mean_shift_segmentation's return) or CB200_U16 (detect.py:30,161).
  *   pix_index may be NULL: labels are then written densely, labels_out[i].
+ *   grid + workspace (cb200_assign_workspace_bytes) switch on the pruned search: centres are
+ *   hashed into cells of edge >= bandwidth, a centre found within one edge in the 3^D block is
+ *   the global nearest, the remaining points (orphans) are finished by brute force.
+ *   grid == NULL or workspace == NULL: brute force over all centres.
  */
+CB200_API int64_t cb200_assign_workspace_bytes(int64_t n_points, int n_centres, int64_t n_cells);
 CB200_API int cb200_assign_labels(const double* points, int64_t n_points, int64_t pts_stride, int num_dims,
-                        const double* centres, int64_t centre_stride, int n_centres,
-                        const int32_t* pix_index, void* labels_out, int label_dtype, void* stream);
+                        const double* centres, int64_t centre_stride, int n_centres, const cb200_grid* grid,
+                        const int32_t* pix_index, void* labels_out, int label_dtype, void* workspace, void* stream);
 
 /*
  * Connected-component size filter, utils/misc.py:11-25 (skimage.measure.label:

@@ -478,6 +478,36 @@ def test_mean_shift_kats_and_edges():
         cluster_points_device(pts, 3, pts, 3, 5.0, seeds=np.array([[50.0, 50.0]]), method="grid")
 
 
+@pytest.mark.parametrize("nd", [2, 3])
+def test_pruned_label_assignment_equals_brute_force(nd):
+    """The grid-pruned nearest-centre search (+ brute force for orphans) is exactly `predict`:
+    nearest centre, ties -> lowest index, points far from every centre still labelled."""
+    from cellulus_b200 import kernels as K
+
+    dev = _dev()
+    rng = np.random.default_rng(nd)
+    bw = 3.0
+    centres = rng.uniform(0, 60, size=(200, nd))
+    centres[10] = centres[11]  # exact duplicate: tie -> lowest index
+    pts = np.concatenate([
+        centres[rng.integers(0, 200, 20000)] + rng.normal(0, 1.5, size=(20000, nd)),
+        rng.uniform(-500, 500, size=(500, nd)),           # orphans, some far outside the grid
+        (centres[3] + centres[4])[None] / 2,               # equidistant point
+        np.round(centres[:50]),                            # integer-valued points
+    ])
+    ref = oms.predict_labels(pts, centres) + 1
+    P, Cn = _soa(pts, dev), _soa(centres, dev)
+    lo, hi = K.bounding_box(Cn, len(centres))
+    grid = K.plan_grid(lo, hi, bw)
+    for dtype in [torch.int32, torch.uint16]:
+        brute = torch.zeros(len(pts), dtype=dtype, device=dev)
+        K.assign_labels(P, len(pts), Cn, len(centres), None, brute)
+        pruned = torch.zeros(len(pts), dtype=dtype, device=dev)
+        K.assign_labels(P, len(pts), Cn, len(centres), None, pruned, grid=grid)
+        assert torch.equal(brute, pruned)
+        assert np.array_equal(brute.cpu().numpy().astype(np.int64), ref)
+
+
 def test_detect_full_pipeline_3d_properties():
     """BASELINE config #3 shape (128 x 256 x 256, 3-D embeddings): no oracle at this size; size-independent
     properties instead -- idempotent, every object recovered, labels constant inside an object."""

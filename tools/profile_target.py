@@ -19,8 +19,11 @@ if what in ("all", "loss"):
     offsets = torch.randn(bench.B, bench.D, *bench.OUT, device=dev)
     anchors, refs = K.sample_pairs(bench.B, (bench.OUT[1], bench.OUT[0]), bench.KAPPA, bench.N_ANCHORS, bench.N_REFS,
                                    seed=1, device=dev)
-    for _ in range(4):
+    off_cl = offsets.contiguous(memory_format=torch.channels_last)
+    for _ in range(3):
         K.oce_loss_fwd_bwd(offsets, anchors, refs, bench.TEMP, bench.REGW)
+    for _ in range(3):
+        K.oce_loss_fwd_bwd(off_cl, anchors, refs, bench.TEMP, bench.REGW)
     torch.cuda.synchronize()
 if what in ("all", "tta"):
     stack = torch.randn(32, 2, 496, 496, device=dev)
