@@ -140,6 +140,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 per rank; the reference arm is allowed every host core
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     cores = torch.get_num_threads()
     t_one = cpu_loss_step_time(1, 1, 1)
     budget = 100.0 / max(args.steps + args.warmup, 1)  # whole run within a couple of minutes

@@ -51,6 +51,9 @@ PROTOTYPES = {
     "cb200_tta_aggregate": (_i, [_p, _i, _i, _i64, _p, _p]),
     "cb200_tta_accumulate": (_i, [_p, _p, _i, _i, _i64, _p]),
     "cb200_tta_finalize": (_i, [_p, _i, _i, _i64, _p, _p]),
+    "cb200_salt_pepper": (_i, [_p, _i64, _f, _f, _u64, _u64, _p, _p]),
+    "cb200_centre_workspace_bytes": (_i64, []),
+    "cb200_centre_embeddings": (_i, [_p, _i, _i, _i64, _d, _p, _p, _p, _p]),
     "cb200_reduce_workspace_bytes": (_i64, []),
     "cb200_minmax": (_i, [_p, _i, _i64, _p, _p, _p]),
     "cb200_histogram": (_i, [_p, _i, _i64, _p, _i, _p, _p]),

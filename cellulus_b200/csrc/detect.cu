@@ -128,6 +128,88 @@ histogram_kernel(const T* __restrict__ x, int64_t n, const double* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------
+// centring of detect.py:97-119: per offset channel, the mean over the NON-ZERO entries of mask * channel
+// ---------------------------------------------------------------------------
+struct CentreWorkspace {
+  unsigned int ticket;
+  unsigned int pad;
+  double sum[3][RED_MAX_BLOCKS];
+  double cnt[3][RED_MAX_BLOCKS];
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(RED_THREADS)
+masked_channel_mean_kernel(const T* __restrict__ emb, int64_t n, double threshold, double* __restrict__ means,
+                           CentreWorkspace* ws) {
+  const T* std_channel = emb + (int64_t)D * n;
+  double s[D], c[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) s[k] = c[k] = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (load_as_double<T>(std_channel, i) < threshold) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        const double v = load_as_double<T>(emb, (int64_t)k * n + i);
+        if (v != 0.0) {
+          s[k] += v;
+          c[k] += 1.0;
+        }
+      }
+    }
+  }
+  __shared__ double sh[2 * D][RED_THREADS / 32];
+  __shared__ bool s_last;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const double a = warp_sum_down(s[k]), b = warp_sum_down(c[k]);
+    if (lane_id() == 0) {
+      sh[k][threadIdx.x >> 5] = a;
+      sh[D + k][threadIdx.x >> 5] = b;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      double a = 0.0, b = 0.0;
+      for (int w = 0; w < RED_THREADS / 32; ++w) {
+        a += sh[k][w];
+        b += sh[D + k][w];
+      }
+      ws->sum[k][blockIdx.x] = a;
+      ws->cnt[k][blockIdx.x] = b;
+    }
+    __threadfence();
+    s_last = atomicAdd(&ws->ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < D) {  // fixed-order final sum: deterministic
+    __threadfence();
+    const int k = threadIdx.x;
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < (int)gridDim.x; ++i) {
+      a += *((volatile double*)&ws->sum[k][i]);
+      b += *((volatile double*)&ws->cnt[k][i]);
+    }
+    means[k] = a / b;  // numpy: mean of an empty selection is nan (0/0) -- same here
+    if (k == 0) ws->ticket = 0u;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+centre_kernel(const T* __restrict__ emb, int D, int64_t n, const double* __restrict__ means, T* __restrict__ out) {
+  const int64_t total = (int64_t)(D + 1) * n;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int ch = (int)(i / n);
+    const double v = load_as_double<T>(emb, i);
+    out[i] = (T)(ch < D ? v - means[ch] : v);  // the std channel is copied unchanged
+  }
+}
+
 // foreground predicate: (double) std < threshold   (detect.py:94 / utils/mean_shift.py:34)
 template <typename T>
 struct FgPred {
@@ -267,6 +349,29 @@ int cb200_histogram(const void* x, int dtype, int64_t n, const double* edges, in
     histogram_kernel<double><<<blocks, HIST_THREADS, smem, st>>>((const double*)x, n, edges, nbins, counts);
   else
     return CB200_EUNSUPPORTED;
+  CB200_LAUNCH_CHECK();
+  return CB200_OK;
+}
+
+int64_t cb200_centre_workspace_bytes(void) { return (int64_t)sizeof(CentreWorkspace); }
+
+int cb200_centre_embeddings(const void* emb, int dtype, int num_dims, int64_t n_pix, double threshold, double* means,
+                            void* out, void* workspace, void* stream) {
+  if (!emb || !means || !workspace || n_pix <= 0) return CB200_EINVAL;
+  if (num_dims != 2 && num_dims != 3) return CB200_EUNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  auto* ws = static_cast<CentreWorkspace*>(workspace);
+  const int blocks = grid_for(n_pix, RED_THREADS, 8, 8);
+  const int cblocks = grid_for((int64_t)(num_dims + 1) * n_pix, 256, 4, 16);
+#define CB200_CENTRE(T, DD)                                                                                \
+  masked_channel_mean_kernel<T, DD><<<blocks, RED_THREADS, 0, st>>>((const T*)emb, n_pix, threshold, means, ws); \
+  if (out) centre_kernel<T><<<cblocks, 256, 0, st>>>((const T*)emb, DD, n_pix, means, (T*)out);
+  if (dtype == CB200_F32 && num_dims == 2) { CB200_CENTRE(float, 2) }
+  else if (dtype == CB200_F32) { CB200_CENTRE(float, 3) }
+  else if (dtype == CB200_F64 && num_dims == 2) { CB200_CENTRE(double, 2) }
+  else if (dtype == CB200_F64) { CB200_CENTRE(double, 3) }
+  else return CB200_EUNSUPPORTED;
+#undef CB200_CENTRE
   CB200_LAUNCH_CHECK();
   return CB200_OK;
 }

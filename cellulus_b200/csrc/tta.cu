@@ -137,11 +137,43 @@ tta_finalize_kernel(const float* __restrict__ state, int T, int C, int64_t n, fl
   }
 }
 
+// Salt / pepper noise of the infer-mode forward (models/unet.py:80-82): out = (u <= p) ? value : raw,
+// u ~ U[0,1) from Philox (the reference draws u on the CPU and copies it over for every pass).
+__global__ void __launch_bounds__(256)
+salt_pepper_kernel(const float* __restrict__ raw, int64_t n, float p, float value, uint64_t seed, uint64_t sequence,
+                   float* __restrict__ out) {
+  const Philox rng(seed);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = (n + 3) / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const uint4 r = rng((uint64_t)i, sequence);
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t e = i * 4 + j;
+      if (e < n) {
+        const float u = (float)(rr[j] >> 8) * (1.0f / 16777216.0f);  // 24-bit uniform in [0, 1)
+        out[e] = u <= p ? value : raw[e];
+      }
+    }
+  }
+}
+
 }  // namespace cb200
 
 using namespace cb200;
 
 extern "C" {
+
+int cb200_salt_pepper(const float* raw, int64_t n, float p, float value, uint64_t seed, uint64_t sequence, float* out,
+                      void* stream) {
+  if (!raw || !out || n < 0) return CB200_EINVAL;
+  if (n == 0) return CB200_OK;
+  salt_pepper_kernel<<<grid_for((n + 3) / 4, 256, 2, 16), 256, 0, (cudaStream_t)stream>>>(raw, n, p, value, seed,
+                                                                                          sequence, out);
+  CB200_LAUNCH_CHECK();
+  return CB200_OK;
+}
 
 int cb200_tta_aggregate(const float* stack, int num_passes, int channels, int64_t n, float* out, void* stream) {
   if (!stack || !out || num_passes <= 0 || channels <= 0 || channels > TTA_MAXC || n < 0) return CB200_EINVAL;

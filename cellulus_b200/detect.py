@@ -11,7 +11,10 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+import os
+
 from cellulus_b200 import kernels as K
+from cellulus_b200 import sharding, zarr_lite
 from cellulus_b200.utils import mean_shift as MS
 
 
@@ -66,3 +69,51 @@ def detect_embeddings(embeddings, bandwidth, threshold=None, num_bandwidths=1, r
         infos.append(info)
     result = (torch.stack(out, 0), threshold, mask)
     return result + (infos,) if return_info else result
+
+
+def detect(inference_config) -> None:
+    """`detect(inference_config)` (`cellulus/detect.py:14-192`) for `clustering="meanshift"` without seeds:
+    reads the `embeddings` dataset, writes `detection` (uint16, `(s, num_bandwidths, *spatial)`),
+    `binary-segmentation` and `centered-embeddings` with the reference's attributes.  Samples are dealt
+    round-robin to the ranks under torchrun (each sample is one independent unit, `detect.py:82`)."""
+    from cellulus_b200.datasets.meta_data import DatasetMetaData
+
+    if inference_config.clustering != "meanshift":
+        raise NotImplementedError('clustering="greedy" (utils/greedy_cluster.py) is a SURVEY §8f "next" row')
+    if inference_config.use_seeds:
+        raise NotImplementedError("use_seeds=True (gaussian_filter + peak_local_max seeds) is a SURVEY §8f row")
+    meta = DatasetMetaData.from_dataset_config(inference_config.dataset_config)
+    nd = meta.num_spatial_dims
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    device = torch.device(inference_config.device)
+    if world > 1:
+        device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(device)
+    cfg = inference_config.detection_dataset_config
+    f = zarr_lite.open(cfg.container_path)
+    ds = f[cfg.secondary_dataset_name]
+    attrs = {"axis_names": ["s", "c"] + ["t", "z", "y", "x"][-nd:], "resolution": (1,) * nd, "offset": (0,) * nd}
+    if rank == 0:
+        for name, channels, dtype in [(cfg.dataset_name, inference_config.num_bandwidths, np.uint16),
+                                      ("binary-segmentation", 1, np.uint16), ("centered-embeddings", nd + 1, float)]:
+            d = f.create_dataset(name, shape=(meta.num_samples, channels, *meta.spatial_array), dtype=dtype,
+                                 chunks=(1, 1, *meta.spatial_array) if int(np.prod(meta.spatial_array)) < (1 << 24) else None)
+            d.attrs.update(attrs)
+    if world > 1:
+        torch.distributed.barrier()
+    ds_detection, ds_binary, ds_centred = f[cfg.dataset_name], f["binary-segmentation"], f["centered-embeddings"]
+    for sample in sharding.shard_round_robin(meta.num_samples, rank, world):
+        emb = torch.from_numpy(np.ascontiguousarray(ds[sample])).to(device)  # float64, as stored
+        threshold = inference_config.threshold
+        if threshold is None:
+            threshold = threshold_otsu(emb[nd])
+        print(f"For sample {sample}, binary threshold {threshold} was used.")
+        labels, _, mask = detect_embeddings(
+            emb, inference_config.bandwidth, threshold, inference_config.num_bandwidths,
+            inference_config.reduction_probability, rng="numpy", label_dtype=torch.uint16)
+        _, centred = K.centre_embeddings(emb, threshold)
+        ds_binary[sample, 0, ...] = mask.cpu().numpy().astype(np.uint16)
+        ds_centred[sample] = centred.cpu().numpy()
+        ds_detection[sample] = labels.cpu().numpy()
+    if world > 1:
+        torch.distributed.barrier()

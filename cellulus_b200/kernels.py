@@ -237,8 +237,38 @@ def tta_finalize(state, num_passes, channels, spatial):
     return out
 
 
-# --------------------------------------------------------------------------- detect preamble
 _FLOAT_DTYPES = (torch.float32, torch.float64)
+
+
+def salt_pepper(raw: torch.Tensor, p: float, value: float, seed: int, sequence: int) -> torch.Tensor:
+    """`noisy[rnd <= p] = value` of `models/unet.py:80-82` with the uniform draw on the device."""
+    _require_cuda(raw)
+    raw = raw.contiguous()
+    assert raw.dtype == torch.float32
+    out = torch.empty_like(raw)
+    check(_lib().cb200_salt_pepper(_ptr(raw), raw.numel(), float(p), float(value), int(seed) & (2**64 - 1),
+                                   int(sequence), _ptr(out), _stream(raw)), "cb200_salt_pepper")
+    launch_counter["calls"] += 1
+    return out
+
+
+# --------------------------------------------------------------------------- detect preamble
+def centre_embeddings(emb: torch.Tensor, threshold: float, want_centred: bool = True):
+    """`detect.py:97-119`.  Returns `(means (D,) float64 device, centred copy of emb or None)`."""
+    _require_cuda(emb)
+    emb = emb.contiguous()
+    D = emb.shape[0] - 1
+    n = emb[0].numel()
+    means = torch.empty(D, dtype=torch.float64, device=emb.device)
+    out = torch.empty_like(emb) if want_centred else None
+    ws = _zero_workspace("centre", _lib().cb200_centre_workspace_bytes(), emb.device)
+    check(_lib().cb200_centre_embeddings(_ptr(emb), _code(emb, _FLOAT_DTYPES), D, n, float(threshold), _ptr(means),
+                                         _ptr(out), _ptr(ws), _stream(emb)), "cb200_centre_embeddings")
+    launch_counter["calls"] += 1
+    return means, out
+
+
+
 
 
 def minmax(x: torch.Tensor) -> torch.Tensor:

@@ -1,14 +1,22 @@
-"""The two hot-path pieces that live on the reference's model class
-(`cellulus/models/unet.py`): the neighbour gather `select_and_add_coordinates`
-(:108-124) and the test-time-augmentation aggregate of the infer-mode forward
-(:90-98).  The U-Net backbone itself is not the product and is not here.
+"""`UNetModel` (`cellulus/models/unet.py`): backbone + 1x1 head, with the two hot-path pieces that live on
+the reference's model class running on the B200 kernels:
+
+* `select_and_add_coordinates` (`:108-124`) -- the neighbour gather, differentiable (scatter-add backward);
+* the infer-mode forward (`:73-100`) -- the TTA loop keeps everything on the device: salt/pepper noise from a
+  device Philox stream (`cb200_salt_pepper`) instead of a CPU `torch.rand` + H2D copy per pass, and every
+  prediction is folded into a running Welford state (`cb200_tta_accumulate`) instead of `.cpu()` + stack +
+  `std_mean` on the host.
 """
 
 from __future__ import annotations
 
+from typing import List, Tuple
+
 import torch
+import torch.nn as nn
 
 from cellulus_b200 import kernels as K
+from cellulus_b200.models.backbone import UNet
 
 
 class _GatherAddCoords(torch.autograd.Function):
@@ -25,28 +33,14 @@ class _GatherAddCoords(torch.autograd.Function):
         return K.scatter_add_coords(grad_out, coordinates, ctx.shape).to(ctx.in_dtype), None
 
 
-class UNetModel:
-    """Namespace mirror of the reference class for the static gather
-    (`train.py:170-173` calls `model.select_and_add_coordinates(...)`)."""
-
-    @staticmethod
-    def select_and_add_coordinates(outputs, coordinates):
-        """`models/unet.py:108-124`: outputs (B,C,H,W)/(B,C,D,H,W), coordinates
-        (B,P,D) integer with columns (x, y[, z]) -> (B,P,C) fp32 = gathered offset
-        + coordinate.  Differentiable w.r.t. `outputs` (scatter-add backward)."""
-        return _GatherAddCoords.apply(outputs, coordinates)
-
-
 def tta_aggregate(predictions: torch.Tensor) -> torch.Tensor:
-    """`models/unet.py:90-98`: (T, C, *S) fp32 stack of noisy predictions ->
-    (C+1, *S): channel means, then the per-channel population std summed over
-    channels.  One streaming kernel instead of stack + std_mean + sum + cat."""
+    """`models/unet.py:90-98`: (T, C, *S) fp32 stack of noisy predictions -> (C+1, *S): channel means, then
+    the per-channel population std summed over channels.  One streaming kernel."""
     return K.tta_aggregate(predictions)
 
 
 class TTAAccumulator:
-    """Streaming form for an on-device TTA loop: fold each prediction in as it
-    is produced (no T-deep stack, no `.cpu()` per pass as in `models/unet.py:83-88`)."""
+    """Streaming form: fold each prediction in as it is produced (no T-deep stack, no `.cpu()` per pass)."""
 
     def __init__(self, channels: int, spatial, device):
         self.channels = channels
@@ -63,3 +57,68 @@ class TTAAccumulator:
         if self.t == 0:
             raise RuntimeError("no prediction was accumulated")
         return K.tta_finalize(self.state, self.t, self.channels, self.spatial)
+
+
+class UNetModel(nn.Module):  # type: ignore
+    def __init__(
+        self,
+        in_channels: int,
+        out_channels: int,
+        num_fmaps: int,
+        fmap_inc_factor: int,
+        features_in_last_layer: int,
+        downsampling_factors: List[Tuple[int, ...]],
+        num_spatial_dims: int,
+    ):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.features_in_last_layer = features_in_last_layer
+        self.mode = "train"
+        kernels = [[(3,) * num_spatial_dims, (1,) * num_spatial_dims, (1,) * num_spatial_dims,
+                    (3,) * num_spatial_dims]]
+        self.backbone = UNet(
+            in_channels=in_channels, num_fmaps=num_fmaps, fmap_inc_factor=fmap_inc_factor,
+            downsample_factors=[tuple(f) for f in downsampling_factors], num_fmaps_out=features_in_last_layer,
+            kernel_size_down=kernels * (len(downsampling_factors) + 1),
+            kernel_size_up=kernels * len(downsampling_factors))
+        conv = nn.Conv2d if num_spatial_dims == 2 else nn.Conv3d
+        self.head = nn.Sequential(
+            conv(features_in_last_layer, features_in_last_layer, 1), nn.ReLU(),
+            conv(features_in_last_layer, out_channels, 1))
+        self.tta_seed = 0
+
+    def head_forward(self, backbone_output):
+        return self.head(backbone_output)
+
+    def forward(self, raw):
+        if self.mode == "train":
+            return self.head_forward(self.backbone(raw))
+        # mode == "infer": `models/unet.py:73-100` with the loop resident on the device
+        embeddings = []
+        for sample in range(raw.shape[0]):
+            raw_sample = raw[sample: sample + 1].detach().float().contiguous()
+            acc, pass_index = None, 0
+            for val in [0.5, 1.0]:
+                for _ in range(self.num_infer_iterations):
+                    noisy = K.salt_pepper(raw_sample, self.p_salt_pepper, val, self.tta_seed, pass_index)
+                    prediction = self.head_forward(self.backbone(noisy))[0].detach().float().contiguous()
+                    if acc is None:
+                        acc = TTAAccumulator(prediction.shape[0], prediction.shape[1:], prediction.device)
+                    acc.add(prediction)
+                    pass_index += 1
+            self.tta_seed += 1
+            embeddings.append(acc.result())
+        return torch.stack(embeddings, dim=0)
+
+    def set_infer(self, p_salt_pepper, num_infer_iterations, device):
+        self.mode = "infer"
+        self.p_salt_pepper = p_salt_pepper
+        self.num_infer_iterations = num_infer_iterations
+        self.device: torch.device = device
+
+    @staticmethod
+    def select_and_add_coordinates(outputs, coordinates):
+        """`models/unet.py:108-124`: outputs (B,C,H,W)/(B,C,D,H,W), coordinates (B,P,D) integer with columns
+        (x, y[, z]) -> (B,P,C) fp32 = gathered offset + coordinate; differentiable w.r.t. `outputs`."""
+        return _GatherAddCoords.apply(outputs, coordinates)

@@ -150,6 +150,11 @@ CB200_API int cb200_tta_aggregate(const float* stack, int num_passes, int channe
 CB200_API int cb200_tta_accumulate(float* state, const float* prediction, int t, int channels, int64_t n, void* stream);
 CB200_API int cb200_tta_finalize(const float* state, int num_passes, int channels, int64_t n, float* out, void* stream);
 
+/* Salt / pepper noise of the infer-mode forward, models/unet.py:80-82: out = (u <= p) ? value : raw with
+ * u ~ U[0,1) drawn on the device (Philox; `sequence` distinguishes the passes). */
+CB200_API int cb200_salt_pepper(const float* raw, int64_t n, float p, float value, uint64_t seed, uint64_t sequence,
+                      float* out, void* stream);
+
 /*
  * Foreground threshold, detect.py:88-94 (+ skimage threshold_otsu, np.histogram).
  * cb200_minmax: out2 = {min, max} as doubles.            workspace: cb200_reduce_workspace_bytes()
@@ -161,6 +166,16 @@ CB200_API int64_t cb200_reduce_workspace_bytes(void);
 CB200_API int cb200_minmax(const void* x, int dtype, int64_t n, double* out2, void* workspace, void* stream);
 CB200_API int cb200_histogram(const void* x, int dtype, int64_t n, const double* edges, int nbins,
                     unsigned long long* counts, void* stream);
+
+/*
+ * Centring, detect.py:97-119: means[k] = mean over the NON-ZERO entries of (std < threshold) * emb[k]
+ * (float64, fixed summation order); out (optional, same dtype/shape as emb) = emb with means subtracted
+ * from the D offset channels, std channel copied (the `centered-embeddings` dataset, detect.py:119).
+ *   workspace: cb200_centre_workspace_bytes(), zero-initialised once.
+ */
+CB200_API int64_t cb200_centre_workspace_bytes(void);
+CB200_API int cb200_centre_embeddings(const void* emb, int dtype, int num_dims, int64_t n_pix, double threshold,
+                            double* means /* device, num_dims */, void* out, void* workspace, void* stream);
 
 /*
  * Foreground compaction, utils/mean_shift.py:15-36,85,94 (+ detect.py:94):

@@ -1,0 +1,161 @@
+"""GPU: `train()` / `infer()` end to end on a generated zarr container (BASELINE configs[0], repaired as in
+SURVEY §4), the device-resident TTA loop, and the two small detect-preamble kernels against the oracle."""
+
+import os
+import tomllib
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from cellulus_b200 import synthetic, zarr_lite  # noqa: E402
+from cellulus_b200.configs import ExperimentConfig  # noqa: E402
+from oracle import otsu as ootsu  # noqa: E402
+
+
+def test_centring_matches_oracle():
+    from cellulus_b200 import kernels as K
+
+    emb, _, _ = synthetic.blob_scene((90, 110), 14, radius=8.0, seed=6)
+    for arr in [emb, emb.astype(np.float64)]:
+        arr = arr.copy()
+        arr[0, 5, :] = 0.0  # exact zeros inside the mask are excluded from the mean (detect.py:106-107)
+        d = torch.from_numpy(arr).cuda()
+        means, centred = K.centre_embeddings(d, 0.5)
+        mask = arr[2].astype(np.float64) < 0.5
+        ref = ootsu.centre_embeddings(arr.astype(np.float64), mask)
+        ref_means = (arr[:2].astype(np.float64) - ref[:2]).reshape(2, -1)[:, 0]
+        assert np.allclose(means.cpu().numpy(), ref_means, rtol=1e-12, atol=1e-12)
+        tol = 1e-6 if arr.dtype == np.float32 else 1e-12
+        assert np.abs(centred.cpu().numpy().astype(np.float64) - ref).max() <= tol
+        assert np.array_equal(centred[2].cpu().numpy(), arr[2])
+
+
+def test_salt_pepper_statistics():
+    from cellulus_b200 import kernels as K
+
+    raw = torch.rand(1, 1, 512, 512, device="cuda") * 0.4 + 0.05
+    out = K.salt_pepper(raw, 0.05, 1.0, seed=3, sequence=0)
+    hit = out != raw
+    assert (out[hit] == 1.0).all() and torch.equal(out[~hit], raw[~hit])
+    frac = hit.float().mean().item()
+    assert abs(frac - 0.05) < 4 * np.sqrt(0.05 * 0.95 / raw.numel())
+    assert torch.equal(out, K.salt_pepper(raw, 0.05, 1.0, seed=3, sequence=0))
+    assert not torch.equal(out, K.salt_pepper(raw, 0.05, 1.0, seed=3, sequence=1))
+
+
+def test_infer_mode_forward_matches_reference_formula():
+    """The device TTA loop == the reference's formula applied to the very predictions it made."""
+    from cellulus_b200 import kernels as K
+    from cellulus_b200.models import get_model
+    from oracle import tta as otta
+
+    torch.manual_seed(0)
+    model = get_model(1, 2, 4, 2, 8, [(2, 2)], 2).cuda().eval()
+    model.set_infer(p_salt_pepper=0.05, num_infer_iterations=3, device=torch.device("cuda"))
+    raw = torch.rand(1, 1, 60, 60, device="cuda")
+    with torch.no_grad():
+        out = model(raw)
+        preds = []
+        for i, val in enumerate([0.5] * 3 + [1.0] * 3):
+            noisy = K.salt_pepper(raw, 0.05, val, seed=0, sequence=i)
+            preds.append(model.head_forward(model.backbone(noisy))[0].float())
+    ref = otta.tta_aggregate(torch.stack(preds).cpu())
+    assert out.shape == (1, 3, 44, 44)
+    assert (out[0].cpu() - ref).abs().max().item() <= 1e-5 * max(ref.abs().max().item(), 1.0)
+
+
+def _toml(tmp, crop):
+    return f"""
+experiment_name = "e2e"
+object_size = 12
+
+[model_config]
+num_fmaps = 8
+fmap_inc_factor = 2
+checkpoint = "{tmp}/models/000002.pth"
+
+[train_config]
+batch_size = 4
+crop_size = [{crop}, {crop}]
+max_iterations = 3
+num_workers = 0
+elastic_deform = false
+save_model_every = 1000
+save_snapshot_every = 2
+device = "cuda:0"
+[train_config.train_data_config]
+container_path = "{tmp}/data.zarr"
+dataset_name = "train"
+
+[inference_config]
+crop_size = [{crop}, {crop}]
+num_infer_iterations = 2
+num_bandwidths = 2
+threshold = 0.02
+reduction_probability = 0.5
+grow_distance = 1
+shrink_distance = 2
+device = "cuda:0"
+[inference_config.dataset_config]
+container_path = "{tmp}/data.zarr"
+dataset_name = "test"
+[inference_config.prediction_dataset_config]
+container_path = "{tmp}/out.zarr"
+dataset_name = "embeddings"
+[inference_config.detection_dataset_config]
+container_path = "{tmp}/out.zarr"
+dataset_name = "detection"
+secondary_dataset_name = "embeddings"
+[inference_config.segmentation_dataset_config]
+container_path = "{tmp}/out.zarr"
+dataset_name = "segmentation"
+secondary_dataset_name = "detection"
+"""
+
+
+def test_train_then_infer_end_to_end(tmp_path, monkeypatch):
+    from cellulus_b200.infer import infer
+    from cellulus_b200.train import train
+
+    monkeypatch.chdir(tmp_path)
+    g = zarr_lite.open(tmp_path / "data.zarr")
+    rng = np.random.default_rng(0)
+    for name, n in [("train", 3), ("test", 2)]:
+        a = g.create_dataset(name, shape=(n, 1, 120, 130), dtype=np.uint8)
+        img = np.zeros((n, 1, 120, 130), np.uint8)
+        for s in range(n):
+            _, _, ids = synthetic.blob_scene((120, 130), 12, radius=7.0, seed=int(rng.integers(1000)))
+            img[s, 0] = np.where(ids > 0, 200, 20) + rng.integers(0, 20, size=ids.shape)
+        a[...] = img
+        a.attrs["axis_names"] = ["s", "c", "y", "x"]
+
+    cfg = ExperimentConfig(**tomllib.loads(_toml(tmp_path, 76)))
+    ckpt = cfg.model_config.checkpoint
+    cfg.model_config.checkpoint = None
+    train(cfg)
+    state = torch.load(tmp_path / "models" / "000002.pth", map_location="cpu")
+    assert set(state) == {"iteration", "lowest_loss", "model_state_dict", "optim_state_dict", "logger_data"}
+    assert state["iteration"] == 2 and len(state["logger_data"]["loss"]) == 3
+    assert all(np.isfinite(v) for v in state["logger_data"]["loss"])
+    assert os.path.exists(tmp_path / "loss.csv")
+    snap = zarr_lite.open(tmp_path / "snapshots.zarr", "r")
+    assert snap["2"]["prediction"].shape == (4, 2, 60, 60) and snap["2"]["raw"].attrs["axis_names"] == ["s", "c", "y", "x"]
+
+    cfg.model_config.checkpoint = ckpt
+    np.random.seed(0)
+    infer(cfg)
+    assert cfg.inference_config.bandwidth == 6.0 and cfg.inference_config.min_size == int(0.1 * np.pi * 144 / 4)
+    out = zarr_lite.open(tmp_path / "out.zarr", "r")
+    emb, det, seg = out["embeddings"], out["detection"], out["segmentation"]
+    assert emb.shape == (2, 3, 120, 130) and emb.dtype == np.float64 and emb.attrs["axis_names"] == ["s", "c", "y", "x"]
+    assert det.shape == (2, 2, 120, 130) and det.dtype == np.uint16 and seg.shape == det.shape and seg.dtype == np.uint16
+    assert out["binary-segmentation"].shape == (2, 1, 120, 130) and out["centered-embeddings"].shape == (2, 3, 120, 130)
+    e = emb[...]
+    assert np.isfinite(e).all() and (e[:, 2] >= 0).all()  # the std channel is a sum of standard deviations
+    mask = out["binary-segmentation"][...][:, 0].astype(bool)
+    assert np.array_equal(mask, e[:, 2] < 0.02)  # foreground mask: exact
+    d = det[...]
+    assert np.array_equal(d[:, 0] > 0, mask) and np.array_equal(d[:, 1] > 0, mask)

@@ -1,0 +1,133 @@
+"""CPU: the drop-in boundary around the hot path -- TOML schema, zarr layout, dataset/sampler, U-Net stand-in
+geometry and checkpoint key names, scan blocks.  No kernels are launched here."""
+
+import os
+import tomllib
+
+import numpy as np
+import pytest
+import torch
+
+from cellulus_b200 import zarr_lite
+from cellulus_b200.configs import DatasetConfig, ExperimentConfig
+from cellulus_b200.datasets import get_dataset
+from cellulus_b200.datasets.meta_data import DatasetMetaData
+from cellulus_b200.models import get_model
+from oracle import sampler as osampler
+
+# tests/train.toml of the reference, repaired as SURVEY §4 describes (object_size must be an int)
+TRAIN_TOML = """
+experiment_name = "Train test"
+object_size = 10
+
+[model_config]
+num_fmaps = 12
+fmap_inc_factor = 2
+
+[train_config]
+batch_size = 32
+
+[train_config.train_data_config]
+container_path = "test_data.zarr"
+dataset_name = "train"
+
+[train_config.validate_data_config]
+container_path = "test_data.zarr"
+dataset_name = "validate"
+"""
+
+
+def test_config_schema_matches_reference_defaults():
+    cfg = ExperimentConfig(**tomllib.loads(TRAIN_TOML))
+    assert cfg.model_config.num_fmaps == 12 and cfg.model_config.features_in_last_layer == 64
+    assert cfg.model_config.downsampling_factors == [[2, 2]] and cfg.model_config.initialize is True
+    t = cfg.train_config
+    assert (t.crop_size, t.batch_size, t.max_iterations) == ([252, 252], 32, 100_000)
+    assert (t.initial_learning_rate, t.density, t.kappa, t.temperature, t.regularizer_weight) == (4e-5, 0.1, 10.0, 10.0, 1e-5)
+    assert (t.save_model_every, t.save_best_model_every, t.save_snapshot_every, t.num_workers) == (1000, 100, 1000, 8)
+    assert t.device == "cuda:0" and t.elastic_deform is True
+    assert isinstance(t.train_data_config, DatasetConfig) and t.train_data_config.dataset_name == "train"
+    assert cfg.inference_config is None and cfg.normalization_factor is None
+    with pytest.raises(TypeError):  # the reference's own toml has object_size = 10.0 and fails this validator
+        ExperimentConfig(**tomllib.loads(TRAIN_TOML.replace("object_size = 10", "object_size = 10.0")))
+    inf = ExperimentConfig(**tomllib.loads(TRAIN_TOML + """
+[inference_config]
+num_bandwidths = 2
+[inference_config.dataset_config]
+container_path = "x.zarr"
+dataset_name = "test"
+""")).inference_config
+    assert (inf.p_salt_pepper, inf.num_infer_iterations, inf.reduction_probability) == (0.01, 16, 0.1)
+    assert (inf.clustering, inf.use_seeds, inf.post_processing, inf.grow_distance, inf.shrink_distance) == (
+        "meanshift", False, "cell", 3, 6)
+    assert inf.threshold is None and inf.bandwidth is None and inf.min_size is None
+
+
+def test_zarr_lite_layout_roundtrip(tmp_path):
+    g = zarr_lite.open(tmp_path / "c.zarr")
+    x = np.random.default_rng(0).random((3, 2, 40, 50)).astype(np.float32)
+    a = g.create_dataset("raw", shape=x.shape, dtype=np.float32, chunks=(1, 2, 16, 32))
+    a[...] = x
+    a.attrs["axis_names"] = ["s", "c", "y", "x"]
+    b = zarr_lite.open(tmp_path / "c.zarr", "r")["raw"]
+    assert np.array_equal(b[...], x) and np.array_equal(b[1], x[1]) and np.array_equal(b[2, :, 5:33, 7:41], x[2, :, 5:33, 7:41])
+    a[1, 0, 3:20, 10:45] = 7
+    x[1, 0, 3:20, 10:45] = 7
+    assert np.array_equal(b[...], x)
+    with pytest.raises(ValueError):  # zarr v2: create_dataset on an existing array without overwrite fails
+        g.create_dataset("raw", shape=(1,), dtype=float)
+    # on-disk format: .zgroup / .zarray (zarr_format 2) / .zattrs / dotted chunk keys
+    assert os.path.exists(tmp_path / "c.zarr" / ".zgroup") and os.path.exists(tmp_path / "c.zarr" / "raw" / "0.0.0.0")
+    meta = DatasetMetaData.from_dataset_config(DatasetConfig(container_path=tmp_path / "c.zarr", dataset_name="raw"))
+    assert (meta.num_samples, meta.num_channels, meta.num_spatial_dims, meta.spatial_array) == (3, 2, 2, (40, 50))
+    with pytest.raises(RuntimeError, match="does not contain"):
+        DatasetMetaData.from_dataset_config(DatasetConfig(container_path=tmp_path / "c.zarr", dataset_name="nope"))
+
+
+def _make_container(path, shape=(2, 1, 96, 96)):
+    g = zarr_lite.open(path)
+    rng = np.random.default_rng(1)
+    for name in ["train", "test"]:
+        a = g.create_dataset(name, shape=shape, dtype=np.uint8)
+        a[...] = (rng.random(shape) * 255).astype(np.uint8)
+        a.attrs["axis_names"] = ["s", "c", "y", "x"]
+    return g
+
+
+def test_dataset_crops_and_host_sampler_match_reference_order(tmp_path):
+    _make_container(tmp_path / "d.zarr")
+    ds = get_dataset(DatasetConfig(container_path=tmp_path / "d.zarr", dataset_name="train"), crop_size=(60, 60),
+                     elastic_deform=False, control_point_spacing=64, control_point_jitter=2.0, density=0.1, kappa=10.0,
+                     normalization_factor=None)
+    assert ds.output_shape == (44, 44) and ds.get_num_anchors() == int(0.1 * 24 * 24) and ds.get_num_references() == 31
+    np.random.seed(3)
+    crop, anchors, refs = next(iter(ds))
+    assert crop.shape == (1, 60, 60) and crop.dtype == np.float32 and 0 < crop.max() <= 1.0  # uint8 -> /255
+    np.random.seed(3)
+    a_ref, r_ref = osampler.sample_coordinates((44, 44), 10.0, 0.1, 2)
+    assert np.array_equal(anchors, a_ref) and np.array_equal(refs, r_ref)
+
+
+def test_unet_stand_in_geometry_and_checkpoint_keys():
+    m = get_model(in_channels=1, out_channels=2, num_fmaps=12, fmap_inc_factor=2, features_in_last_layer=64,
+                  downsampling_factors=[(2, 2)], num_spatial_dims=2)
+    with torch.no_grad():
+        assert m(torch.zeros(1, 1, 252, 252)).shape == (1, 2, 236, 236)  # crop - 16, as zarr_dataset.py:94 assumes
+        assert m(torch.zeros(1, 1, 76, 76)).shape == (1, 2, 60, 60)
+    keys = set(m.state_dict())
+    for k in ["backbone.l_conv.0.conv_pass.0.weight", "backbone.l_conv.1.conv_pass.6.bias",
+              "backbone.r_conv.0.0.conv_pass.6.bias", "head.0.weight", "head.2.bias"]:
+        assert k in keys, k
+    m3 = get_model(1, 3, 4, 2, 8, [(1, 2, 2), (1, 2, 2)], 3)
+    with torch.no_grad():
+        assert m3(torch.zeros(1, 1, 40, 92, 92)).shape == (1, 3, 20, 52, 52)
+
+
+def test_entry_points_refuse_cpu(tmp_path):
+    from cellulus_b200.train import train
+
+    _make_container(tmp_path / "e.zarr")
+    cfg = ExperimentConfig(**tomllib.loads(TRAIN_TOML))
+    cfg.train_config.device = "cpu"
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        train(cfg)
