@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -30 gpurun_out/pytest_gpu.log
+timeout 1700 python tools/ms_sweep.py 16 > gpurun_out/ms_sweep.log 2>&1
+cat gpurun_out/ms_sweep.log
