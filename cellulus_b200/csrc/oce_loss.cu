@@ -15,6 +15,8 @@
 // anchor pixels and only run heads issue red.global.add -- ~16x fewer atomics.
 // Loss terms are summed per thread in fp32 (tens of terms), then in fp64
 // through warp shuffles, shared memory and one fp64 atomic per block.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cb200 {
@@ -350,6 +352,9 @@ oce_loss_fused_kernel(const OT* __restrict__ offsets, const CT* __restrict__ anc
     take(cur, c0);
     fetch(c0 + stride);
     chunk_gather<D, OT, IL>(cur, off_b, shape, bad);
+    // the gradient tensor is zero-filled by the preceding grid (programmatic dependent launch): everything
+    // above overlapped with it, nothing below may
+    if constexpr (BWD) asm volatile("griddepcontrol.wait;" ::: "memory");
     for (; c0 < chunks_per_sample; c0 += stride) {
       chunk_finish<D, BWD, IL>(cur, grad_b, shape, neg_log2e_over_t, two_over_t, w, lane, acc_oce, acc_nrm);
       take(nxt, c0 + stride);
@@ -364,6 +369,9 @@ oce_loss_fused_kernel(const OT* __restrict__ offsets, const CT* __restrict__ anc
 // zero-fill of the gradient tensor: 4 independent 16-byte stores per thread per trip, one wave
 __global__ void __launch_bounds__(256) zero_fill_kernel(float4* __restrict__ p, int64_t n4, float* __restrict__ tail,
                                                         int n_tail) {
+  // programmatic dependent launch: the fused loss kernel may start its prologue (list prefetch, first
+  // gathers) while this grid is still writing zeros; it waits (griddepcontrol.wait) before its first reduction
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -520,6 +528,12 @@ static bool make_shape(const int64_t* spatial, Shape<D>& s) {
   return true;
 }
 
+// programmatic dependent launch of the fused kernel behind the zero-fill (A/B switch: CB200_LOSS_PDL=0)
+static const bool g_loss_pdl = [] {
+  const char* e = getenv("CB200_LOSS_PDL");
+  return !(e && e[0] == '0');
+}();
+
 template <int D, typename CT, typename OT, bool BWD, bool IL>
 static int launch_fused_variant(const void* offsets, const void* anchors, const void* refs, int batch,
                                 const Shape<D>& shape, int64_t P, float T, float w, float* grad, float* out,
@@ -539,10 +553,18 @@ static int launch_fused_variant(const void* offsets, const void* anchors, const 
   if (blocks_x > needed) blocks_x = needed;
   if (blocks_x < 1) blocks_x = 1;
   const float log2e = 1.4426950408889634f;
-  kernel<<<dim3(blocks_x, (unsigned)batch), LOSS_THREADS, 0, st>>>(
-      (const OT*)offsets, (const CT*)anchors, (const CT*)refs, (unsigned)P, cps, shape, -log2e / T, 2.0f / T, w, grad,
-      ws, out);
-  CB200_LAUNCH_CHECK();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks_x, (unsigned)batch);
+  cfg.blockDim = dim3(LOSS_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (BWD && g_loss_pdl) ? 1 : 0;  // only behind our own zero-fill grid
+  CB200_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, (const OT*)offsets, (const CT*)anchors, (const CT*)refs, (unsigned)P,
+                                    cps, shape, -log2e / T, 2.0f / T, w, grad, ws, out));
   return CB200_OK;
 }
 
