@@ -54,6 +54,10 @@ PROTOTYPES = {
     "cb200_salt_pepper": (_i, [_p, _i64, _f, _f, _u64, _u64, _p, _p]),
     "cb200_centre_workspace_bytes": (_i64, []),
     "cb200_centre_embeddings": (_i, [_p, _i, _i, _i64, _d, _p, _p, _p, _p]),
+    "cb200_channel_norm": (_i, [_p, _i, _i, _i64, _p, _p]),
+    "cb200_gaussian_blur": (_i, [_p, _p, _p, _i, _pi64, C.POINTER(_d), _i, _i, _p]),
+    "cb200_peaks_workspace_bytes": (_i64, [_i64]),
+    "cb200_local_peaks": (_i, [_p, _i, _pi64, _d, _p, _p, _i64, _p, _p, _p]),
     "cb200_reduce_workspace_bytes": (_i64, []),
     "cb200_minmax": (_i, [_p, _i, _i64, _p, _p, _p]),
     "cb200_histogram": (_i, [_p, _i, _i64, _p, _i, _p, _p]),

@@ -80,8 +80,6 @@ def detect(inference_config) -> None:
 
     if inference_config.clustering != "meanshift":
         raise NotImplementedError('clustering="greedy" (utils/greedy_cluster.py) is a SURVEY §8f "next" row')
-    if inference_config.use_seeds:
-        raise NotImplementedError("use_seeds=True (gaussian_filter + peak_local_max seeds) is a SURVEY §8f row")
     meta = DatasetMetaData.from_dataset_config(inference_config.dataset_config)
     nd = meta.num_spatial_dims
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -108,10 +106,19 @@ def detect(inference_config) -> None:
         if threshold is None:
             threshold = threshold_otsu(emb[nd])
         print(f"For sample {sample}, binary threshold {threshold} was used.")
-        labels, _, mask = detect_embeddings(
-            emb, inference_config.bandwidth, threshold, inference_config.num_bandwidths,
-            inference_config.reduction_probability, rng="numpy", label_dtype=torch.uint16)
         _, centred = K.centre_embeddings(emb, threshold)
+        if inference_config.use_seeds:
+            # detect.py:128-144: seeds from the centred embeddings, clustering on the centred embeddings.
+            # (The reference adds the coordinates to `embeddings_centered` in place on every pass, so its
+            # bandwidth index >= 1 runs on doubly-shifted data -- SURVEY quirk Q9; index 0 is reproduced.)
+            seeds = K.find_seeds(centred)
+            labels, _, mask = detect_embeddings(
+                centred, inference_config.bandwidth, threshold, inference_config.num_bandwidths,
+                inference_config.reduction_probability, seeds=seeds, rng="numpy", label_dtype=torch.uint16)
+        else:
+            labels, _, mask = detect_embeddings(
+                emb, inference_config.bandwidth, threshold, inference_config.num_bandwidths,
+                inference_config.reduction_probability, rng="numpy", label_dtype=torch.uint16)
         ds_binary[sample, 0, ...] = mask.cpu().numpy().astype(np.uint16)
         ds_centred[sample] = centred.cpu().numpy()
         ds_detection[sample] = labels.cpu().numpy()

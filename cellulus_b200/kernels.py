@@ -271,6 +271,53 @@ def centre_embeddings(emb: torch.Tensor, threshold: float, want_centred: bool = 
 
 
 
+def gaussian_weights(sigma: float, truncate: float = 4.0):
+    """scipy's `_gaussian_kernel1d` (order 0): `(w[0..radius] with w[0] the centre, radius)`."""
+    radius = int(truncate * float(sigma) + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * x**2)
+    phi = phi / phi.sum()
+    return np.ascontiguousarray(phi[radius:]), radius
+
+
+def find_seeds(centred: torch.Tensor, sigma: float = 2.0) -> np.ndarray:
+    """`detect.py:129-132` on the device: (n_seeds, D) int64 numpy array in (x, y[, z]) order, sorted by
+    descending peak intensity (stable), i.e. `np.flip(peak_local_max(-gaussian_filter(norm(...), 2)), 1)`."""
+    _require_cuda(centred)
+    centred = centred.contiguous()
+    D = centred.shape[0] - 1
+    spatial = tuple(centred.shape[1:])
+    n = int(np.prod(spatial))
+    dev = centred.device
+    st = _stream(centred)
+    mag = torch.empty(spatial, dtype=torch.float64, device=dev)
+    check(_lib().cb200_channel_norm(_ptr(centred), _code(centred, _FLOAT_DTYPES), D, n, _ptr(mag), st),
+          "cb200_channel_norm")
+    w, radius = gaussian_weights(sigma)
+    smooth, scratch = torch.empty_like(mag), torch.empty_like(mag)
+    check(_lib().cb200_gaussian_blur(_ptr(mag), _ptr(smooth), _ptr(scratch), D, spatial_array(spatial),
+                                     w.ctypes.data_as(C.POINTER(C.c_double)), radius, 1, st), "cb200_gaussian_blur")
+    lo = float(minmax(smooth)[0].item())  # threshold_abs = image.min()
+    cap = max(1024, n // 27 + 16)
+    ws = torch.empty(_lib().cb200_peaks_workspace_bytes(n), dtype=torch.uint8, device=dev)
+    n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+    while True:
+        idx = torch.empty(cap, dtype=torch.int32, device=dev)
+        val = torch.empty(cap, dtype=torch.float64, device=dev)
+        check(_lib().cb200_local_peaks(_ptr(smooth), D, spatial_array(spatial), lo, _ptr(idx), _ptr(val), cap,
+                                       _ptr(n_out), _ptr(ws), st), "cb200_local_peaks")
+        k = int(n_out.item())
+        if k <= cap:
+            break
+        cap = k
+    launch_counter["calls"] += 4
+    idx = idx[:k].cpu().numpy().astype(np.int64)
+    val = val[:k].cpu().numpy()
+    order = np.argsort(-val, kind="stable")
+    coords = np.stack(np.unravel_index(idx[order], spatial), axis=1) if k else np.zeros((0, D), np.int64)
+    return np.flip(coords, 1).astype(np.int64)
+
+
 def minmax(x: torch.Tensor) -> torch.Tensor:
     """{min, max} of x as a 2-element float64 device tensor."""
     _require_cuda(x)

@@ -178,6 +178,25 @@ CB200_API int cb200_centre_embeddings(const void* emb, int dtype, int num_dims, 
                             double* means /* device, num_dims */, void* out, void* workspace, void* stream);
 
 /*
+ * Seed finder of the use_seeds branch, detect.py:128-132:
+ *   cb200_channel_norm:   out[i] = sqrt(sum_k emb[k][i]^2) in float64 (np.linalg.norm(centred[:-1], axis=0))
+ *   cb200_gaussian_blur:  scipy.ndimage.gaussian_filter (separable, mode="reflect"), bit-exact: per axis
+ *                         tmp = x0*w0; for j = radius..1: tmp += (x[-j] + x[+j])*w[j]; weights (host, radius+1,
+ *                         w[0] = centre) from scipy's _gaussian_kernel1d; `negate` flips the sign of the result
+ *                         (peaks of -smooth).  scratch: one more n_pix doubles.
+ *   cb200_local_peaks:    skimage.feature.peak_local_max defaults: pixel equals the 3^D maximum, is strictly above
+ *                         `threshold` (the image minimum), not on the 1-px border; raster-ordered linear indices
+ *                         and values (sort by value on the host: the list is short).  n_out: device int64.
+ */
+CB200_API int cb200_channel_norm(const void* emb, int dtype, int num_channels, int64_t n_pix, double* out, void* stream);
+CB200_API int cb200_gaussian_blur(const double* in, double* out, double* scratch, int num_dims, const int64_t* spatial,
+                        const double* weights, int radius, int negate, void* stream);
+CB200_API int64_t cb200_peaks_workspace_bytes(int64_t n_pix);
+CB200_API int cb200_local_peaks(const double* img, int num_dims, const int64_t* spatial, double threshold,
+                      int32_t* peak_index, double* peak_value, int64_t capacity, long long* n_out,
+                      void* workspace, void* stream);
+
+/*
  * Foreground compaction, utils/mean_shift.py:15-36,85,94 (+ detect.py:94):
  *   mask = std < threshold (compared in float64); foreground pixels, in raster
  *   order, become points X[k][i] = emb[k][pix] + coordinate_k (float64, SoA:

@@ -33,6 +33,53 @@ def test_centring_matches_oracle():
         assert np.array_equal(centred[2].cpu().numpy(), arr[2])
 
 
+@pytest.mark.parametrize("shape", [(90, 110), (20, 48, 52), (6, 9)])
+def test_seed_finder_matches_scipy_and_restated_skimage(shape):
+    """detect.py:128-132: norm -> gaussian_filter (bit-exact vs scipy) -> peak_local_max -> flip."""
+    from scipy import ndimage
+
+    from cellulus_b200 import kernels as K
+    from oracle import seeds as oseeds
+
+    D = len(shape)
+    emb, _, _ = synthetic.blob_scene(shape, 10, radius=1.5 if min(shape) < 10 else 6.0, seed=7, dtype=np.float64)
+    centred = ootsu.centre_embeddings(emb, emb[D] < 0.5)
+    ref = oseeds.find_seeds(centred)
+    got = K.find_seeds(torch.from_numpy(centred).cuda())
+    assert got.dtype == np.int64 and got.shape == ref.shape
+    assert np.array_equal(got, ref)  # integer seeds: exact, same order
+    # the blur itself, bit for bit
+    mag = np.linalg.norm(centred[:-1], axis=0)
+    from cellulus_b200._cabi import check, load, spatial_array
+    import ctypes as C
+    w, radius = K.gaussian_weights(2.0)
+    d_in = torch.from_numpy(mag).cuda()
+    out, scratch = torch.empty_like(d_in), torch.empty_like(d_in)
+    check(load().cb200_gaussian_blur(d_in.data_ptr(), out.data_ptr(), scratch.data_ptr(), D, spatial_array(shape),
+                                     w.ctypes.data_as(C.POINTER(C.c_double)), radius, 0,
+                                     torch.cuda.current_stream().cuda_stream), "blur")
+    assert np.array_equal(out.cpu().numpy(), ndimage.gaussian_filter(mag, sigma=2))
+
+
+def test_mean_shift_with_integer_seeds_matches_oracle():
+    """use_seeds branch end to end on the device: seeds -> mean-shift(seeds) -> labels, vs the oracle port."""
+    from cellulus_b200 import kernels as K
+    from cellulus_b200.detect import detect_embeddings
+    from oracle import mean_shift as oms
+    from oracle import seeds as oseeds
+
+    emb, _, _ = synthetic.blob_scene((100, 120), 16, radius=8.0, seed=11, dtype=np.float64)
+    thr, bw, rp = 0.5, 5.0, 0.4
+    centred = ootsu.centre_embeddings(emb, emb[2] < thr)
+    seeds = oseeds.find_seeds(centred)
+    np.random.seed(4)
+    ref = oms.mean_shift_segmentation(centred[np.newaxis, :2].copy(), centred[2], bw, 0, rp, thr, seeds)
+    d = torch.from_numpy(centred).cuda()
+    np.random.seed(4)
+    labels, _, _ = detect_embeddings(d, bw, thr, 1, rp, seeds=K.find_seeds(d), rng="numpy", label_dtype=torch.int32)
+    assert np.array_equal(labels[0].cpu().numpy(), ref)
+
+
 def test_salt_pepper_statistics():
     from cellulus_b200 import kernels as K
 

@@ -205,3 +205,18 @@ def test_size_filter_restatement(shape):
     sizes = np.bincount(out.ravel())[1:]
     assert (sizes >= 5).all()
     assert osize.size_filter(seg, 0) is seg
+
+
+@pytest.mark.parametrize("shape", [(50, 61), (9, 30, 33), (5, 7)])
+def test_seed_oracle_blur_restatement_is_scipy(shape):
+    """The operation order the CUDA blur reproduces (oracle/seeds.py) is bit-identical to scipy's."""
+    from scipy import ndimage
+
+    from oracle import seeds as oseeds
+
+    img = np.random.default_rng(0).random(shape) * 10
+    assert np.array_equal(oseeds.gaussian_filter_restated(img, 2.0), ndimage.gaussian_filter(img, sigma=2))
+    peaks = oseeds.peak_local_max(-ndimage.gaussian_filter(img, sigma=2))
+    assert peaks.ndim == 2 and peaks.shape[1] == len(shape)
+    if len(peaks):
+        assert peaks.min() >= 1 and (peaks.max(0) <= np.array(shape) - 2).all()  # 1-px border excluded
