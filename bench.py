@@ -46,7 +46,7 @@ N_PX = B * OUT[0] * OUT[1]  # 1 968 128
 # algorithmic bytes per step: both int64 coordinate lists once, offsets once, dense gradient once
 ALGO_BYTES = B * P * D * 8 * 2 + N_PX * D * 4 + N_PX * D * 4
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu capture (profiles/), or None
-TRAFFIC_NCU = None
+TRAFFIC_NCU = 208_558_848  # profiles/r01_loss_ncu_full_summary.txt: 204.45 MB read + 4.11 MB written
 WORKLOAD = "configs[1]: OCELoss fwd+bwd, offsets (8,2,496,496) f32, 8x702367 pairs, int64 coords, kappa=10, density=0.1"
 
 # ---- BASELINE config #3 (secondary: detect) ----------------------------------------------
@@ -214,6 +214,35 @@ def bench_detect(dev, windows):
     }
 
 
+def bench_tta(dev, windows):
+    """TTA aggregate (models/unet.py:90-98) of T = 32 passes over a 496 x 496 scan block and a 3-D block."""
+    from cellulus_b200.models import tta_aggregate
+
+    out = {}
+    peak, _ = measured_peak_gbs()
+    for name, shape in [("2d_32x2x496x496", (32, 2, 496, 496)), ("3d_32x3x20x212x212", (32, 3, 20, 212, 212))]:
+        stacks = [torch.randn(shape, device=dev) for _ in range(3 if name.startswith("2d") else 2)]
+        nbytes = stacks[0].numel() * 4 + (shape[1] + 1) * int(np.prod(shape[2:])) * 4
+        # rotate over enough distinct stacks that none is L2-resident when re-read (66 MB each in 2-D)
+        for i in range(6):
+            tta_aggregate(stacks[i % len(stacks)])
+        torch.cuda.synchronize(dev)
+        reps = 60
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        e0.record()
+        for i in range(reps):
+            tta_aggregate(stacks[i % len(stacks)])
+        e1.record()
+        torch.cuda.synchronize(dev)
+        windows.append((w0, time.time()))
+        us = e0.elapsed_time(e1) / reps * 1e3
+        out[name] = {"us": us, "GB/s": nbytes / us / 1e3, "frac_of_hbm_peak": nbytes / us / 1e3 / peak,
+                     "Mpx/s": float(np.prod(shape[2:])) / us, "algorithmic_bytes": nbytes}
+        del stacks
+    return out
+
+
 def cpu_detect_baseline():
     """Oracle port of `mean_shift_segmentation` (scikit-learn MeanShift, hill climb on ONE core as shipped)
     on a bounded sub-volume of the same scene family."""
@@ -338,11 +367,32 @@ def run_b200(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * N_PX / e2e_s.item()
 
+    # (3b) the same step when the pair lists are drawn ON THE DEVICE (cb200_sample_pairs replaces the
+    # DataLoader-side sampler of zarr_dataset.py:198-242): only the offsets cross PCIe
+    def e2e_sampled_step(i):
+        o = h_off.to(dev, non_blocking=True).requires_grad_(True)
+        a, r = K.sample_pairs(B, (OUT[1], OUT[0]), KAPPA, N_ANCHORS, N_REFS, seed=99, sequence=i, device=dev)
+        loss, _, _ = oce_loss_fused(o, a, r, TEMP, REGW)
+        loss.backward()
+        return loss.item()
+
+    for i in range(2):
+        e2e_sampled_step(i)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_sampled_step(i)
+    torch.cuda.synchronize(dev)
+    e2e_sampled_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=dev)
+    if dist is not None:
+        dist.all_reduce(e2e_sampled_s, op=dist.ReduceOp.MAX)
+
     detect = None
     cpu_base = None
     if rank == 0:
         if not args.skip_detect:
             detect = bench_detect(dev, windows)
+            detect["tta_aggregate"] = bench_tta(dev, windows)
         if world == 1 and not args.skip_cpu:
             t_cpu = cpu_loss_step_time(B, 3, 1)
             cpu_base = {"value": N_PX / t_cpu, "unit": "px/s", "cores": torch.get_num_threads(), "kind": "port",
@@ -378,7 +428,12 @@ def run_b200(args):
             "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_value, "unit": "px/s",
                     "h2d_bytes_per_step": int(h_off.numel() * 4 + h_anc.numel() * 8 + h_ref.numel() * 8),
-                    "d2h_bytes_per_step": 4, "steps": e2e_steps, "ms_per_step": e2e_s.item() * 1e3},
+                    "d2h_bytes_per_step": 4, "steps": e2e_steps, "ms_per_step": e2e_s.item() * 1e3,
+                    "with_device_pair_sampler": {
+                        "value": world * N_PX / e2e_sampled_s.item(), "unit": "px/s",
+                        "ms_per_step": e2e_sampled_s.item() * 1e3, "h2d_bytes_per_step": int(h_off.numel() * 4),
+                        "note": "pair lists drawn on the device (same distribution as the reference sampler), "
+                                "sampling kernel inside the timed step"}},
             "gpu_launches": int(launches * world),
             "clocks": clocks,
             "detect": detect,

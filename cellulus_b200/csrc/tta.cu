@@ -13,45 +13,67 @@ namespace cb200 {
 constexpr int TTA_THREADS = 128;
 constexpr int TTA_MAXC = 4;
 
-struct Welford4 {
-  float4 mean, m2;
+template <int V>
+struct Vec {
+  float v[V];
+};
+template <int V>
+__device__ __forceinline__ Vec<V> ld_stream_vec(const float* p);
+template <>
+__device__ __forceinline__ Vec<4> ld_stream_vec<4>(const float* p) {
+  const float4 t = ld_stream_f4(p);
+  return Vec<4>{{t.x, t.y, t.z, t.w}};
+}
+template <>
+__device__ __forceinline__ Vec<2> ld_stream_vec<2>(const float* p) {
+  Vec<2> r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.v[0]), "=f"(r.v[1]) : "l"(p));
+  return r;
+}
+template <int V>
+__device__ __forceinline__ void st_stream_vec(float* p, const Vec<V>& x) {
+  if constexpr (V == 4) st_stream_f4(p, make_float4(x.v[0], x.v[1], x.v[2], x.v[3]));
+  else asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(x.v[0]), "f"(x.v[1]));
+}
+
+template <int V>
+struct WelfordV {
+  Vec<V> mean, m2;
   __device__ __forceinline__ void init() {
-    mean = make_float4(0.f, 0.f, 0.f, 0.f);
-    m2 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < V; ++j) mean.v[j] = m2.v[j] = 0.f;
   }
-  __device__ __forceinline__ void push(const float4 x, const float inv_count) {
-#define CB200_W(f)                          \
-  {                                         \
-    const float d = x.f - mean.f;           \
-    mean.f = fmaf(d, inv_count, mean.f);    \
-    m2.f = fmaf(d, x.f - mean.f, m2.f);     \
-  }
-    CB200_W(x) CB200_W(y) CB200_W(z) CB200_W(w)
-#undef CB200_W
+  __device__ __forceinline__ void push(const Vec<V>& x, const float inv_count) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float d = x.v[j] - mean.v[j];
+      mean.v[j] = fmaf(d, inv_count, mean.v[j]);
+      m2.v[j] = fmaf(d, x.v[j] - mean.v[j], m2.v[j]);
+    }
   }
 };
 
-// One thread owns 4 consecutive pixels of every channel.  The T passes are consumed in batches of U; batch
-// b+1 is loaded (U*C independent 16-byte requests) BEFORE batch b is folded into the Welford state, so the
-// HBM stream never drains even when the block being aggregated is small (a 496x496 scan block is only 61 k
-// threads -- 20 % occupancy -- and must live on memory-level parallelism, not on warps).
-template <int C>
+// One thread owns V consecutive pixels of every channel (V = 4, or 2 when the block being aggregated is so
+// small -- a 496x496 scan block is 246 k pixels -- that 16-byte granules would leave most of the chip without
+// a thread).  The T passes are consumed in batches of U; batch b+1 is loaded (U*C independent requests) BEFORE
+// batch b is folded into the Welford state, so the HBM stream never drains.
+template <int C, int V>
 __global__ void __launch_bounds__(TTA_THREADS)
-tta_aggregate_kernel(const float* __restrict__ stack, int T, int64_t n, int64_t n4, float* __restrict__ out) {
-  constexpr int U = 8 / C > 0 ? 8 / C : 1;
+tta_aggregate_kernel(const float* __restrict__ stack, int T, int64_t n, int64_t nv, float* __restrict__ out) {
+  constexpr int U = (8 / C > 0 ? 8 / C : 1) * (V == 2 ? 2 : 1);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const float inv_T = 1.0f / (float)T;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    Welford4 w[C];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    WelfordV<V> w[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) w[c].init();
-    float4 cur[U][C], nxt[U][C];
-    auto load = [&](float4 (&v)[U][C], int t0) {
+    Vec<V> cur[U][C], nxt[U][C];
+    auto load = [&](Vec<V> (&v)[U][C], int t0) {
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int c = 0; c < C; ++c)
-          if (t0 + u < T) v[u][c] = ld_stream_f4(stack + ((int64_t)(t0 + u) * C + c) * n + i * 4);
+          if (t0 + u < T) v[u][c] = ld_stream_vec<V>(stack + ((int64_t)(t0 + u) * C + c) * n + i * V);
     };
     load(cur, 0);
     for (int t = 0; t < T; t += U) {
@@ -69,16 +91,16 @@ tta_aggregate_kernel(const float* __restrict__ stack, int T, int64_t n, int64_t 
 #pragma unroll
         for (int c = 0; c < C; ++c) cur[u][c] = nxt[u][c];
     }
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    Vec<V> s;
+#pragma unroll
+    for (int j = 0; j < V; ++j) s.v[j] = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      st_stream_f4(out + (int64_t)c * n + i * 4, w[c].mean);
-      s.x += sqrtf(w[c].m2.x * inv_T);
-      s.y += sqrtf(w[c].m2.y * inv_T);
-      s.z += sqrtf(w[c].m2.z * inv_T);
-      s.w += sqrtf(w[c].m2.w * inv_T);
+      st_stream_vec<V>(out + (int64_t)c * n + i * V, w[c].mean);
+#pragma unroll
+      for (int j = 0; j < V; ++j) s.v[j] += sqrtf(w[c].m2.v[j] * inv_T);
     }
-    st_stream_f4(out + (int64_t)C * n + i * 4, s);
+    st_stream_vec<V>(out + (int64_t)C * n + i * V, s);
   }
 }
 
@@ -183,14 +205,20 @@ int cb200_tta_aggregate(const float* stack, int num_passes, int channels, int64_
                       ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   int64_t first_scalar = 0;
   if (vec_ok) {
-    const int64_t n4 = n / 4;
-    const int blocks = grid_for(n4, TTA_THREADS, 1, 16);
+    // 16-byte granules when they still give every SM ~1k threads, 8-byte granules for small blocks
+    const bool wide = n / 4 >= (int64_t)CB200_SM_COUNT * 1024;
+    const int64_t nv = wide ? n / 4 : n / 2;
+    const int blocks = grid_for(nv, TTA_THREADS, 1, 16);
+#define CB200_TTA(CC)                                                                                      \
+  if (wide) tta_aggregate_kernel<CC, 4><<<blocks, TTA_THREADS, 0, st>>>(stack, num_passes, n, nv, out);    \
+  else tta_aggregate_kernel<CC, 2><<<blocks, TTA_THREADS, 0, st>>>(stack, num_passes, n, nv, out);
     switch (channels) {
-      case 1: tta_aggregate_kernel<1><<<blocks, TTA_THREADS, 0, st>>>(stack, num_passes, n, n4, out); break;
-      case 2: tta_aggregate_kernel<2><<<blocks, TTA_THREADS, 0, st>>>(stack, num_passes, n, n4, out); break;
-      case 3: tta_aggregate_kernel<3><<<blocks, TTA_THREADS, 0, st>>>(stack, num_passes, n, n4, out); break;
-      default: tta_aggregate_kernel<4><<<blocks, TTA_THREADS, 0, st>>>(stack, num_passes, n, n4, out); break;
+      case 1: CB200_TTA(1) break;
+      case 2: CB200_TTA(2) break;
+      case 3: CB200_TTA(3) break;
+      default: CB200_TTA(4) break;
     }
+#undef CB200_TTA
     CB200_LAUNCH_CHECK();
     first_scalar = n;
   }
