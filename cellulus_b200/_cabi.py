@@ -77,6 +77,10 @@ PROTOTYPES = {
     "cb200_nms_emit": (_i, [_p, _i64, _i, _p, _i64, _d, C.POINTER(Grid), _i, _p, _i64, _p, _i64, _p]),
     "cb200_assign_workspace_bytes": (_i64, [_i64, _i, _i64]),
     "cb200_assign_labels": (_i, [_p, _i64, _i64, _i, _p, _i64, _i, C.POINTER(Grid), _p, _p, _i, _p, _p]),
+    "cb200_greedy_workspace_bytes": (_i64, [_i64]),
+    "cb200_greedy_prepare": (_i, [_p, _i, _i, _pi64, _p, _i, _d, _d, _p, _i64, _p, _p, _p, _p, _p]),
+    "cb200_greedy_cluster": (_i, [_p, _i64, _p, _i64, _i, _i, _d, _i, _d, C.c_longlong, _p, _p, _p, _p]),
+    "cb200_scatter_i16": (_i, [_p, _p, _i64, _p, _p]),
     "cb200_cc_workspace_bytes": (_i64, [_i64]),
     "cb200_label_components": (_i, [_p, _i, _pi64, _p, _p, _p, _p]),
     "cb200_size_filter": (_i, [_p, _i, _pi64, _i64, _p, _p, _p, _p]),

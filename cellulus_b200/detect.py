@@ -78,8 +78,6 @@ def detect(inference_config) -> None:
     round-robin to the ranks under torchrun (each sample is one independent unit, `detect.py:82`)."""
     from cellulus_b200.datasets.meta_data import DatasetMetaData
 
-    if inference_config.clustering != "meanshift":
-        raise NotImplementedError('clustering="greedy" (utils/greedy_cluster.py) is a SURVEY §8f "next" row')
     meta = DatasetMetaData.from_dataset_config(inference_config.dataset_config)
     nd = meta.num_spatial_dims
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -107,7 +105,12 @@ def detect(inference_config) -> None:
             threshold = threshold_otsu(emb[nd])
         print(f"For sample {sample}, binary threshold {threshold} was used.")
         _, centred = K.centre_embeddings(emb, threshold)
-        if inference_config.use_seeds:
+        if inference_config.clustering == "greedy":  # detect.py:162-192
+            mask = (emb[nd] < threshold).to(torch.uint8)
+            labels = torch.stack([
+                K.greedy_cluster(emb, mask, inference_config.bandwidth / (2**k), inference_config.min_size)[0]
+                .to(torch.int32).to(torch.uint16) for k in range(inference_config.num_bandwidths)])
+        elif inference_config.use_seeds:
             # detect.py:128-144: seeds from the centred embeddings, clustering on the centred embeddings.
             # (The reference adds the coordinates to `embeddings_centered` in place on every pass, so its
             # bandwidth index >= 1 runs on doubly-shifted data -- SURVEY quirk Q9; index 0 is reproduced.)

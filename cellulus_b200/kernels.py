@@ -538,6 +538,48 @@ def assign_labels(points, n, centres, k, pix_index, labels_out, grid: Optional[G
     return labels_out
 
 
+def greedy_cluster(emb: torch.Tensor, fg_mask: torch.Tensor, bandwidth: float, min_object_size: int,
+                   seed_thresh: float = 0.9, min_unclustered_sum: int = 0, compute_dtype=None):
+    """`Cluster2d/3d.cluster` (utils/greedy_cluster.py) on the device.  emb (D+1, *S) fp32/fp64, fg_mask (*S)
+    uint8/bool.  Returns `(instance_map (*S) int16, n_objects, n_seeds_tried)`."""
+    _require_cuda(emb, fg_mask)
+    emb = emb.contiguous()
+    D = emb.shape[0] - 1
+    spatial = tuple(emb.shape[1:])
+    n_pix = int(np.prod(spatial))
+    dev = emb.device
+    if compute_dtype is None:  # the reference: `.float()` in 2-D (:84), the stored dtype in 3-D (:240)
+        compute_dtype = torch.float32 if D == 2 else emb.dtype
+    mask = fg_mask.to(torch.uint8).contiguous()
+    seed = emb[D].to(compute_dtype)
+    mm = minmax(seed.to(torch.float32) if compute_dtype == torch.float32 else seed).cpu().numpy()
+    n_fg = int(mask.sum().item())
+    out = torch.zeros(spatial, dtype=torch.int16, device=dev)
+    if n_fg == 0:
+        return out, 0, 0
+    cap = max(2, (n_fg + 1) & ~1)
+    emb_m = torch.empty((D, cap), dtype=compute_dtype, device=dev)
+    seed_m = torch.empty(cap, dtype=compute_dtype, device=dev)
+    pix = torch.empty(cap, dtype=torch.int32, device=dev)
+    n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = torch.empty(_lib().cb200_compact_workspace_bytes(n_pix), dtype=torch.uint8, device=dev)
+    st = _stream(emb)
+    check(_lib().cb200_greedy_prepare(_ptr(emb), _code(emb, _FLOAT_DTYPES), D, spatial_array(spatial), _ptr(mask),
+                                      _DTYPE_CODE[compute_dtype], float(mm[0]), float(mm[1]), _ptr(emb_m), cap,
+                                      _ptr(seed_m), _ptr(pix), _ptr(n_out), _ptr(ws), st), "cb200_greedy_prepare")
+    inst = torch.empty(cap, dtype=torch.int16, device=dev)
+    res = torch.zeros(2, dtype=torch.int32, device=dev)
+    gws = torch.empty(_lib().cb200_greedy_workspace_bytes(n_fg), dtype=torch.uint8, device=dev)
+    check(_lib().cb200_greedy_cluster(_ptr(emb_m), cap, _ptr(seed_m), n_fg, D, _DTYPE_CODE[compute_dtype],
+                                      float(bandwidth), int(min_object_size), float(seed_thresh),
+                                      int(min_unclustered_sum), _ptr(inst), _ptr(res), _ptr(gws), st),
+          "cb200_greedy_cluster")
+    check(_lib().cb200_scatter_i16(_ptr(inst), _ptr(pix), n_fg, _ptr(out), st), "cb200_scatter_i16")
+    launch_counter["calls"] += 3
+    n_obj, n_iter = (int(x) for x in res.tolist())
+    return out, n_obj, n_iter
+
+
 # --------------------------------------------------------------------------- size filter
 def label_components(seg: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     _require_cuda(seg)

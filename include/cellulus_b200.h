@@ -312,6 +312,26 @@ CB200_API int cb200_assign_labels(const double* points, int64_t n_points, int64_
                         const int32_t* pix_index, void* labels_out, int label_dtype, void* workspace, void* stream);
 
 /*
+ * Greedy seed-and-grow clustering, utils/greedy_cluster.py:46-120,176-253 (clustering = "greedy",
+ * detect.py:162-192): one persistent cooperative kernel runs the whole sequential loop on the device.
+ *   cb200_greedy_prepare: foreground pixels (fg_mask != 0, raster order) -> emb_masked SoA (D x capacity) =
+ *       emb[k] + coordinate_k and seed_masked = (std - max) / (min - max), both in compute_dtype (the
+ *       reference computes 2-D in fp32 and 3-D in the dtype of the stored embeddings); pix_index for the scatter.
+ *   cb200_greedy_cluster: instance_masked (int16, n_points) = 1.. per accepted proposal, 0 otherwise;
+ *       n_objects_and_iterations (device int[2], optional).
+ *   cb200_scatter_i16: dst[pix_index[i]] = src[i].
+ */
+CB200_API int64_t cb200_greedy_workspace_bytes(int64_t n_points);
+CB200_API int cb200_greedy_prepare(const void* emb, int dtype, int num_dims, const int64_t* spatial, const uint8_t* fg_mask,
+                         int compute_dtype, double seed_min, double seed_max, void* emb_masked, int64_t capacity,
+                         void* seed_masked, int32_t* pix_index, long long* n_out, void* workspace, void* stream);
+CB200_API int cb200_greedy_cluster(const void* emb_masked, int64_t stride, const void* seed_masked, int64_t n_points,
+                         int num_dims, int compute_dtype, double bandwidth, int min_object_size, double seed_thresh,
+                         long long min_unclustered_sum, short* instance_masked, int* n_objects_and_iterations,
+                         void* workspace, void* stream);
+CB200_API int cb200_scatter_i16(const short* src, const int32_t* pix_index, int64_t n, short* dst, void* stream);
+
+/*
  * Connected-component size filter, utils/misc.py:11-25 (skimage.measure.label:
  * full connectivity, equal-valued regions, 0 = background, raster-order ids).
  *   cb200_label_components: labels_out int32 (n_pix); *n_labels device int.

@@ -19,6 +19,7 @@ symbols is executed by the functions we call:
   * `mean_shift_segmentation`, `AnchorMeanshift`               (utils/mean_shift.py)
         loaded by file path (the package __init__ pulls matplotlib)
   * scikit-learn 1.9.0 `_mean_shift_single_seed` for per-seed (mode, count, iters)
+  * `Cluster2d` / `Cluster3d`                                  (utils/greedy_cluster.py), loaded by file path
 
 The fixtures cannot be regenerated on the GPU box (no /root/reference there);
 tests only read the committed .npz files.
@@ -250,6 +251,26 @@ def golden_mean_shift(ms):
     np.savez_compressed(os.path.join(HERE, "mean_shift.npz"), **out)
 
 
+def golden_greedy(gc):
+    """`Cluster2d/3d.cluster` of the reference (utils/greedy_cluster.py, loaded by path) on small scenes."""
+    out = {}
+    for name, shape, K, radius, bw, min_size in [("2d", (72, 80), 9, 7.0, 3.0, 10), ("3d", (16, 40, 44), 5, 6.0, 3.0, 20)]:
+        emb, _, _ = synthetic.blob_scene(shape, K, radius=radius, seed=21 + len(shape), offset_sigma=0.3)
+        D = len(shape)
+        pred = emb.astype(np.float64)  # what detect.py reads from the float64 `embeddings` dataset
+        fg = pred[D] < 0.5
+        if D == 2:
+            cl = gc.Cluster2d(width=shape[1], height=shape[0], fg_mask=fg, device="cpu")
+        else:
+            cl = gc.Cluster3d(width=shape[2], height=shape[1], depth=shape[0], fg_mask=fg, device="cpu")
+        seg = cl.cluster(prediction=pred, bandwidth=bw, min_object_size=min_size)
+        out[f"{name}_emb"] = emb
+        out[f"{name}_cfg"] = np.array([bw, min_size], dtype=np.float64)
+        out[f"{name}_labels"] = seg.numpy().astype(np.int16)
+        print("greedy", name, "fg", int(fg.sum()), "instances", int(seg.max()))
+    np.savez_compressed(os.path.join(HERE, "greedy.npz"), **out)
+
+
 def main():
     install_stubs()
     from cellulus.criterions import get_loss
@@ -261,6 +282,7 @@ def main():
     golden_sampler(ZarrDataset)
     golden_tta(UNetModel)
     golden_mean_shift(ms)
+    golden_greedy(load_by_path("ref_greedy_cluster", os.path.join(REF, "cellulus/utils/greedy_cluster.py")))
 
 
 if __name__ == "__main__":

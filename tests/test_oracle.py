@@ -220,3 +220,16 @@ def test_seed_oracle_blur_restatement_is_scipy(shape):
     assert peaks.ndim == 2 and peaks.shape[1] == len(shape)
     if len(peaks):
         assert peaks.min() >= 1 and (peaks.max(0) <= np.array(shape) - 2).all()  # 1-px border excluded
+
+
+@pytest.mark.parametrize("case", ["2d", "3d"])
+def test_greedy_port_matches_reference(golden, case):
+    from oracle import greedy as ogreedy
+
+    g = golden("greedy")
+    emb = g[f"{case}_emb"].astype(np.float64)
+    bw, min_size = g[f"{case}_cfg"]
+    D = emb.shape[0] - 1
+    labels, n_obj, tried = ogreedy.greedy_cluster(emb, emb[D] < 0.5, bw, int(min_size))
+    assert labels.dtype == np.int16 and np.array_equal(labels, g[f"{case}_labels"])
+    assert n_obj == labels.max() and tried >= n_obj
