@@ -184,6 +184,47 @@ def test_fused_loss_edge_cases():
     assert abs(l_neg.item() - l_ref2.item()) <= LOSS_RTOL * abs(l_ref2.item())
 
 
+def test_fused_loss_autograd_generality():
+    """Differentiating `oce_loss` or `regularization_loss` on their own, a weighted mix, and a second backward
+    through a retained graph all agree with the oracle (the common `loss.backward()` path is the fast one)."""
+    from cellulus_b200.criterions import get_loss, oce_loss_fused
+    from cellulus_b200.models import UNetModel
+
+    dev = _dev()
+    out_shape = (60, 60)
+    np.random.seed(5)
+    a, r = osampler.sample_coordinates(out_shape, 10.0, 0.1, 2)
+    anchors, refs = torch.from_numpy(a)[None], torch.from_numpy(r)[None]
+    offsets = torch.from_numpy(synthetic.loss_offsets(1, 2, out_shape, seed=4))
+
+    def oracle_grad(wl, wo, wr):
+        o = offsets.clone().requires_grad_(True)
+        ea = oloss.select_and_add_coordinates(o, anchors)
+        er = oloss.select_and_add_coordinates(o, refs)
+        loss, oce, reg = oloss.oce_loss(ea, er, 10.0, 1e-2)
+        (wl * loss + wo * oce + wr * reg).backward()
+        return o.grad.numpy()
+
+    for wl, wo, wr in [(0.0, 1.0, 0.0), (0.0, 0.0, 1.0), (0.5, 2.0, -1.0), (3.0, 0.0, 0.0)]:
+        o = offsets.to(dev).requires_grad_(True)
+        loss, oce, reg = oce_loss_fused(o, anchors.to(dev), refs.to(dev), 10.0, 1e-2)
+        (wl * loss + wo * oce + wr * reg).backward()
+        assert _rel(o.grad.cpu().numpy(), oracle_grad(wl, wo, wr)) <= 2e-5, (wl, wo, wr)
+    # retained graph: two backward passes accumulate twice the gradient
+    o = offsets.to(dev).requires_grad_(True)
+    loss, _, _ = oce_loss_fused(o, anchors.to(dev), refs.to(dev), 10.0, 1e-2)
+    loss.backward(retain_graph=True)
+    loss.backward()
+    assert _rel(o.grad.cpu().numpy(), 2.0 * oracle_grad(1.0, 0.0, 0.0)) <= LOSS_RTOL
+    # the unfused three-call shape with a weighted mix
+    o = offsets.to(dev).requires_grad_(True)
+    crit = get_loss(temperature=10.0, regularizer_weight=1e-2, density=0.1, num_spatial_dims=2, device=dev)
+    loss, oce, reg = crit(UNetModel.select_and_add_coordinates(o, anchors.to(dev)),
+                          UNetModel.select_and_add_coordinates(o, refs.to(dev)))
+    (0.5 * loss + 2.0 * oce - reg).backward()
+    assert _rel(o.grad.cpu().numpy(), oracle_grad(0.5, 2.0, -1.0)) <= 2e-5
+
+
 def test_fused_loss_bf16_offsets():
     from cellulus_b200.criterions import oce_loss_fused
 

@@ -37,3 +37,25 @@ if what in ("all", "detect"):
         detect_embeddings(d, bandwidth=bench.DET_BW, threshold=bench.DET_THR, reduction_probability=bench.DET_RP,
                           rng="philox")
     torch.cuda.synchronize()
+
+if what in ("all", "brute", "greedy"):
+    from cellulus_b200.utils.mean_shift import segment_embeddings_device
+    import time
+    emb, _, _ = synthetic.blob_scene((64, 256, 256), 200, radius=bench.DET_RADIUS, seed=1)
+    d = torch.from_numpy(emb).to(dev)
+    if what in ("all", "brute"):
+        for _ in range(2):
+            torch.cuda.synchronize(); t0 = time.time()
+            labels, info = segment_embeddings_device(d, bench.DET_BW, bench.DET_THR, 0.1, rng="philox", method="brute")
+            torch.cuda.synchronize()
+            iters = info["iters"][: info["n_seeds"]].double()
+            pair_tests = float((iters + 1).sum().item()) * info["n_fit"]
+            print(f"brute: n_fit {info['n_fit']} seeds {info['n_seeds']} k {info['k']} total {time.time() - t0:.4f} s "
+                  f"pair tests {pair_tests:.3e}")
+    if what in ("all", "greedy"):
+        mask = (d[3] < 0.5).to(torch.uint8)
+        for _ in range(2):
+            torch.cuda.synchronize(); t0 = time.time()
+            inst, n_obj, n_iter = K.greedy_cluster(d, mask, bench.DET_BW, 100)
+            torch.cuda.synchronize()
+            print(f"greedy: fg {int(mask.sum())} objects {n_obj} seeds tried {n_iter} total {time.time() - t0:.4f} s")
