@@ -290,10 +290,10 @@ def run_b200(args):
     N_SETS = 3
     torch.manual_seed(rank)
 
-    def make_steps(memory_format):
+    def make_steps(memory_format, dtype=torch.float32):
         steps = []
         for i in range(N_SETS):
-            off = torch.randn(B, D, *OUT, device=dev).contiguous(memory_format=memory_format)
+            off = torch.randn(B, D, *OUT, device=dev).to(dtype).contiguous(memory_format=memory_format)
             anc, ref = K.sample_pairs(B, (OUT[1], OUT[0]), KAPPA, N_ANCHORS, N_REFS, seed=1234 + 17 * rank + i,
                                       device=dev, dtype=torch.int64)
             steps.append(GraphedLossStep(off, anc, ref, TEMP, REGW))
@@ -332,6 +332,11 @@ def run_b200(args):
     # (2) same op on the planar NCHW tensor the reference's model emits
     steps_pl = make_steps(torch.contiguous_format)
     ms_planar = timed(steps_pl, args.steps, warm)
+    # (2b) bf16 offsets (BASELINE configs[1] trains the U-Net in bf16): bf16 storage, fp32 arithmetic and gradient
+    steps_bf = make_steps(torch.channels_last, torch.bfloat16)
+    ms_bf16 = timed(steps_bf, args.steps, warm)
+    del steps_bf
+    algo_bf16 = B * P * D * 8 * 2 + N_PX * D * 2 + N_PX * D * 4
     peak, peak_src = measured_peak_gbs()
     achieved = ALGO_BYTES / (ms_per_step * 1e-3) / 1e9
     achieved_planar = ALGO_BYTES / (ms_planar * 1e-3) / 1e9
@@ -425,6 +430,12 @@ def run_b200(args):
                        "offsets_layout": "planar NCHW (what the reference's model emits)",
                        "roofline": {"bound": "hbm", "achieved": achieved_planar, "peak": peak, "unit": "GB/s",
                                     "frac": achieved_planar / peak}},
+            "bf16_offsets": {"value": world * N_PX / (ms_bf16 * 1e-3), "unit": "px/s", "ms_per_step": ms_bf16,
+                             "offsets_layout": "channels_last, bf16 storage, fp32 arithmetic, fp32 gradient",
+                             "roofline": {"bound": "hbm", "achieved": algo_bf16 / (ms_bf16 * 1e-3) / 1e9,
+                                          "peak": peak, "unit": "GB/s",
+                                          "frac": algo_bf16 / (ms_bf16 * 1e-3) / 1e9 / peak,
+                                          "algorithmic_bytes_per_launch": algo_bf16}},
             "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_value, "unit": "px/s",
                     "h2d_bytes_per_step": int(h_off.numel() * 4 + h_anc.numel() * 8 + h_ref.numel() * 8),

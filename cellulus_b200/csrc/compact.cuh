@@ -73,33 +73,51 @@ compact_scan_kernel(const int* __restrict__ tile_counts, int64_t n_tiles, long l
   if (threadIdx.x == 0) *total = s_carry;
 }
 
+// All CMP_ITEMS predicates of a thread are evaluated first (independent loads in flight), the per-warp
+// ballots of every item go to shared memory, ONE warp scans the CMP_ITEMS x warps counts, and only then are
+// the selected elements emitted -- two block barriers per 2048-element tile instead of sixteen.
 template <class Pred, class Emit>
 __global__ void __launch_bounds__(CMP_THREADS)
 compact_emit_kernel(Pred pred, Emit emit, int64_t n, const long long* __restrict__ tile_offsets, int64_t capacity) {
+  constexpr int WARPS = CMP_THREADS / 32;
   const int64_t base = (int64_t)blockIdx.x * CMP_TILE;
-  __shared__ int s_warp[CMP_THREADS / 32];
-  long long running = tile_offsets[blockIdx.x];
+  __shared__ int s_cnt[CMP_ITEMS * WARPS];  // [item][warp] -> exclusive prefix after the scan
   const int warp = threadIdx.x >> 5, lane = lane_id();
-#pragma unroll 1
+  unsigned ballots[CMP_ITEMS];
+  bool p[CMP_ITEMS];
+#pragma unroll
   for (int j = 0; j < CMP_ITEMS; ++j) {
     const int64_t i = base + j * CMP_THREADS + threadIdx.x;
-    const bool p = (i < n) && pred(i);
-    const unsigned ballot = __ballot_sync(FULL, p);
-    if (lane == 0) s_warp[warp] = __popc(ballot);
-    __syncthreads();
-    int before = 0, all = 0;
+    p[j] = (i < n) && pred(i);
+  }
 #pragma unroll
-    for (int w = 0; w < CMP_THREADS / 32; ++w) {
-      const int c = s_warp[w];
-      before += (w < warp) ? c : 0;
-      all += c;
+  for (int j = 0; j < CMP_ITEMS; ++j) {
+    ballots[j] = __ballot_sync(FULL, p[j]);
+    if (lane == 0) s_cnt[j * WARPS + warp] = __popc(ballots[j]);
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan of CMP_ITEMS * WARPS (= 64) counts: two per lane
+    static_assert(CMP_ITEMS * WARPS == 64, "scan below assumes 64 counts");
+    const int a = s_cnt[2 * lane], b = s_cnt[2 * lane + 1];
+    int inc = a + b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(FULL, inc, o);
+      if (lane >= o) inc += t;
     }
-    if (p) {
-      const long long dst = running + before + __popc(ballot & ((1u << lane) - 1u));
+    const int excl = inc - a - b;
+    s_cnt[2 * lane] = excl;
+    s_cnt[2 * lane + 1] = excl + a;
+  }
+  __syncthreads();
+  const long long tile_off = tile_offsets[blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < CMP_ITEMS; ++j) {
+    if (p[j]) {
+      const int64_t i = base + j * CMP_THREADS + threadIdx.x;
+      const long long dst = tile_off + s_cnt[j * WARPS + warp] + __popc(ballots[j] & ((1u << lane) - 1u));
       if (dst < capacity) emit(i, dst);
     }
-    running += all;
-    __syncthreads();
   }
 }
 
