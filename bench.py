@@ -290,12 +290,12 @@ def run_b200(args):
     N_SETS = 3
     torch.manual_seed(rank)
 
-    def make_steps(memory_format, dtype=torch.float32):
+    def make_steps(memory_format, dtype=torch.float32, coord_dtype=torch.int64):
         steps = []
         for i in range(N_SETS):
             off = torch.randn(B, D, *OUT, device=dev).to(dtype).contiguous(memory_format=memory_format)
             anc, ref = K.sample_pairs(B, (OUT[1], OUT[0]), KAPPA, N_ANCHORS, N_REFS, seed=1234 + 17 * rank + i,
-                                      device=dev, dtype=torch.int64)
+                                      device=dev, dtype=coord_dtype)
             steps.append(GraphedLossStep(off, anc, ref, TEMP, REGW))
         return steps
 
@@ -337,6 +337,11 @@ def run_b200(args):
     ms_bf16 = timed(steps_bf, args.steps, warm)
     del steps_bf
     algo_bf16 = B * P * D * 8 * 2 + N_PX * D * 2 + N_PX * D * 4
+    # (2c) int16 coordinate lists, the format the device pair sampler hands to the training loop (train.py)
+    steps_i16 = make_steps(torch.channels_last, torch.float32, torch.int16)
+    ms_i16 = timed(steps_i16, args.steps, warm)
+    del steps_i16
+    algo_i16 = B * P * D * 2 * 2 + N_PX * D * 4 * 2
     peak, peak_src = measured_peak_gbs()
     achieved = ALGO_BYTES / (ms_per_step * 1e-3) / 1e9
     achieved_planar = ALGO_BYTES / (ms_planar * 1e-3) / 1e9
@@ -376,7 +381,8 @@ def run_b200(args):
     # DataLoader-side sampler of zarr_dataset.py:198-242): only the offsets cross PCIe
     def e2e_sampled_step(i):
         o = h_off.to(dev, non_blocking=True).requires_grad_(True)
-        a, r = K.sample_pairs(B, (OUT[1], OUT[0]), KAPPA, N_ANCHORS, N_REFS, seed=99, sequence=i, device=dev)
+        a, r = K.sample_pairs(B, (OUT[1], OUT[0]), KAPPA, N_ANCHORS, N_REFS, seed=99, sequence=i, device=dev,
+                                  dtype=torch.int16)  # the training loop's list format
         loss, _, _ = oce_loss_fused(o, a, r, TEMP, REGW)
         loss.backward()
         return loss.item()
@@ -436,6 +442,12 @@ def run_b200(args):
                                           "peak": peak, "unit": "GB/s",
                                           "frac": algo_bf16 / (ms_bf16 * 1e-3) / 1e9 / peak,
                                           "algorithmic_bytes_per_launch": algo_bf16}},
+            "i16_pairs": {"value": world * N_PX / (ms_i16 * 1e-3), "unit": "px/s", "ms_per_step": ms_i16,
+                          "note": "channels_last fp32 offsets, int16 coordinate lists as drawn by the device pair "
+                                  "sampler (the training loop's format; the reference's lists are int64)",
+                          "roofline": {"bound": "hbm", "achieved": algo_i16 / (ms_i16 * 1e-3) / 1e9, "peak": peak,
+                                       "unit": "GB/s", "frac": algo_i16 / (ms_i16 * 1e-3) / 1e9 / peak,
+                                       "algorithmic_bytes_per_launch": algo_i16}},
             "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_value, "unit": "px/s",
                     "h2d_bytes_per_step": int(h_off.numel() * 4 + h_anc.numel() * 8 + h_ref.numel() * 8),
@@ -443,8 +455,8 @@ def run_b200(args):
                     "with_device_pair_sampler": {
                         "value": world * N_PX / e2e_sampled_s.item(), "unit": "px/s",
                         "ms_per_step": e2e_sampled_s.item() * 1e3, "h2d_bytes_per_step": int(h_off.numel() * 4),
-                        "note": "pair lists drawn on the device (same distribution as the reference sampler), "
-                                "sampling kernel inside the timed step"}},
+                        "note": "int16 pair lists drawn on the device (same distribution as the reference "
+                                "sampler), sampling kernel inside the timed step"}},
             "gpu_launches": int(launches * world),
             "clocks": clocks,
             "detect": detect,

@@ -108,9 +108,16 @@ class ZarrDataset(IterableDataset):  # type: ignore
         reference_samples = anchor_samples + self.sample_offsets_within_radius(self.kappa, len(anchor_samples))
         return anchor_samples, reference_samples
 
-    def sample_coordinates_device(self, batch_size, device, seed, sequence=0, dtype=torch.int64):
-        """The same distribution drawn on the GPU: (B, P, D) anchors and references."""
+    def sample_coordinates_device(self, batch_size, device, seed, sequence=0, dtype=None):
+        """The same distribution drawn on the GPU: (B, P, D) anchors and references.
+
+        `dtype=None` picks the narrowest coordinate type that holds the output extent (int16 below 32768
+        pixels per axis): the lists never leave the device, and the fused loss reads them at a quarter of the
+        bytes of the reference's int64 lists.  Pass `torch.int64` for the reference's own format."""
         from cellulus_b200 import kernels as K
+
+        if dtype is None:
+            dtype = torch.int16 if max(self.output_shape[: self.num_spatial_dims]) < 2**15 else torch.int32
 
         return K.sample_pairs(batch_size, self.output_shape[: self.num_spatial_dims], self.kappa,
                               self.get_num_anchors(), self.get_num_references(), seed, sequence, dtype, device)
