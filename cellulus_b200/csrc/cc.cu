@@ -8,29 +8,9 @@
 // then ranked with the order-preserving compaction scan.
 #include "common.cuh"
 #include "compact.cuh"
+#include "unionfind.cuh"
 
 namespace cb200 {
-
-__device__ __forceinline__ int uf_find(const int* parent, int i) {
-  int p = parent[i];
-  while (p != i) {
-    i = p;
-    p = parent[i];
-  }
-  return i;
-}
-
-__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
-  while (true) {
-    a = uf_find(parent, a);
-    b = uf_find(parent, b);
-    if (a == b) return;
-    if (a < b) { const int t = a; a = b; b = t; }  // a > b: hang a under b
-    const int old = atomicMin(parent + a, b);
-    if (old == a) return;  // a was still a root: linked
-    a = old;               // somebody re-rooted a meanwhile; retry from there
-  }
-}
 
 __global__ void __launch_bounds__(256) cc_init_kernel(const int32_t* __restrict__ seg, int64_t n, int* __restrict__ parent) {
   const int64_t gs = (int64_t)gridDim.x * blockDim.x;

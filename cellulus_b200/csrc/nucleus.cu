@@ -1,0 +1,318 @@
+// "nucleus" post-processing for sm_100a (segment.py:52-101): per instance, an Otsu threshold of the raw
+// intensities under the instance, `mask = instance & (raw > threshold)`, holes of the mask filled inside the
+// instance's bounding box (scipy.ndimage.binary_fill_holes: background not reachable from the box border
+// through face neighbours), instances written in ascending id order.
+//
+// Three device stages, all streaming / atomics-bound:
+//   1. cb200_label_stats      per-label raw min / max and bounding box (atomics with a read-before-write test)
+//   2. cb200_label_histogram  per-label histograms: one bin per value for integer images (skimage's bincount
+//                             path), numpy-exact 256 bins over [min, max] for float images
+//      (the O(bins) Otsu tail per label runs on the host, like detect's)
+//   3. cb200_nucleus_fill     union-find over the NON-mask voxels of every bounding box, each box with a
+//                             virtual "outside" node joined to its border; voxels of the mask and voxels not
+//                             connected to the outside get the id (atomicMax = "later ids overwrite")
+#include "common.cuh"
+#include "unionfind.cuh"
+
+namespace cb200 {
+
+template <typename T>
+__device__ __forceinline__ double raw_as_double(const T* p, int64_t i) {
+  return (double)p[i];
+}
+
+// order-preserving map double -> uint64 (so that atomicMin / atomicMax work on the bits)
+__device__ __forceinline__ unsigned long long ordered_bits(double v) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+struct LabelStats {
+  unsigned long long* raw_min;  // ordered bits
+  unsigned long long* raw_max;
+  int* box;  // [label][6]: lo z, y, x, hi z, y, x (inclusive)
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+label_stats_kernel(const int32_t* __restrict__ seg, const T* __restrict__ raw, int64_t n, int ex, int ey, int max_label,
+                   LabelStats s) {
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
+    const int32_t l = seg[i];
+    if (l <= 0 || l > max_label) continue;
+    const unsigned long long v = ordered_bits(raw_as_double<T>(raw, i));
+    if (v < s.raw_min[l]) atomicMin(s.raw_min + l, v);
+    if (v > s.raw_max[l]) atomicMax(s.raw_max + l, v);
+    const int x = (int)(i % ex);
+    const int64_t r = i / ex;
+    const int c[3] = {(int)(r / ey), (int)(r % ey), x};
+    int* b = s.box + (int64_t)l * 6;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (c[k] < b[k]) atomicMin(b + k, c[k]);
+      if (c[k] > b[3 + k]) atomicMax(b + 3 + k, c[k]);
+    }
+  }
+}
+
+__global__ void label_stats_init_kernel(int max_label, LabelStats s) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l > max_label) return;
+  s.raw_min[l] = ~0ull;
+  s.raw_max[l] = 0ull;
+  for (int k = 0; k < 3; ++k) {
+    s.box[(int64_t)l * 6 + k] = INT32_MAX;
+    s.box[(int64_t)l * 6 + 3 + k] = -1;
+  }
+}
+
+__global__ void label_stats_decode_kernel(int max_label, LabelStats s, double* __restrict__ out_min,
+                                          double* __restrict__ out_max) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l > max_label) return;
+  auto decode = [](unsigned long long o) {
+    const unsigned long long b = (o >> 63) ? (o & 0x7fffffffffffffffull) : ~o;
+    return __longlong_as_double((long long)b);
+  };
+  const bool present = s.box[(int64_t)l * 6 + 3] >= 0;
+  out_min[l] = present ? decode(s.raw_min[l]) : 0.0;
+  out_max[l] = present ? decode(s.raw_max[l]) : 0.0;
+}
+
+// integer images: hist[offset[l] + (v - min[l])] += 1
+template <typename T>
+__global__ void __launch_bounds__(256)
+label_bincount_kernel(const int32_t* __restrict__ seg, const T* __restrict__ raw, int64_t n, int max_label,
+                      const double* __restrict__ raw_min, const int64_t* __restrict__ offset,
+                      unsigned int* __restrict__ hist) {
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
+    const int32_t l = seg[i];
+    if (l <= 0 || l > max_label) continue;
+    const int64_t bin = (int64_t)raw[i] - (int64_t)raw_min[l];
+    atomicAdd(hist + offset[l] + bin, 1u);
+  }
+}
+
+// float images: np.histogram(values, nbins) over [min, max] of the label; edges[l][nbins + 1] as numpy
+// builds them (host linspace in the image's dtype).  The bin is the one with edges[b] <= v < edges[b+1]
+// (last bin closed), which is what numpy's index arithmetic plus its two corrections arrive at.
+template <typename T>
+__global__ void __launch_bounds__(256)
+label_histogram_kernel(const int32_t* __restrict__ seg, const T* __restrict__ raw, int64_t n, int max_label,
+                       const double* __restrict__ edges, int nbins, unsigned int* __restrict__ hist) {
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
+    const int32_t l = seg[i];
+    if (l <= 0 || l > max_label) continue;
+    const double v = raw_as_double<T>(raw, i);
+    const double* e = edges + (int64_t)l * (nbins + 1);
+    const double first = e[0], last = e[nbins];
+    if (!(v >= first) || !(v <= last)) continue;  // NaN
+    int idx = 0;
+    if (last > first) {
+      idx = (int)(((v - first) / (last - first)) * (double)nbins);
+      idx = min(max(idx, 0), nbins - 1);
+      while (idx > 0 && v < e[idx]) --idx;
+      while (idx < nbins - 1 && v >= e[idx + 1]) ++idx;
+    }
+    atomicAdd(hist + (int64_t)l * nbins + idx, 1u);
+  }
+}
+
+// ------------------------------------------------------------------ hole filling
+struct Boxes {
+  int n;                      // instances
+  const int32_t* ids;         // [n] ascending
+  const double* thresholds;   // [n]
+  const int32_t* box;         // [n][6] lo z,y,x, hi z,y,x (inclusive)
+  const int64_t* offset;      // [n + 1] prefix of box volumes
+};
+
+struct BoxVoxel {
+  int k;          // instance
+  int z, y, x;    // position inside the box
+  int bz, by, bx; // box extents
+  int64_t pixel;  // linear index in the image
+};
+
+__device__ __forceinline__ BoxVoxel locate(const Boxes& b, int64_t j, int ex, int ey) {
+  int lo = 0, hi = b.n - 1;  // last k with offset[k] <= j
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (b.offset[mid] <= j) lo = mid;
+    else hi = mid - 1;
+  }
+  BoxVoxel v;
+  v.k = lo;
+  const int32_t* bb = b.box + (int64_t)lo * 6;
+  v.bz = bb[3] - bb[0] + 1;
+  v.by = bb[4] - bb[1] + 1;
+  v.bx = bb[5] - bb[2] + 1;
+  const int64_t local = j - b.offset[lo];
+  v.x = (int)(local % v.bx);
+  const int64_t r = local / v.bx;
+  v.y = (int)(r % v.by);
+  v.z = (int)(r / v.by);
+  v.pixel = ((int64_t)(bb[0] + v.z) * ey + (bb[1] + v.y)) * ex + (bb[2] + v.x);
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+fill_init_kernel(const int32_t* __restrict__ seg, const T* __restrict__ raw, Boxes b, int64_t total, int ex, int ey,
+                 int* __restrict__ parent) {
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total + b.n; j += gs) {
+    if (j >= total) {  // the virtual "outside" node of instance j - total
+      parent[j] = (int)j;
+      continue;
+    }
+    const BoxVoxel v = locate(b, j, ex, ey);
+    const bool in_mask = seg[v.pixel] == b.ids[v.k] && raw_as_double<T>(raw, v.pixel) > b.thresholds[v.k];
+    parent[j] = in_mask ? -1 : (int)j;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+fill_merge_kernel(Boxes b, int64_t total, int ex, int ey, int num_dims, int* parent) {
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gs) {
+    if (parent[j] < 0) continue;
+    const BoxVoxel v = locate(b, j, ex, ey);
+    const bool border = v.x == 0 || v.x == v.bx - 1 || v.y == 0 || v.y == v.by - 1 ||
+                        (num_dims == 3 && (v.z == 0 || v.z == v.bz - 1));
+    if (border) uf_union(parent, (int)j, (int)(total + v.k));
+    if (v.x > 0 && parent[j - 1] >= 0) uf_union(parent, (int)j, (int)(j - 1));
+    if (v.y > 0 && parent[j - v.bx] >= 0) uf_union(parent, (int)j, (int)(j - v.bx));
+    if (v.z > 0 && parent[j - (int64_t)v.bx * v.by] >= 0) uf_union(parent, (int)j, (int)(j - (int64_t)v.bx * v.by));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+fill_write_kernel(Boxes b, int64_t total, int ex, int ey, const int* __restrict__ parent, int32_t* __restrict__ out) {
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gs) {
+    const BoxVoxel v = locate(b, j, ex, ey);
+    bool covered = parent[j] < 0;  // in the thresholded mask
+    if (!covered) covered = uf_find(parent, (int)j) != uf_find(parent, (int)(total + v.k));  // a hole
+    if (covered) atomicMax(out + v.pixel, b.ids[v.k]);
+  }
+}
+
+struct StatsWorkspace {
+  static int64_t bytes(int max_label) { return (int64_t)(max_label + 1) * (8 + 8) + 256; }
+};
+
+}  // namespace cb200
+
+using namespace cb200;
+
+extern "C" {
+
+int cb200_label_stats(const int32_t* seg, const void* raw, int raw_dtype, int num_dims, const int64_t* spatial,
+                      int max_label, double* raw_min, double* raw_max, int32_t* box, void* workspace, void* stream) {
+  if (!seg || !raw || !spatial || !raw_min || !raw_max || !box || !workspace || max_label < 0) return CB200_EINVAL;
+  if (num_dims != 2 && num_dims != 3) return CB200_EUNSUPPORTED;
+  int64_t n = 1;
+  for (int k = 0; k < num_dims; ++k) {
+    if (spatial[k] <= 0 || spatial[k] > INT32_MAX) return CB200_EINVAL;
+    n *= spatial[k];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ex = (int)spatial[num_dims - 1], ey = (int)spatial[num_dims - 2];
+  LabelStats s;
+  s.raw_min = static_cast<unsigned long long*>(workspace);
+  s.raw_max = s.raw_min + (max_label + 1);
+  s.box = box;
+  const int tb = (max_label + 1 + 255) / 256;
+  label_stats_init_kernel<<<tb, 256, 0, st>>>(max_label, s);
+  CB200_LAUNCH_CHECK();
+  const int blocks = grid_for(n, 256, 4, 16);
+#define CB200_STATS(T) label_stats_kernel<T><<<blocks, 256, 0, st>>>(seg, (const T*)raw, n, ex, ey, max_label, s)
+  if (raw_dtype == CB200_F32) CB200_STATS(float);
+  else if (raw_dtype == CB200_F64) CB200_STATS(double);
+  else if (raw_dtype == CB200_U8) CB200_STATS(uint8_t);
+  else if (raw_dtype == CB200_U16) CB200_STATS(uint16_t);
+  else return CB200_EUNSUPPORTED;
+#undef CB200_STATS
+  CB200_LAUNCH_CHECK();
+  label_stats_decode_kernel<<<tb, 256, 0, st>>>(max_label, s, raw_min, raw_max);
+  CB200_LAUNCH_CHECK();
+  return CB200_OK;
+}
+
+int64_t cb200_label_stats_workspace_bytes(int max_label) { return max_label < 0 ? 0 : StatsWorkspace::bytes(max_label); }
+
+int cb200_label_histogram(const int32_t* seg, const void* raw, int raw_dtype, int64_t n_pix, int max_label,
+                          const double* raw_min, const int64_t* hist_offset, const double* edges, int nbins,
+                          unsigned int* hist, void* stream) {
+  if (!seg || !raw || !hist || n_pix < 0 || max_label < 0) return CB200_EINVAL;
+  if (n_pix == 0) return CB200_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = grid_for(n_pix, 256, 4, 16);
+  if (raw_dtype == CB200_U8 || raw_dtype == CB200_U16) {
+    if (!raw_min || !hist_offset) return CB200_EINVAL;
+    if (raw_dtype == CB200_U8)
+      label_bincount_kernel<uint8_t><<<blocks, 256, 0, st>>>(seg, (const uint8_t*)raw, n_pix, max_label, raw_min,
+                                                            hist_offset, hist);
+    else
+      label_bincount_kernel<uint16_t><<<blocks, 256, 0, st>>>(seg, (const uint16_t*)raw, n_pix, max_label, raw_min,
+                                                             hist_offset, hist);
+  } else if (raw_dtype == CB200_F32 || raw_dtype == CB200_F64) {
+    if (!edges || nbins <= 0) return CB200_EINVAL;
+    if (raw_dtype == CB200_F32)
+      label_histogram_kernel<float><<<blocks, 256, 0, st>>>(seg, (const float*)raw, n_pix, max_label, edges, nbins, hist);
+    else
+      label_histogram_kernel<double><<<blocks, 256, 0, st>>>(seg, (const double*)raw, n_pix, max_label, edges, nbins,
+                                                             hist);
+  } else {
+    return CB200_EUNSUPPORTED;
+  }
+  CB200_LAUNCH_CHECK();
+  return CB200_OK;
+}
+
+int64_t cb200_nucleus_fill_workspace_bytes(int64_t total_box_voxels, int n_instances) {
+  if (total_box_voxels < 0 || n_instances < 0) return 0;
+  return (total_box_voxels + n_instances) * 4 + 256;
+}
+
+int cb200_nucleus_fill(const int32_t* seg, const void* raw, int raw_dtype, int num_dims, const int64_t* spatial,
+                       int n_instances, const int32_t* ids, const double* thresholds, const int32_t* boxes,
+                       const int64_t* box_offset, int64_t total_box_voxels, int32_t* out, void* workspace,
+                       void* stream) {
+  if (!seg || !raw || !spatial || !out || n_instances < 0) return CB200_EINVAL;
+  if (num_dims != 2 && num_dims != 3) return CB200_EUNSUPPORTED;
+  int64_t n = 1;
+  for (int k = 0; k < num_dims; ++k) {
+    if (spatial[k] <= 0 || spatial[k] > INT32_MAX) return CB200_EINVAL;
+    n *= spatial[k];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  CB200_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(int32_t) * (size_t)n, st));
+  if (n_instances == 0 || total_box_voxels == 0) return CB200_OK;
+  if (!ids || !thresholds || !boxes || !box_offset || !workspace) return CB200_EINVAL;
+  if (total_box_voxels + n_instances > INT32_MAX) return CB200_EUNSUPPORTED;  // int parents
+  const int ex = (int)spatial[num_dims - 1], ey = (int)spatial[num_dims - 2];
+  Boxes b{n_instances, ids, thresholds, boxes, box_offset};
+  int* parent = static_cast<int*>(workspace);
+  const int blocks = grid_for(total_box_voxels + n_instances, 256, 2, 16);
+#define CB200_FILL_INIT(T) \
+  fill_init_kernel<T><<<blocks, 256, 0, st>>>(seg, (const T*)raw, b, total_box_voxels, ex, ey, parent)
+  if (raw_dtype == CB200_F32) CB200_FILL_INIT(float);
+  else if (raw_dtype == CB200_F64) CB200_FILL_INIT(double);
+  else if (raw_dtype == CB200_U8) CB200_FILL_INIT(uint8_t);
+  else if (raw_dtype == CB200_U16) CB200_FILL_INIT(uint16_t);
+  else return CB200_EUNSUPPORTED;
+#undef CB200_FILL_INIT
+  CB200_LAUNCH_CHECK();
+  fill_merge_kernel<<<blocks, 256, 0, st>>>(b, total_box_voxels, ex, ey, num_dims, parent);
+  CB200_LAUNCH_CHECK();
+  fill_write_kernel<<<blocks, 256, 0, st>>>(b, total_box_voxels, ex, ey, parent, out);
+  CB200_LAUNCH_CHECK();
+  return CB200_OK;
+}
+
+}  // extern "C"

@@ -21,7 +21,11 @@ from cellulus_b200.utils import mean_shift as MS
 def otsu_from_histogram(counts: np.ndarray, edges: np.ndarray):
     """The O(nbins) tail of scikit-image's `threshold_otsu` (host, 256 numbers):
     float32 counts, bin centres, argmax of w1*w2*(mu1-mu2)^2, returns a bin centre."""
-    bin_centers = (edges[:-1] + edges[1:]) / 2.0
+    return otsu_from_centers(counts, (edges[:-1] + edges[1:]) / 2.0)
+
+
+def otsu_from_centers(counts: np.ndarray, bin_centers: np.ndarray):
+    """Same tail for any histogram given as (counts, bin centres) -- integer images have one bin per value."""
     counts = counts.astype("float32", copy=False)
     weight1 = np.cumsum(counts)
     weight2 = np.cumsum(counts[::-1])[::-1]

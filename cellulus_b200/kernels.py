@@ -606,3 +606,78 @@ def size_filter_(seg: torch.Tensor, min_size: int) -> Tuple[torch.Tensor, torch.
     check(rc, "cb200_size_filter")
     launch_counter["calls"] += 1
     return labels, n_labels
+
+
+# --------------------------------------------------------------------------- "cell" post-processing
+def edt_within(mask: torch.Tensor, radius: float) -> torch.Tensor:
+    """`cb200_edt_within`: `distance_transform_edt(mask) < radius` as a uint8 mask (2-D / 3-D)."""
+    _require_cuda(mask)
+    assert mask.dtype in (torch.uint8, torch.bool) and mask.is_contiguous() and mask.ndim in (2, 3)
+    src = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+    out = torch.empty_like(src)
+    ws = torch.empty(_lib().cb200_edt_workspace_bytes(src.numel()), dtype=torch.uint8, device=src.device)
+    rc = _lib().cb200_edt_within(_ptr(src), src.ndim, spatial_array(src.shape), float(radius), _ptr(out), _ptr(ws),
+                                 _stream(src))
+    check(rc, "cb200_edt_within")
+    launch_counter["calls"] += 1
+    return out
+
+
+def grow_shrink_(seg: torch.Tensor, grow_distance: float, shrink_distance: float) -> torch.Tensor:
+    """`cb200_grow_shrink`, in place on int32 labels: segment.py:47-50."""
+    _require_cuda(seg)
+    assert seg.dtype == torch.int32 and seg.is_contiguous() and seg.ndim in (2, 3)
+    ws = torch.empty(_lib().cb200_edt_workspace_bytes(seg.numel()), dtype=torch.uint8, device=seg.device)
+    rc = _lib().cb200_grow_shrink(_ptr(seg), seg.ndim, spatial_array(seg.shape), float(grow_distance),
+                                  float(shrink_distance), _ptr(ws), _stream(seg))
+    check(rc, "cb200_grow_shrink")
+    launch_counter["calls"] += 1
+    return seg
+
+
+# --------------------------------------------------------------------------- "nucleus" post-processing
+_RAW_DTYPES = (torch.float32, torch.float64, torch.uint8, torch.uint16)
+
+
+def label_stats(seg: torch.Tensor, raw: torch.Tensor, max_label: int):
+    """`cb200_label_stats`: per label id in [0, max_label] -> (raw_min, raw_max) float64 and box (.., 6) int32
+    = lo z,y,x, hi z,y,x inclusive (hi < 0: label absent)."""
+    _require_cuda(seg, raw)
+    assert seg.dtype == torch.int32 and seg.is_contiguous() and raw.is_contiguous() and raw.shape == seg.shape
+    dev = seg.device
+    mn = torch.empty(max_label + 1, dtype=torch.float64, device=dev)
+    mx = torch.empty_like(mn)
+    box = torch.empty((max_label + 1, 6), dtype=torch.int32, device=dev)
+    ws = torch.empty(_lib().cb200_label_stats_workspace_bytes(max_label), dtype=torch.uint8, device=dev)
+    rc = _lib().cb200_label_stats(_ptr(seg), _ptr(raw), _code(raw, _RAW_DTYPES), seg.ndim, spatial_array(seg.shape),
+                                  int(max_label), _ptr(mn), _ptr(mx), _ptr(box), _ptr(ws), _stream(seg))
+    check(rc, "cb200_label_stats")
+    launch_counter["calls"] += 1
+    return mn, mx, box
+
+
+def label_histogram(seg, raw, max_label, hist, raw_min=None, hist_offset=None, edges=None, nbins=0):
+    """`cb200_label_histogram` into the zeroed int32 tensor `hist`."""
+    _require_cuda(seg, raw, hist)
+    assert hist.dtype == torch.int32 and hist.is_contiguous()
+    rc = _lib().cb200_label_histogram(_ptr(seg), _ptr(raw), _code(raw, _RAW_DTYPES), seg.numel(), int(max_label),
+                                      _ptr(raw_min), _ptr(hist_offset), _ptr(edges), int(nbins), _ptr(hist),
+                                      _stream(seg))
+    check(rc, "cb200_label_histogram")
+    launch_counter["calls"] += 1
+    return hist
+
+
+def nucleus_fill(seg, raw, ids, thresholds, boxes, box_offset, total_box_voxels):
+    """`cb200_nucleus_fill`: thresholded instance masks with their holes filled -> int32 label image."""
+    _require_cuda(seg, raw)
+    out = torch.empty_like(seg)
+    n_inst = int(ids.numel())
+    ws = torch.empty(_lib().cb200_nucleus_fill_workspace_bytes(int(total_box_voxels), n_inst), dtype=torch.uint8,
+                     device=seg.device)
+    rc = _lib().cb200_nucleus_fill(_ptr(seg), _ptr(raw), _code(raw, _RAW_DTYPES), seg.ndim, spatial_array(seg.shape),
+                                   n_inst, _ptr(ids), _ptr(thresholds), _ptr(boxes), _ptr(box_offset),
+                                   int(total_box_voxels), _ptr(out), _ptr(ws), _stream(seg))
+    check(rc, "cb200_nucleus_fill")
+    launch_counter["calls"] += 1
+    return out

@@ -1,30 +1,98 @@
 """`segment(inference_config)` (`cellulus/segment.py:13-108`): post-processing of the detection.
 
-Only `size_filter` (`utils/misc.py:11-25`) is on the hot path and runs on the device
-(`cb200_size_filter`).  The morphological grow/shrink ("cell") and per-instance Otsu + hole filling
-("nucleus") are SURVEY §8f "next" rows; they are carried out here with scipy on the host exactly as the
-reference writes them so that `infer()` completes end to end.
+All three pixel-heavy steps run on the device: the grow / shrink of "cell" (`cb200_grow_shrink`: two
+thresholded Euclidean distance transforms), the per-instance Otsu + hole filling of "nucleus"
+(`cb200_label_stats`, `cb200_label_histogram`, `cb200_nucleus_fill`; only the O(bins) Otsu tail per instance
+is host arithmetic) and `size_filter` (`cb200_size_filter`, `utils/misc.py:11-25`).
 """
 
 from __future__ import annotations
 
 import numpy as np
-from scipy.ndimage import binary_fill_holes
-from scipy.ndimage import distance_transform_edt as dtedt
 
 from cellulus_b200 import zarr_lite
 from cellulus_b200.datasets.meta_data import DatasetMetaData
 from cellulus_b200.utils.misc import size_filter
 
 
-def _otsu(values: np.ndarray):
-    from cellulus_b200.detect import otsu_from_histogram
+def _bin_edges(lo, hi, dtype, nbins=256):
+    """The edges `np.histogram(values, nbins)` builds for values of `dtype` spanning [lo, hi]."""
+    first, last = dtype.type(lo), dtype.type(hi)
+    return np.linspace(first, last, nbins + 1, endpoint=True, dtype=np.result_type(first, last, dtype))
 
-    first = values.reshape(-1)[0]
-    if np.all(values == first):
-        return first
-    counts, edges = np.histogram(values.reshape(-1), 256)
-    return otsu_from_histogram(counts, edges)
+
+def nucleus(segmentation: np.ndarray, raw_image: np.ndarray, device="cuda") -> np.ndarray:
+    """`segment.py:52-101` on the device; numpy in, numpy out (a new array like the reference's dataset)."""
+    import torch
+
+    from cellulus_b200 import kernels as K
+    from cellulus_b200.detect import otsu_from_centers
+
+    seg_np = np.ascontiguousarray(segmentation)
+    out_dtype = seg_np.dtype
+    raw_np = np.ascontiguousarray(raw_image)
+    if raw_np.dtype not in (np.float32, np.float64, np.uint8, np.uint16):
+        raise TypeError(f"nucleus post-processing: raw dtype {raw_np.dtype} is not supported "
+                        "(float32, float64, uint8, uint16)")
+    seg = torch.from_numpy(seg_np.astype(np.int32)).to(device)
+    raw = torch.from_numpy(raw_np).to(device)
+    max_label = int(seg.max().item()) if seg.numel() else 0
+    if max_label <= 0:
+        return np.zeros_like(seg_np)
+    mn_t, mx_t, box_t = K.label_stats(seg, raw, max_label)
+    mn, mx, box = mn_t.cpu().numpy(), mx_t.cpu().numpy(), box_t.cpu().numpy()
+    ids = np.nonzero(box[:, 3] >= 0)[0]
+    ids = ids[ids != 0]
+    integer = np.issubdtype(raw_np.dtype, np.integer)
+    thresholds = np.empty(len(ids), np.float64)
+    if integer:  # skimage: one bin per value in [min, max] of the instance
+        span = np.zeros(max_label + 1, np.int64)
+        span[ids] = (mx[ids] - mn[ids]).astype(np.int64) + 1
+        offset = np.concatenate([[0], np.cumsum(span)[:-1]])
+        hist = torch.zeros(int(span.sum()), dtype=torch.int32, device=device)
+        K.label_histogram(seg, raw, max_label, hist, raw_min=mn_t,
+                          hist_offset=torch.from_numpy(offset).to(device))
+        counts = hist.cpu().numpy()
+        for n, i in enumerate(ids):
+            if mn[i] == mx[i]:
+                thresholds[n] = mn[i]  # constant: skimage returns that value
+            else:
+                thresholds[n] = otsu_from_centers(counts[offset[i]:offset[i] + span[i]],
+                                                  np.arange(int(mn[i]), int(mx[i]) + 1))
+    else:  # np.histogram, 256 bins over [min, max] of the instance, edges in the image's dtype
+        nbins = 256
+        edges = np.zeros((max_label + 1, nbins + 1), np.float64)
+        for i in ids:
+            edges[i] = _bin_edges(mn[i], mx[i], raw_np.dtype, nbins)
+        hist = torch.zeros((max_label + 1) * nbins, dtype=torch.int32, device=device)
+        K.label_histogram(seg, raw, max_label, hist, edges=torch.from_numpy(edges).to(device), nbins=nbins)
+        counts = hist.cpu().numpy().reshape(max_label + 1, nbins)
+        for n, i in enumerate(ids):
+            if mn[i] == mx[i]:
+                thresholds[n] = mn[i]
+            else:
+                e = _bin_edges(mn[i], mx[i], raw_np.dtype, nbins)
+                thresholds[n] = otsu_from_centers(counts[i], (e[:-1] + e[1:]) / 2.0)
+    boxes = box[ids].astype(np.int32)
+    volumes = np.prod(boxes[:, 3:].astype(np.int64) - boxes[:, :3] + 1, axis=1)
+    box_offset = np.concatenate([[0], np.cumsum(volumes)]).astype(np.int64)
+    out = K.nucleus_fill(seg, raw, torch.from_numpy(ids.astype(np.int32)).to(device),
+                         torch.from_numpy(thresholds).to(device), torch.from_numpy(boxes).to(device),
+                         torch.from_numpy(box_offset).to(device), int(box_offset[-1]))
+    return out.cpu().numpy().astype(out_dtype)
+
+
+def grow_shrink(segmentation: np.ndarray, grow_distance, shrink_distance, device="cuda") -> np.ndarray:
+    """`segment.py:46-50` (two Euclidean distance transforms and their thresholds) on the device
+    (`cb200_grow_shrink`); numpy in, numpy out, `segmentation` is modified in place like the reference's."""
+    import torch
+
+    from cellulus_b200 import kernels as K
+
+    seg = torch.from_numpy(np.ascontiguousarray(segmentation).astype(np.int32)).to(device)
+    K.grow_shrink_(seg, grow_distance, shrink_distance)
+    segmentation[...] = seg.cpu().numpy().astype(segmentation.dtype)
+    return segmentation
 
 
 def segment(inference_config) -> None:
@@ -46,21 +114,9 @@ def segment(inference_config) -> None:
     for sample in range(meta.num_samples):
         for k in range(inference_config.num_bandwidths):
             segmentation = np.asarray(ds[sample, k])
-            if inference_config.post_processing == "cell":  # segment.py:41-51
-                expanded = dtedt(segmentation == 0) < inference_config.grow_distance
-                segmentation[dtedt(expanded) < inference_config.shrink_distance] = 0
-                out = segmentation
-            else:  # "nucleus", segment.py:52-101
-                out = np.zeros_like(segmentation)
-                raw_image = np.asarray(ds_raw[sample, 0])
-                for id_ in np.unique(segmentation):
-                    if id_ == 0:
-                        continue
-                    m = segmentation == id_
-                    idx = np.where(m)
-                    box = tuple(slice(int(i.min()), int(i.max()) + 1) for i in idx)
-                    mask = m & (raw_image > _otsu(raw_image[m]))
-                    mask[box] = binary_fill_holes(mask[box])
-                    out[mask] = id_
+            if inference_config.post_processing == "cell":  # segment.py:41-51, on the device
+                out = grow_shrink(segmentation, inference_config.grow_distance, inference_config.shrink_distance)
+            else:  # "nucleus", segment.py:52-101, on the device
+                out = nucleus(segmentation, np.asarray(ds_raw[sample, 0]))
             # size filter: remove small objects (segment.py:104-108) -- device connected components
             ds_segmented[sample, k, ...] = size_filter(out, inference_config.min_size).astype(np.uint16)

@@ -344,6 +344,47 @@ CB200_API int cb200_label_components(const int32_t* seg, int num_dims, const int
 CB200_API int cb200_size_filter(int32_t* seg, int num_dims, const int64_t* spatial, int64_t min_size,
                       int32_t* labels_out, int* n_labels, void* workspace, void* stream);
 
+/*
+ * "cell" post-processing, segment.py:42-52 (scipy.ndimage.distance_transform_edt, unit sampling):
+ *   cb200_edt_within : out[p] = (dtedt(input)[p] < radius); `input` uint8, nonzero = inside.  An input without
+ *                      any zero element measures distances to the virtual element (-1, 0, ..., 0), as scipy does.
+ *   cb200_grow_shrink: in place on int32 labels,
+ *                        expanded = dtedt(seg == 0) < grow_distance        (:47-48)
+ *                        seg[dtedt(expanded) < shrink_distance] = 0        (:49-50)
+ *   radius < 16384; num_dims 2 or 3.
+ */
+CB200_API int64_t cb200_edt_workspace_bytes(int64_t n_pix);
+CB200_API int cb200_edt_within(const uint8_t* input, int num_dims, const int64_t* spatial, double radius, uint8_t* out,
+                     void* workspace, void* stream);
+CB200_API int cb200_grow_shrink(int32_t* seg, int num_dims, const int64_t* spatial, double grow_distance,
+                      double shrink_distance, void* workspace, void* stream);
+
+/*
+ * "nucleus" post-processing, segment.py:52-101: per instance an Otsu threshold of the raw intensities under
+ * the instance (skimage.filters.threshold_otsu), mask = instance & (raw > threshold), holes filled inside the
+ * instance's bounding box (scipy.ndimage.binary_fill_holes), ids written in ascending order.
+ *   raw dtype: CB200_U8 / CB200_U16 (skimage's one-bin-per-value histogram) or CB200_F32 / CB200_F64
+ *   (np.histogram, 256 bins over the instance's [min, max]).
+ *   cb200_label_stats     : per label id in [0, max_label]: raw_min / raw_max (double) and box[id][6] =
+ *                           lo z,y,x, hi z,y,x (inclusive; hi < 0 = label absent; z = 0 in 2-D)
+ *   cb200_label_histogram : integer raw: hist[hist_offset[id] + (v - raw_min[id])]++ ;
+ *                           float raw  : hist[id * nbins + b]++ with edges[id][nbins + 1] as numpy builds them
+ *                           (`hist` zeroed by the caller; the O(bins) Otsu tail runs on the host)
+ *   cb200_nucleus_fill    : out (int32, zeroed by the call) gets ids[k] on mask_k and on its holes; boxes[k][6]
+ *                           and box_offset[k] = prefix sum of the box volumes (n_instances + 1 entries)
+ */
+CB200_API int64_t cb200_label_stats_workspace_bytes(int max_label);
+CB200_API int cb200_label_stats(const int32_t* seg, const void* raw, int raw_dtype, int num_dims, const int64_t* spatial,
+                      int max_label, double* raw_min, double* raw_max, int32_t* box, void* workspace, void* stream);
+CB200_API int cb200_label_histogram(const int32_t* seg, const void* raw, int raw_dtype, int64_t n_pix, int max_label,
+                          const double* raw_min, const int64_t* hist_offset, const double* edges, int nbins,
+                          unsigned int* hist, void* stream);
+CB200_API int64_t cb200_nucleus_fill_workspace_bytes(int64_t total_box_voxels, int n_instances);
+CB200_API int cb200_nucleus_fill(const int32_t* seg, const void* raw, int raw_dtype, int num_dims, const int64_t* spatial,
+                       int n_instances, const int32_t* ids, const double* thresholds, const int32_t* boxes,
+                       const int64_t* box_offset, int64_t total_box_voxels, int32_t* out, void* workspace,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

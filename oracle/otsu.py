@@ -27,6 +27,12 @@ def threshold_otsu(image: np.ndarray, nbins: int = 256):
     first = flat[0]
     if np.all(image == first):
         return first
+    if np.issubdtype(flat.dtype, np.integer):
+        # `exposure.histogram` takes its bincount path for integer images: one bin per value in
+        # [min, max], the bin centres are those integers
+        lo, hi = int(flat.min()), int(flat.max())
+        counts = np.bincount((flat.astype(np.int64) - lo).ravel(), minlength=hi - lo + 1)
+        return otsu_from_centers(counts, np.arange(lo, hi + 1))
     counts, edges = np.histogram(flat, nbins)
     return otsu_from_histogram(counts, edges)
 
@@ -34,7 +40,10 @@ def threshold_otsu(image: np.ndarray, nbins: int = 256):
 def otsu_from_histogram(counts: np.ndarray, edges: np.ndarray):
     """The O(nbins) tail of `threshold_otsu`, split out because the CUDA path
     computes the histogram on the device and finishes with these few lines."""
-    bin_centers = (edges[:-1] + edges[1:]) / 2.0
+    return otsu_from_centers(counts, (edges[:-1] + edges[1:]) / 2.0)
+
+
+def otsu_from_centers(counts: np.ndarray, bin_centers: np.ndarray):
     counts = counts.astype("float32", copy=False)
     weight1 = np.cumsum(counts)
     weight2 = np.cumsum(counts[::-1])[::-1]

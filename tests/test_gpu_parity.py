@@ -12,11 +12,13 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+from cellulus_b200 import kernels as K  # noqa: E402
 from cellulus_b200 import synthetic  # noqa: E402
 from oracle import mean_shift as oms  # noqa: E402
 from oracle import oce_loss as oloss  # noqa: E402
 from oracle import otsu as ootsu  # noqa: E402
 from oracle import sampler as osampler  # noqa: E402
+from oracle import post_process as opost  # noqa: E402
 from oracle import size_filter as osize  # noqa: E402
 from oracle import tta as otta  # noqa: E402
 
@@ -601,3 +603,92 @@ def test_size_filter_exact(shape):
         ref = osize.size_filter(b, min_size)
         assert np.array_equal(a, b)  # in-place removal set: exact
         assert np.array_equal(np.asarray(out), np.asarray(ref))
+
+
+# ---------------------------------------------------------------------------------------------------
+# "cell" post-processing (segment.py:41-51): thresholded Euclidean distance transforms, exact
+def _label_blobs(shape, n_blobs, radius, seed):
+    rng = np.random.default_rng(seed)
+    seg = np.zeros(shape, np.int32)
+    grids = np.indices(shape)
+    for k in range(n_blobs):
+        c = [rng.uniform(0, s) for s in shape]
+        r = rng.uniform(0.5 * radius, radius)
+        d2 = sum((g - ci) ** 2 for g, ci in zip(grids, c))
+        seg[d2 < r * r] = k + 1
+    return seg
+
+
+@pytest.mark.parametrize("shape", [(97, 131), (5, 7), (1, 40), (23, 37, 41), (3, 50, 2)])
+@pytest.mark.parametrize("radius", [0, 1, 1.5, 3, 6, 9.99, 25])
+def test_edt_within_exact(shape, radius):
+    rng = np.random.default_rng(hash((shape, radius)) % 2**32)
+    mask = rng.random(shape) < 0.97  # sparse zeros: long distances
+    mask[tuple(s // 2 for s in shape)] = False
+    ref = opost.edt_within(mask, radius)
+    got = K.edt_within(torch.from_numpy(mask).to(_dev()), radius).cpu().numpy().astype(bool)
+    assert np.array_equal(got, ref)
+    dense = rng.random(shape) < 0.5
+    assert np.array_equal(K.edt_within(torch.from_numpy(dense).to(_dev()), radius).cpu().numpy().astype(bool),
+                          opost.edt_within(dense, radius))
+
+
+@pytest.mark.parametrize("shape", [(6, 9), (4, 5, 6)])
+def test_edt_within_no_zero_element(shape):
+    """scipy measures distances to a virtual element at (-1, 0, ..., 0) when the input has no zero."""
+    mask = np.ones(shape, bool)
+    for radius in [1, 2.5, 4, 7, 100]:
+        got = K.edt_within(torch.from_numpy(mask).to(_dev()), radius).cpu().numpy().astype(bool)
+        assert np.array_equal(got, opost.edt_within(mask, radius)), radius
+
+
+@pytest.mark.parametrize("shape,blobs,radius", [((200, 260), 40, 14), ((40, 90, 70), 30, 10), ((31, 17), 0, 5),
+                                                ((12, 12), 3, 30)])
+@pytest.mark.parametrize("grow,shrink", [(3, 6), (1, 1), (5, 2), (0, 3), (4, 0)])
+def test_grow_shrink_exact(shape, blobs, radius, grow, shrink):
+    seg = _label_blobs(shape, blobs, radius, seed=len(shape) * 100 + blobs)
+    ref = opost.grow_shrink(seg.copy(), grow, shrink)
+    got = K.grow_shrink_(torch.from_numpy(seg.copy()).to(_dev()), grow, shrink).cpu().numpy()
+    assert np.array_equal(got, ref)
+
+
+# ---------------------------------------------------------------------------------------------------
+# "nucleus" post-processing (segment.py:52-101): per-instance Otsu + hole filling, exact
+def _nucleus_scene(shape, n_blobs, radius, dtype, seed):
+    rng = np.random.default_rng(seed)
+    seg = _label_blobs(shape, n_blobs, radius, seed)
+    grids = np.indices(shape)
+    raw = rng.random(shape) * 0.3
+    for k in range(1, n_blobs + 1):  # a bright shell with a dim, noisy core: thresholded masks get holes
+        m = seg == k
+        if not m.any():
+            continue
+        c = [g[m].mean() for g in grids]
+        d = np.sqrt(sum((g - ci) ** 2 for g, ci in zip(grids, c)))
+        r = max(d[m].max(), 1.0)
+        raw[m] += np.where(d[m] > 0.45 * r, 0.6, 0.0) + 0.2 * rng.random(int(m.sum()))
+    if n_blobs >= 3:  # one instance of constant intensity: skimage returns that value, the mask is empty
+        raw[seg == 2] = 0.5
+    if np.issubdtype(np.dtype(dtype), np.integer):
+        scale = 200 if dtype == np.uint8 else 40000
+        return seg, (raw / raw.max() * scale).astype(dtype)
+    return seg, raw.astype(dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.float32, np.float64])
+@pytest.mark.parametrize("shape,blobs,radius", [((150, 170), 25, 16), ((24, 60, 50), 14, 11), ((40, 40), 1, 30),
+                                                ((30, 30), 0, 5), ((1, 64, 64), 6, 9)])
+def test_nucleus_post_processing_exact(shape, blobs, radius, dtype):
+    from cellulus_b200.segment import nucleus
+
+    seg, raw = _nucleus_scene(shape, blobs, radius, dtype, seed=7 + len(shape) + blobs)
+    ref = opost.nucleus(seg.copy(), raw)
+    got = nucleus(seg.copy(), raw)
+    assert got.dtype == seg.dtype
+    assert np.array_equal(got, ref)
+    if blobs > 3 and min(shape) > 1:  # the scene does exercise hole filling (a 1-voxel-thick 3-D box has no interior)
+        thresholded = np.zeros_like(seg)
+        for k in np.unique(seg)[1:]:
+            m = seg == k
+            thresholded[m & (raw > ootsu.threshold_otsu(raw[m]))] = k
+        assert (ref != thresholded).sum() > 0
