@@ -87,6 +87,8 @@ PROTOTYPES = {
     "cb200_edt_workspace_bytes": (_i64, [_i64]),
     "cb200_edt_within": (_i, [_p, _i, _pi64, _d, _p, _p, _p]),
     "cb200_grow_shrink": (_i, [_p, _i, _pi64, _d, _d, _p, _p]),
+    "cb200_label_presence": (_i, [_p, _i, _i64, _i, _p, _p]),
+    "cb200_contingency": (_i, [_p, _p, _i, _i64, _p, _p, _i, _i, _p, _p]),
     "cb200_label_stats_workspace_bytes": (_i64, [_i]),
     "cb200_label_stats": (_i, [_p, _p, _i, _i, _pi64, _i, _p, _p, _p, _p, _p]),
     "cb200_label_histogram": (_i, [_p, _p, _i, _i64, _i, _p, _p, _p, _i, _p, _p]),

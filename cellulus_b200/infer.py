@@ -10,6 +10,7 @@ import torch
 
 from cellulus_b200.datasets.meta_data import DatasetMetaData
 from cellulus_b200.detect import detect
+from cellulus_b200.evaluate import evaluate
 from cellulus_b200.models import get_model
 from cellulus_b200.predict import predict
 from cellulus_b200.segment import segment
@@ -61,4 +62,4 @@ def infer(experiment_config):
     if inference_config.segmentation_dataset_config is not None and rank == 0:
         segment(inference_config)
     if inference_config.evaluation_dataset_config is not None and rank == 0:
-        print("evaluate (F1 / SEG against ground truth, cellulus/evaluate.py) is outside the hot path and not built")
+        evaluate(inference_config)

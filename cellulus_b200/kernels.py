@@ -681,3 +681,33 @@ def nucleus_fill(seg, raw, ids, thresholds, boxes, box_offset, total_box_voxels)
     check(rc, "cb200_nucleus_fill")
     launch_counter["calls"] += 1
     return out
+
+
+# --------------------------------------------------------------------------- evaluation counts
+_LABEL_DTYPES = (torch.uint16, torch.int32)
+
+
+def label_presence(labels: torch.Tensor, max_value: int) -> torch.Tensor:
+    """`cb200_label_presence`: uint8 (max_value + 1), 1 where the value occurs."""
+    _require_cuda(labels)
+    assert labels.is_contiguous()
+    present = torch.empty(max_value + 1, dtype=torch.uint8, device=labels.device)
+    rc = _lib().cb200_label_presence(_ptr(labels), _code(labels, _LABEL_DTYPES), labels.numel(), int(max_value),
+                                     _ptr(present), _stream(labels))
+    check(rc, "cb200_label_presence")
+    launch_counter["calls"] += 1
+    return present
+
+
+def contingency(pred: torch.Tensor, gt: torch.Tensor, rank_pred: torch.Tensor, rank_gt: torch.Tensor, rows: int,
+                cols: int) -> torch.Tensor:
+    """`cb200_contingency`: (rows, cols) int32 table of joint label counts."""
+    _require_cuda(pred, gt, rank_pred, rank_gt)
+    assert pred.dtype == gt.dtype and pred.shape == gt.shape and pred.is_contiguous() and gt.is_contiguous()
+    assert rank_pred.dtype == torch.int32 and rank_gt.dtype == torch.int32
+    table = torch.empty((rows, cols), dtype=torch.int32, device=pred.device)
+    rc = _lib().cb200_contingency(_ptr(pred), _ptr(gt), _code(pred, _LABEL_DTYPES), pred.numel(), _ptr(rank_pred),
+                                  _ptr(rank_gt), int(rows), int(cols), _ptr(table), _stream(pred))
+    check(rc, "cb200_contingency")
+    launch_counter["calls"] += 1
+    return table

@@ -385,6 +385,18 @@ CB200_API int cb200_nucleus_fill(const int32_t* seg, const void* raw, int raw_dt
                        const int64_t* box_offset, int64_t total_box_voxels, int32_t* out, void* workspace,
                        void* stream);
 
+/*
+ * Evaluation counts, evaluate.py:72-98 (compute_pairwise_IoU): one pass instead of four per id pair.
+ *   cb200_label_presence: present[v] = 1 for every value v in [0, max_value] that occurs in `labels`
+ *                         (CB200_U16 or CB200_I32; values outside the range are ignored)
+ *   cb200_contingency   : table[rank_pred[pred[i]] * cols + rank_gt[gt[i]]]++ over all pixels; the rank
+ *                         tables map a label value to its row / column (0 = background); `table` is zeroed
+ *                         by the call.  Intersections are the entries, areas the row / column sums.
+ */
+CB200_API int cb200_label_presence(const void* labels, int dtype, int64_t n, int max_value, uint8_t* present, void* stream);
+CB200_API int cb200_contingency(const void* pred, const void* gt, int dtype, int64_t n, const int32_t* rank_pred,
+                      const int32_t* rank_gt, int rows, int cols, unsigned int* table, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

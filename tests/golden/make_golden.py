@@ -20,6 +20,11 @@ symbols is executed by the functions we call:
         loaded by file path (the package __init__ pulls matplotlib)
   * scikit-learn 1.9.0 `_mean_shift_single_seed` for per-seed (mode, count, iters)
   * `Cluster2d` / `Cluster3d`                                  (utils/greedy_cluster.py), loaded by file path
+  * `segment(inference_config)`                                (segment.py:13-108) over an IN-MEMORY stand-in
+        for zarr (`_MemoryStore`): the "cell" branch runs unmodified on scipy's distance transform; the
+        "nucleus" branch runs with `skimage.filters.threshold_otsu` (not installed) replaced by the
+        restatement in oracle/otsu.py -- bounding boxes, hole filling and write order are the reference's
+  * `compute_pairwise_IoU`, `compute_F1`                       (evaluate.py:72-105)
 
 The fixtures cannot be regenerated on the GPU box (no /root/reference there);
 tests only read the committed .npz files.
@@ -271,6 +276,139 @@ def golden_greedy(gc):
     np.savez_compressed(os.path.join(HERE, "greedy.npz"), **out)
 
 
+class _MemoryArray:
+    """What the reference touches of a zarr array: shape, attrs, reads that COPY, slice writes."""
+
+    def __init__(self, data):
+        self.data = data
+        self.attrs = {}
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+    def __getitem__(self, key):
+        return np.array(self.data[key])
+
+    def __setitem__(self, key, value):
+        self.data[key] = value
+
+
+class _MemoryStore:
+    containers = {}
+
+    def __init__(self, path):
+        self.arrays = _MemoryStore.containers.setdefault(str(path), {})
+
+    def __getitem__(self, name):
+        return self.arrays[name]
+
+    def create_dataset(self, name, shape, dtype, **kwargs):
+        self.arrays[name] = _MemoryArray(np.zeros(shape, dtype))
+        return self.arrays[name]
+
+
+def _label_blobs(shape, n_blobs, radius, seed):
+    rng = np.random.default_rng(seed)
+    seg = np.zeros(shape, np.uint16)
+    grids = np.indices(shape)
+    for k in range(n_blobs):
+        c = [rng.uniform(0, s) for s in shape]
+        r = rng.uniform(0.5 * radius, radius)
+        seg[sum((g - ci) ** 2 for g, ci in zip(grids, c)) < r * r] = k + 1
+    return seg
+
+
+def _shell_intensities(seg, dtype, seed):
+    """Bright shell, dim noisy core under every instance: the thresholded masks have holes."""
+    rng = np.random.default_rng(seed)
+    grids = np.indices(seg.shape)
+    raw = rng.random(seg.shape) * 0.3
+    for k in np.unique(seg)[1:]:
+        m = seg == k
+        c = [g[m].mean() for g in grids]
+        d = np.sqrt(sum((g - ci) ** 2 for g, ci in zip(grids, c)))
+        raw[m] += np.where(d[m] > 0.45 * max(d[m].max(), 1.0), 0.6, 0.0) + 0.2 * rng.random(int(m.sum()))
+    if np.issubdtype(np.dtype(dtype), np.integer):
+        return (raw / raw.max() * (200 if dtype == np.uint8 else 40000)).astype(dtype)
+    return raw.astype(dtype)
+
+
+def golden_post_process():
+    """The reference's `segment()` itself, fed from memory."""
+    import zarr  # the stub
+
+    zarr.open = lambda path, mode=None: _MemoryStore(path)
+    from oracle import otsu as ootsu
+    from oracle import size_filter as osize
+
+    _stub("skimage")
+    _stub("skimage.filters", threshold_otsu=ootsu.threshold_otsu)
+    _stub("skimage.measure", label=osize.label_equal_regions)
+    sys.modules["skimage"].measure = sys.modules["skimage.measure"]
+    from cellulus.configs.inference_config import InferenceConfig
+    from cellulus.segment import segment
+
+    out = {}
+    cases = [("cell2d", (90, 110), 14, 12, "cell", np.uint8, (3, 6)), ("cell2d_b", (60, 64), 9, 9, "cell", np.uint8, (5, 2)),
+             ("cell3d", (18, 44, 40), 8, 9, "cell", np.uint8, (3, 6)),
+             ("nuc2d_u8", (90, 110), 14, 14, "nucleus", np.uint8, (3, 6)),
+             ("nuc2d_u16", (80, 70), 10, 13, "nucleus", np.uint16, (3, 6)),
+             ("nuc2d_f32", (80, 70), 10, 13, "nucleus", np.float32, (3, 6)),
+             ("nuc3d_f32", (16, 40, 36), 6, 9, "nucleus", np.float32, (3, 6))]
+    for name, shape, blobs, radius, mode, raw_dtype, (grow, shrink) in cases:
+        nd = len(shape)
+        axes = ["s", "c"] + ["z", "y", "x"][-nd:]
+        seg = _label_blobs(shape, blobs, radius, seed=len(name) * 7 + blobs)
+        raw = _shell_intensities(seg, raw_dtype, seed=blobs)
+        store = _MemoryStore(name + ".zarr")
+        store.arrays["raw"] = _MemoryArray(raw[None, None])
+        store.arrays["raw"].attrs["axis_names"] = axes
+        store.arrays["detection"] = _MemoryArray(seg[None, None].copy())
+        cfg = InferenceConfig(
+            dataset_config={"container_path": name + ".zarr", "dataset_name": "raw"},
+            segmentation_dataset_config={"container_path": name + ".zarr", "dataset_name": "segmentation",
+                                         "secondary_dataset_name": "detection"},
+            post_processing=mode, grow_distance=grow, shrink_distance=shrink, min_size=0, num_bandwidths=1)
+        segment(cfg)
+        result = store.arrays["segmentation"].data[0, 0]
+        out[f"{name}_detection"] = seg
+        out[f"{name}_raw"] = raw
+        out[f"{name}_cfg"] = np.array([grow, shrink], dtype=np.int64)
+        out[f"{name}_segmentation"] = result.copy()
+        print("segment", name, mode, "instances in", int(seg.max()), "labelled px in/out", int((seg > 0).sum()),
+              int((result > 0).sum()))
+    np.savez_compressed(os.path.join(HERE, "post_process.npz"), **out)
+
+
+def golden_evaluate():
+    """`compute_pairwise_IoU` + `compute_F1` of the reference (evaluate.py:72-105)."""
+    from cellulus.evaluate import compute_F1, compute_pairwise_IoU
+
+    out = {}
+    for name, shape, blobs, radius in [("2d", (96, 120), 12, 13), ("3d", (14, 40, 44), 7, 9), ("empty_gt", (20, 20), 0, 5)]:
+        gt = _label_blobs(shape, blobs, radius, seed=31 + blobs)
+        rng = np.random.default_rng(5 + blobs)
+        pred = np.zeros_like(gt)
+        for k in np.unique(gt)[1:]:  # shifted / partly merged / dropped copies of the ground truth
+            if rng.random() < 0.15:
+                continue
+            shift = tuple(int(v) for v in rng.integers(-3, 4, size=gt.ndim))
+            m = np.roll(gt == k, shift, axis=tuple(range(gt.ndim)))
+            pred[m] = k + 100 if rng.random() < 0.8 else 100
+        out[f"{name}_groundtruth"] = gt
+        out[f"{name}_prediction"] = pred
+        returned = compute_pairwise_IoU(pred, gt)
+        out[f"{name}_none"] = np.array(returned is None)
+        if returned is not None:
+            IoU, SEG, n = returned
+            F1, TP, FP, FN = compute_F1(IoU)
+            out[f"{name}_IoU"] = IoU
+            out[f"{name}_scalars"] = np.array([SEG, n, F1, TP, FP, FN], dtype=np.float64)
+            print("evaluate", name, "IoU table", IoU.shape, "SEG", SEG / n, "F1", F1, TP, FP, FN)
+    np.savez_compressed(os.path.join(HERE, "evaluate.npz"), **out)
+
+
 def main():
     install_stubs()
     from cellulus.criterions import get_loss
@@ -283,6 +421,8 @@ def main():
     golden_tta(UNetModel)
     golden_mean_shift(ms)
     golden_greedy(load_by_path("ref_greedy_cluster", os.path.join(REF, "cellulus/utils/greedy_cluster.py")))
+    golden_post_process()
+    golden_evaluate()
 
 
 if __name__ == "__main__":

@@ -14,6 +14,7 @@ pytestmark = pytest.mark.gpu
 
 from cellulus_b200 import kernels as K  # noqa: E402
 from cellulus_b200 import synthetic  # noqa: E402
+from oracle import evaluate as oeval  # noqa: E402
 from oracle import mean_shift as oms  # noqa: E402
 from oracle import oce_loss as oloss  # noqa: E402
 from oracle import otsu as ootsu  # noqa: E402
@@ -692,3 +693,45 @@ def test_nucleus_post_processing_exact(shape, blobs, radius, dtype):
             m = seg == k
             thresholded[m & (raw > ootsu.threshold_otsu(raw[m]))] = k
         assert (ref != thresholded).sum() > 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# golden fixtures written by the reference's own segment() / compute_pairwise_IoU (tests/golden/make_golden.py)
+@pytest.mark.parametrize("case", ["cell2d", "cell2d_b", "cell3d", "nuc2d_u8", "nuc2d_u16", "nuc2d_f32", "nuc3d_f32"])
+def test_post_process_golden(golden, case):
+    from cellulus_b200.segment import grow_shrink, nucleus
+
+    g = golden("post_process")
+    detection = g[f"{case}_detection"]
+    if case.startswith("cell"):
+        grow, shrink = (int(v) for v in g[f"{case}_cfg"])
+        out = grow_shrink(detection.copy(), grow, shrink)
+    else:
+        out = nucleus(detection.copy(), g[f"{case}_raw"])
+    assert out.dtype == detection.dtype
+    assert np.array_equal(out, g[f"{case}_segmentation"])
+
+
+@pytest.mark.parametrize("case", ["2d", "3d"])
+def test_evaluate_golden(golden, case):
+    from cellulus_b200.evaluate import compute_F1, compute_pairwise_IoU
+
+    g = golden("evaluate")
+    IoU, SEG, n = compute_pairwise_IoU(g[f"{case}_prediction"], g[f"{case}_groundtruth"])
+    assert np.array_equal(IoU, g[f"{case}_IoU"])  # bit-identical tables
+    F1, TP, FP, FN = compute_F1(IoU)
+    assert np.array_equal(np.array([SEG, n, F1, TP, FP, FN], dtype=np.float64), g[f"{case}_scalars"])
+    assert compute_pairwise_IoU(g["empty_gt_prediction"], g["empty_gt_groundtruth"]) is None
+
+
+def test_evaluate_against_oracle_many_ids():
+    from cellulus_b200.evaluate import compute_pairwise_IoU
+
+    rng = np.random.default_rng(11)
+    gt = _label_blobs((220, 260), 60, 14, seed=3).astype(np.uint16)
+    pred = np.roll(gt, (2, -3), axis=(0, 1)).copy()
+    pred[pred > 0] += 1000  # ids are arbitrary 16-bit values
+    pred[rng.random(pred.shape) < 0.02] = 0
+    IoU, SEG, n = compute_pairwise_IoU(pred, gt)
+    rIoU, rSEG, rn = oeval.compute_pairwise_IoU(pred, gt)
+    assert np.array_equal(IoU, rIoU) and SEG == rSEG and n == rn

@@ -6,9 +6,11 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import evaluate as oeval
 from oracle import mean_shift as oms
 from oracle import oce_loss as oloss
 from oracle import otsu as ootsu
+from oracle import post_process as opost
 from oracle import sampler as osampler
 from oracle import size_filter as osize
 from oracle import tta as otta
@@ -233,3 +235,43 @@ def test_greedy_port_matches_reference(golden, case):
     labels, n_obj, tried = ogreedy.greedy_cluster(emb, emb[D] < 0.5, bw, int(min_size))
     assert labels.dtype == np.int16 and np.array_equal(labels, g[f"{case}_labels"])
     assert n_obj == labels.max() and tried >= n_obj
+
+
+POST_CASES = ["cell2d", "cell2d_b", "cell3d", "nuc2d_u8", "nuc2d_u16", "nuc2d_f32", "nuc3d_f32"]
+
+
+@pytest.mark.parametrize("case", POST_CASES)
+def test_post_process_matches_reference(golden, case):
+    """oracle/post_process.py against what the reference's own `segment()` wrote (segment.py:41-101)."""
+    g = golden("post_process")
+    detection = g[f"{case}_detection"]
+    if case.startswith("cell"):
+        grow, shrink = (int(v) for v in g[f"{case}_cfg"])
+        out = opost.grow_shrink(detection.copy(), grow, shrink)
+    else:
+        out = opost.nucleus(detection.copy(), g[f"{case}_raw"])
+    assert np.array_equal(out, g[f"{case}_segmentation"])
+
+
+def test_otsu_integer_image_uses_one_bin_per_value():
+    rng = np.random.default_rng(2)
+    img = np.concatenate([rng.integers(10, 40, 500), rng.integers(150, 200, 300)]).astype(np.uint8)
+    t = ootsu.threshold_otsu(img)
+    assert isinstance(t, (int, np.integer)) and 39 <= t < 150  # an integer grey level between the two modes
+    assert ootsu.threshold_otsu(np.full(7, 9, np.uint16)) == 9
+
+
+@pytest.mark.parametrize("case", ["2d", "3d"])
+def test_evaluate_matches_reference(golden, case):
+    g = golden("evaluate")
+    returned = oeval.compute_pairwise_IoU(g[f"{case}_prediction"], g[f"{case}_groundtruth"])
+    IoU, SEG, n = returned
+    assert np.array_equal(IoU, g[f"{case}_IoU"])
+    F1, TP, FP, FN = oeval.compute_F1(IoU)
+    assert np.array_equal(np.array([SEG, n, F1, TP, FP, FN], dtype=np.float64), g[f"{case}_scalars"])
+
+
+def test_evaluate_without_ground_truth(golden):
+    g = golden("evaluate")
+    assert bool(g["empty_gt_none"])
+    assert oeval.compute_pairwise_IoU(g["empty_gt_prediction"], g["empty_gt_groundtruth"]) is None
