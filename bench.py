@@ -251,6 +251,81 @@ def bench_tta(dev, windows):
     return out
 
 
+def _label_scene(shape, n_blobs, radius, seed):
+    """Label image of filled discs + a raw image with a bright shell / dim core per object (uint16)."""
+    rng = np.random.default_rng(seed)
+    seg = np.zeros(shape, np.int32)
+    raw = rng.random(shape) * 0.3
+    yy, xx = np.mgrid[: shape[0], : shape[1]]
+    for k in range(n_blobs):
+        cy, cx, r = rng.uniform(0, shape[0]), rng.uniform(0, shape[1]), rng.uniform(0.6 * radius, radius)
+        y0, y1, x0, x1 = int(max(cy - r, 0)), int(min(cy + r + 1, shape[0])), int(max(cx - r, 0)), int(min(cx + r + 1, shape[1]))
+        d = np.sqrt((yy[y0:y1, x0:x1] - cy) ** 2 + (xx[y0:y1, x0:x1] - cx) ** 2)
+        m = d < r
+        seg[y0:y1, x0:x1][m] = k + 1
+        raw[y0:y1, x0:x1][m] = np.where(d[m] > 0.45 * r, 0.9, 0.3) + 0.1 * rng.random(int(m.sum()))
+    return seg, (raw / raw.max() * 40000).astype(np.uint16)
+
+
+def bench_post(dev, with_cpu):
+    """The rows after the path: segment() post-processing and evaluate() counts on a 2048^2 image
+    with ~1200 objects; CPU legs (oracle = scipy / the reference's loops) on bounded samples."""
+    from cellulus_b200 import kernels as K
+    from cellulus_b200.evaluate import compute_pairwise_IoU
+    from cellulus_b200.segment import nucleus
+
+    shape, blobs = (2048, 2048), 1200
+    seg_np, raw_np = _label_scene(shape, blobs, 26, seed=3)
+    seg = torch.from_numpy(seg_np).to(dev)
+
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize(dev)
+        return (time.perf_counter() - t0) / reps
+
+    n = float(np.prod(shape))
+    t_gs = timed(lambda: K.grow_shrink_(seg.clone(), 3, 6))
+    t_sf = timed(lambda: K.size_filter_(seg.clone(), 25))
+    t_nuc = timed(lambda: nucleus(seg_np, raw_np), reps=3)  # numpy in / numpy out
+    gt = np.roll(seg_np, (3, -2), axis=(0, 1)).astype(np.uint16)
+    t_ev = timed(lambda: compute_pairwise_IoU(seg_np.astype(np.uint16), gt), reps=3)
+    out = {
+        "workload": f"{shape[0]}x{shape[1]} label image, {int(seg_np.max())} objects, uint16 raw",
+        "grow_shrink": {"ms": t_gs * 1e3, "Mpx/s": n / t_gs / 1e6, "note": "device tensor in place (segment.py:46-50)"},
+        "size_filter": {"ms": t_sf * 1e3, "Mpx/s": n / t_sf / 1e6, "note": "device tensor (utils/misc.py:11-25)"},
+        "nucleus": {"ms": t_nuc * 1e3, "Mpx/s": n / t_nuc / 1e6, "note": "numpy in/out incl. the host<->device copies (per-instance Otsu runs on the device)"},
+        "evaluate_tables": {"ms": t_ev * 1e3, "Mpx/s": n / t_ev / 1e6, "note": "numpy in/out, IoU table of all id pairs"},
+    }
+    if with_cpu:
+        from oracle import evaluate as oeval
+        from oracle import post_process as opost
+
+        small, small_raw = seg_np[:1024, :1024].copy(), raw_np[:1024, :1024]
+        t0 = time.perf_counter()
+        opost.grow_shrink(small.copy(), 3, 6)
+        t_c = time.perf_counter() - t0
+        out["grow_shrink"]["cpu_baseline"] = {"Mpx/s": small.size / t_c / 1e6, "kind": "port",
+                                              "sample": "1024x1024 corner, scipy distance_transform_edt x2, 1 core"}
+        tiny, tiny_raw = seg_np[:512, :512].copy(), raw_np[:512, :512]
+        t0 = time.perf_counter()
+        opost.nucleus(tiny, tiny_raw)
+        t_c = time.perf_counter() - t0
+        out["nucleus"]["cpu_baseline"] = {"Mpx/s": tiny.size / t_c / 1e6, "kind": "port",
+                                          "sample": f"512x512 corner, {len(np.unique(tiny)) - 1} objects, 1 core"}
+        tiny_gt = gt[:384, :384]
+        t0 = time.perf_counter()
+        oeval.compute_pairwise_IoU(seg_np[:384, :384].astype(np.uint16), tiny_gt)
+        t_c = time.perf_counter() - t0
+        out["evaluate_tables"]["cpu_baseline"] = {"Mpx/s": tiny_gt.size / t_c / 1e6, "kind": "port",
+                                                  "sample": f"384x384 corner, {len(np.unique(tiny_gt)) - 1} ground-truth "
+                                                            "objects (cost grows with the product of the id counts)"}
+    return out
+
+
 def cpu_detect_baseline():
     """Oracle port of `mean_shift_segmentation` (scikit-learn MeanShift, hill climb on ONE core as shipped)
     on a bounded sub-volume of the same scene family."""
@@ -412,6 +487,7 @@ def run_b200(args):
         if not args.skip_detect:
             detect = bench_detect(dev, windows)
             detect["tta_aggregate"] = bench_tta(dev, windows)
+            detect["post_processing"] = bench_post(dev, with_cpu=(world == 1 and not args.skip_cpu))
         if world == 1 and not args.skip_cpu:
             t_cpu = cpu_loss_step_time(B, 3, 1)
             cpu_base = {"value": N_PX / t_cpu, "unit": "px/s", "cores": torch.get_num_threads(), "kind": "port",

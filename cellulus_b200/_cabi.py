@@ -92,6 +92,8 @@ PROTOTYPES = {
     "cb200_label_stats_workspace_bytes": (_i64, [_i]),
     "cb200_label_stats": (_i, [_p, _p, _i, _i, _pi64, _i, _p, _p, _p, _p, _p]),
     "cb200_label_histogram": (_i, [_p, _p, _i, _i64, _i, _p, _p, _p, _i, _p, _p]),
+    "cb200_label_otsu_workspace_bytes": (_i64, [_i64]),
+    "cb200_label_otsu": (_i, [_p, _p, _p, _p, _p, _i, _i, _i64, _p, _p, _p]),
     "cb200_nucleus_fill_workspace_bytes": (_i64, [_i64, _i]),
     "cb200_nucleus_fill": (_i, [_p, _p, _i, _i, _pi64, _i, _p, _p, _p, _p, _i64, _p, _p, _p]),
 }

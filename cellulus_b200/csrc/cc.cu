@@ -17,11 +17,17 @@ __global__ void __launch_bounds__(256) cc_init_kernel(const int32_t* __restrict_
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) parent[i] = seg[i] != 0 ? (int)i : -1;
 }
 
-// Each pixel links to the "earlier" half of its 3^D - 1 neighbours.
+// Each pixel links to the "earlier" half of its 3^D - 1 neighbours -- but only where the link is not already
+// implied by a link another pixel makes: inside a region nearly every pixel has an equal left neighbour whose
+// own upward link covers it, so unions (atomics) happen along run boundaries only.
+//   in-plane:  left always; up unless (left and up-left are equal too: the left pixel links upward);
+//              up-left / up-right only when up differs (otherwise they hang on `up` through their own row)
+//   3-D:       the voxel in front (z-1) like `up`; the other eight of the z-1 plane only when it differs
 template <int D>
 __global__ void __launch_bounds__(256)
 cc_merge_kernel(const int32_t* __restrict__ seg, int64_t n, int ex, int ey, int ez, int* parent) {
   const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  const int64_t plane = (int64_t)ex * ey;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
     const int32_t v = seg[i];
     if (v == 0) continue;
@@ -29,14 +35,32 @@ cc_merge_kernel(const int32_t* __restrict__ seg, int64_t n, int ex, int ey, int 
     const int64_t r = i / ex;
     const int y = (int)(D == 2 ? r : r % ey);
     const int z = (int)(D == 2 ? 0 : r / ey);
-    for (int dz = (D == 3 ? -1 : 0); dz <= 0; ++dz)
-      for (int dy = -1; dy <= (dz < 0 ? 1 : 0); ++dy)
-        for (int dx = -1; dx <= ((dz < 0 || dy < 0) ? 1 : -1); ++dx) {
-          const int xx = x + dx, yy = y + dy, zz = z + dz;
-          if (xx < 0 || xx >= ex || yy < 0 || yy >= ey || zz < 0 || zz >= ez) continue;
-          const int64_t j = ((int64_t)zz * ey + yy) * ex + xx;
-          if (seg[j] == v) uf_union(parent, (int)i, (int)j);
-        }
+    const bool has_l = x > 0, has_r = x < ex - 1, has_u = y > 0;
+    const bool L = has_l && seg[i - 1] == v;
+    const bool U = has_u && seg[i - ex] == v;
+    if (L) uf_union(parent, (int)i, (int)(i - 1));
+    if (U) {
+      if (!(L && seg[i - ex - 1] == v)) uf_union(parent, (int)i, (int)(i - ex));
+    } else if (has_u) {
+      if (has_l && !L && seg[i - ex - 1] == v) uf_union(parent, (int)i, (int)(i - ex - 1));
+      if (has_r && seg[i - ex + 1] == v) uf_union(parent, (int)i, (int)(i - ex + 1));
+    }
+    if constexpr (D == 3) {
+      if (z == 0) continue;
+      const int64_t f = i - plane;
+      if (seg[f] == v) {
+        if (!(L && seg[f - 1] == v)) uf_union(parent, (int)i, (int)f);
+      } else {
+        for (int dy = -1; dy <= 1; ++dy)
+          for (int dx = -1; dx <= 1; ++dx) {
+            if (dx == 0 && dy == 0) continue;
+            const int xx = x + dx, yy = y + dy;
+            if (xx < 0 || xx >= ex || yy < 0 || yy >= ey) continue;
+            const int64_t j = f + (int64_t)dy * ex + dx;
+            if (seg[j] == v) uf_union(parent, (int)i, (int)j);
+          }
+      }
+    }
   }
 }
 

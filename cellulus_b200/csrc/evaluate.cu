@@ -9,34 +9,82 @@
 
 namespace cb200 {
 
+// Both kernels read 16 bytes (8 uint16 / 4 int32 labels) per thread and work on RUNS of equal labels inside
+// those 16 bytes -- label images are piecewise constant, so nearly every thread sees a single run.
 template <typename T>
-__global__ void __launch_bounds__(256)
-label_presence_kernel(const T* __restrict__ labels, int64_t n, int max_value, uint8_t* __restrict__ present) {
-  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
-  int last = -1;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
-    const int v = (int)labels[i];
-    if (v == last || v < 0 || v > max_value) continue;
-    last = v;
-    if (!present[v]) present[v] = 1;
-  }
+struct LabelVec {
+  static constexpr int N = 16 / sizeof(T);
+  T v[N];
+};
+template <typename T>
+__device__ __forceinline__ LabelVec<T> load_labels(const T* p, int64_t vec_index) {
+  LabelVec<T> r;
+  *reinterpret_cast<uint4*>(r.v) = __ldg(reinterpret_cast<const uint4*>(p) + vec_index);
+  return r;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-contingency_kernel(const T* __restrict__ pred, const T* __restrict__ gt, int64_t n, const int32_t* __restrict__ rank_p,
-                   const int32_t* __restrict__ rank_g, int cols, unsigned int* __restrict__ table) {
+label_presence_kernel(const T* __restrict__ labels, int64_t n, int64_t nvec, int max_value, uint8_t* __restrict__ present) {
+  constexpr int N = LabelVec<T>::N;
   const int64_t gs = (int64_t)gridDim.x * blockDim.x;
-  const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  // whole warps iterate together (the tail lanes carry an impossible key)
-  for (int64_t base = first - (threadIdx.x & 31); base < n; base += gs) {
-    const int64_t i = base + (threadIdx.x & 31);
-    unsigned key = 0xffffffffu;
-    if (i < n) key = (unsigned)rank_p[(int)pred[i]] * (unsigned)cols + (unsigned)rank_g[(int)gt[i]];
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
-    if (key != 0xffffffffu && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1))
-      atomicAdd(table + key, (unsigned)__popc(peers));
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int last = -1;
+  auto mark = [&](int v) {
+    if (v == last || v < 0 || v > max_value) return;
+    last = v;
+    if (!present[v]) present[v] = 1;
+  };
+  for (int64_t i = tid; i < nvec; i += gs) {
+    const LabelVec<T> x = load_labels<T>(labels, i);
+#pragma unroll
+    for (int k = 0; k < N; ++k) mark((int)x.v[k]);
   }
+  for (int64_t i = nvec * N + tid; i < n; i += gs) mark((int)labels[i]);  // tail
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+contingency_kernel(const T* __restrict__ pred, const T* __restrict__ gt, int64_t n, int64_t nvec,
+                   const int32_t* __restrict__ rank_p, const int32_t* __restrict__ rank_g, int cols,
+                   unsigned int* __restrict__ table) {
+  constexpr int N = LabelVec<T>::N;
+  constexpr unsigned NONE = 0xffffffffu;
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  const unsigned lane = threadIdx.x & 31;
+  const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // whole warps iterate together: the first run of every lane is added with one warp-aggregated atomic
+  for (int64_t base = first - lane; base < nvec; base += gs) {
+    const int64_t i = base + lane;
+    unsigned key0 = NONE;
+    int count0 = 0;
+    if (i < nvec) {
+      const LabelVec<T> p = load_labels<T>(pred, i), g = load_labels<T>(gt, i);
+      unsigned key = (unsigned)rank_p[(int)p.v[0]] * (unsigned)cols + (unsigned)rank_g[(int)g.v[0]];
+      int count = 1;
+      bool in_first = true;
+      key0 = key;
+#pragma unroll
+      for (int k = 1; k < N; ++k) {
+        if (p.v[k] == p.v[k - 1] && g.v[k] == g.v[k - 1]) {
+          ++count;
+          continue;
+        }
+        if (in_first) count0 = count;
+        else atomicAdd(table + key, (unsigned)count);
+        in_first = false;
+        key = (unsigned)rank_p[(int)p.v[k]] * (unsigned)cols + (unsigned)rank_g[(int)g.v[k]];
+        count = 1;
+      }
+      if (in_first) count0 = count;
+      else atomicAdd(table + key, (unsigned)count);
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, key0);
+    const int total = __reduce_add_sync(peers, count0);
+    if (key0 != NONE && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(table + key0, (unsigned)total);
+  }
+  for (int64_t i = nvec * N + first; i < n; i += gs)  // tail
+    atomicAdd(table + (unsigned)rank_p[(int)pred[i]] * (unsigned)cols + (unsigned)rank_g[(int)gt[i]], 1u);
 }
 
 }  // namespace cb200
@@ -50,10 +98,16 @@ int cb200_label_presence(const void* labels, int dtype, int64_t n, int max_value
   cudaStream_t st = (cudaStream_t)stream;
   CB200_CUDA_TRY(cudaMemsetAsync(present, 0, (size_t)max_value + 1, st));
   if (n == 0) return CB200_OK;
-  const int blocks = grid_for(n, 256, 8, 8);
-  if (dtype == CB200_U16) label_presence_kernel<uint16_t><<<blocks, 256, 0, st>>>((const uint16_t*)labels, n, max_value, present);
-  else if (dtype == CB200_I32) label_presence_kernel<int32_t><<<blocks, 256, 0, st>>>((const int32_t*)labels, n, max_value, present);
-  else return CB200_EUNSUPPORTED;
+  const bool aligned = reinterpret_cast<uintptr_t>(labels) % 16 == 0;
+  if (dtype == CB200_U16) {
+    const int64_t nvec = aligned ? n / 8 : 0;
+    label_presence_kernel<uint16_t><<<grid_for(nvec + 256, 256, 2, 8), 256, 0, st>>>((const uint16_t*)labels, n, nvec, max_value, present);
+  } else if (dtype == CB200_I32) {
+    const int64_t nvec = aligned ? n / 4 : 0;
+    label_presence_kernel<int32_t><<<grid_for(nvec + 256, 256, 2, 8), 256, 0, st>>>((const int32_t*)labels, n, nvec, max_value, present);
+  } else {
+    return CB200_EUNSUPPORTED;
+  }
   CB200_LAUNCH_CHECK();
   return CB200_OK;
 }
@@ -65,12 +119,18 @@ int cb200_contingency(const void* pred, const void* gt, int dtype, int64_t n, co
   cudaStream_t st = (cudaStream_t)stream;
   CB200_CUDA_TRY(cudaMemsetAsync(table, 0, sizeof(unsigned int) * (size_t)rows * cols, st));
   if (n == 0) return CB200_OK;
-  const int blocks = grid_for(n, 256, 8, 8);
-  if (dtype == CB200_U16)
-    contingency_kernel<uint16_t><<<blocks, 256, 0, st>>>((const uint16_t*)pred, (const uint16_t*)gt, n, rank_pred, rank_gt, cols, table);
-  else if (dtype == CB200_I32)
-    contingency_kernel<int32_t><<<blocks, 256, 0, st>>>((const int32_t*)pred, (const int32_t*)gt, n, rank_pred, rank_gt, cols, table);
-  else return CB200_EUNSUPPORTED;
+  const bool aligned = reinterpret_cast<uintptr_t>(pred) % 16 == 0 && reinterpret_cast<uintptr_t>(gt) % 16 == 0;
+  if (dtype == CB200_U16) {
+    const int64_t nvec = aligned ? n / 8 : 0;
+    contingency_kernel<uint16_t><<<grid_for(nvec + 256, 256, 2, 8), 256, 0, st>>>(
+        (const uint16_t*)pred, (const uint16_t*)gt, n, nvec, rank_pred, rank_gt, cols, table);
+  } else if (dtype == CB200_I32) {
+    const int64_t nvec = aligned ? n / 4 : 0;
+    contingency_kernel<int32_t><<<grid_for(nvec + 256, 256, 2, 8), 256, 0, st>>>(
+        (const int32_t*)pred, (const int32_t*)gt, n, nvec, rank_pred, rank_gt, cols, table);
+  } else {
+    return CB200_EUNSUPPORTED;
+  }
   CB200_LAUNCH_CHECK();
   return CB200_OK;
 }

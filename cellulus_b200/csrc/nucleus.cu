@@ -121,6 +121,78 @@ label_histogram_kernel(const int32_t* __restrict__ seg, const T* __restrict__ ra
   }
 }
 
+// ------------------------------------------------------------------ Otsu tail per label
+// scikit-image's threshold_otsu after the histogram, one thread per label, in numpy's own arithmetic:
+//   counts float32; weight1 = cumsum(counts), weight2 = cumsum(counts[::-1])[::-1]            (float32, sequential)
+//   mean1 = cumsum(counts * centres) / weight1, mean2 likewise from the far end                (A)
+//   variance12 = weight1[:-1] * weight2[1:] * (mean1[:-1] - mean2[1:]) ** 2 ; first argmax
+// A = float for float32 images (float32 * float32), double for integer / float64 images (float32 * int64 or
+// float64 promotes to float64).  np.cumsum accumulates sequentially, so a sequential loop reproduces it bit
+// for bit.  scratch_w / scratch_c hold the reversed cumulative sums (one entry per bin).
+template <typename A>
+__device__ __forceinline__ A otsu_mul(float c, double centre);
+template <>
+__device__ __forceinline__ float otsu_mul<float>(float c, double centre) { return __fmul_rn(c, (float)centre); }
+template <>
+__device__ __forceinline__ double otsu_mul<double>(float c, double centre) { return __dmul_rn((double)c, centre); }
+__device__ __forceinline__ float otsu_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double otsu_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float otsu_div(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double otsu_div(double a, float b) { return __ddiv_rn(a, (double)b); }
+__device__ __forceinline__ float otsu_var(float w1, float w2, float m1, float m2) {
+  const float d = __fsub_rn(m1, m2);
+  return __fmul_rn(__fmul_rn(w1, w2), __fmul_rn(d, d));
+}
+__device__ __forceinline__ double otsu_var(float w1, float w2, double m1, double m2) {
+  const double d = __dsub_rn(m1, m2);
+  return __dmul_rn((double)__fmul_rn(w1, w2), __dmul_rn(d, d));
+}
+
+template <typename A>
+__global__ void __launch_bounds__(64)
+label_otsu_kernel(const unsigned int* __restrict__ hist, const int64_t* __restrict__ offset,
+                  const int64_t* __restrict__ nbins, const double* __restrict__ centre0,
+                  const double* __restrict__ centres, int n_labels, float* __restrict__ scratch_w,
+                  A* __restrict__ scratch_c, double* __restrict__ threshold) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_labels) return;
+  const int64_t off = offset[l], nb = nbins[l];
+  if (nb <= 0) return;
+  // integer images: centre i = centre0[l] + i; float images: centres[off + i]
+  auto centre = [&](int64_t i) { return centres ? centres[off + i] : centre0[l] + (double)i; };
+  if (nb == 1) {
+    threshold[l] = centre(0);
+    return;
+  }
+  float w = 0.f;
+  A cs = (A)0;
+  for (int64_t i = nb - 1; i >= 0; --i) {  // reversed cumulative sums
+    const float c = (float)hist[off + i];
+    w = otsu_add(w, c);
+    cs = otsu_add(cs, otsu_mul<A>(c, centre(i)));
+    scratch_w[off + i] = w;
+    scratch_c[off + i] = cs;
+  }
+  w = 0.f;
+  cs = (A)0;
+  A best = (A)0;
+  int64_t best_i = 0;
+  for (int64_t i = 0; i + 1 < nb; ++i) {
+    const float c = (float)hist[off + i];
+    w = otsu_add(w, c);
+    cs = otsu_add(cs, otsu_mul<A>(c, centre(i)));
+    const A m1 = otsu_div(cs, w);
+    const float w2 = scratch_w[off + i + 1];
+    const A m2 = otsu_div(scratch_c[off + i + 1], w2);
+    const A v = otsu_var(w, w2, m1, m2);
+    if (i == 0 || v > best) {  // np.argmax: first maximum (NaN cannot occur: both end bins are occupied)
+      best = v;
+      best_i = i;
+    }
+  }
+  threshold[l] = centre(best_i);
+}
+
 // ------------------------------------------------------------------ hole filling
 struct Boxes {
   int n;                      // instances
@@ -181,12 +253,17 @@ fill_merge_kernel(Boxes b, int64_t total, int ex, int ey, int num_dims, int* par
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gs) {
     if (parent[j] < 0) continue;
     const BoxVoxel v = locate(b, j, ex, ey);
-    const bool border = v.x == 0 || v.x == v.bx - 1 || v.y == 0 || v.y == v.by - 1 ||
-                        (num_dims == 3 && (v.z == 0 || v.z == v.bz - 1));
-    if (border) uf_union(parent, (int)j, (int)(total + v.k));
-    if (v.x > 0 && parent[j - 1] >= 0) uf_union(parent, (int)j, (int)(j - 1));
-    if (v.y > 0 && parent[j - v.bx] >= 0) uf_union(parent, (int)j, (int)(j - v.bx));
-    if (v.z > 0 && parent[j - (int64_t)v.bx * v.by] >= 0) uf_union(parent, (int)j, (int)(j - (int64_t)v.bx * v.by));
+    // links already implied by the left neighbour's own links are skipped (see cc_merge_kernel)
+    const bool left = v.x > 0 && parent[j - 1] >= 0;
+    const bool edge_yz = v.y == 0 || v.y == v.by - 1 || (num_dims == 3 && (v.z == 0 || v.z == v.bz - 1));
+    const bool border = v.x == 0 || v.x == v.bx - 1 || edge_yz;
+    if (border && !(left && edge_yz)) uf_union(parent, (int)j, (int)(total + v.k));
+    if (left) uf_union(parent, (int)j, (int)(j - 1));
+    if (v.y > 0 && parent[j - v.bx] >= 0 && !(left && parent[j - v.bx - 1] >= 0))
+      uf_union(parent, (int)j, (int)(j - v.bx));
+    const int64_t slab = (int64_t)v.bx * v.by;
+    if (v.z > 0 && parent[j - slab] >= 0 && !(left && parent[j - slab - 1] >= 0))
+      uf_union(parent, (int)j, (int)(j - slab));
   }
 }
 
@@ -270,6 +347,31 @@ int cb200_label_histogram(const int32_t* seg, const void* raw, int raw_dtype, in
   } else {
     return CB200_EUNSUPPORTED;
   }
+  CB200_LAUNCH_CHECK();
+  return CB200_OK;
+}
+
+int64_t cb200_label_otsu_workspace_bytes(int64_t total_bins) { return total_bins < 0 ? 0 : total_bins * 12 + 512; }
+
+int cb200_label_otsu(const unsigned int* hist, const int64_t* hist_offset, const int64_t* num_bins,
+                     const double* centre0, const double* centres, int arithmetic_dtype, int n_labels,
+                     int64_t total_bins, double* thresholds, void* workspace, void* stream) {
+  if (!hist || !hist_offset || !num_bins || !thresholds || !workspace || n_labels < 0 || total_bins < 0) return CB200_EINVAL;
+  if (!centre0 && !centres) return CB200_EINVAL;
+  if (n_labels == 0) return CB200_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* p = static_cast<uint8_t*>(workspace);
+  float* sw = reinterpret_cast<float*>(p);
+  void* sc = p + ((total_bins * 4 + 255) / 256) * 256;
+  const int blocks = (n_labels + 63) / 64;
+  if (arithmetic_dtype == CB200_F32)
+    label_otsu_kernel<float><<<blocks, 64, 0, st>>>(hist, hist_offset, num_bins, centre0, centres, n_labels, sw,
+                                                    static_cast<float*>(sc), thresholds);
+  else if (arithmetic_dtype == CB200_F64)
+    label_otsu_kernel<double><<<blocks, 64, 0, st>>>(hist, hist_offset, num_bins, centre0, centres, n_labels, sw,
+                                                     static_cast<double*>(sc), thresholds);
+  else
+    return CB200_EUNSUPPORTED;
   CB200_LAUNCH_CHECK();
   return CB200_OK;
 }

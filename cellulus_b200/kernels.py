@@ -668,6 +668,21 @@ def label_histogram(seg, raw, max_label, hist, raw_min=None, hist_offset=None, e
     return hist
 
 
+def label_otsu(hist, hist_offset, num_bins, total_bins, arithmetic_dtype, centre0=None, centres=None):
+    """`cb200_label_otsu`: float64 threshold per label (labels with num_bins <= 0 keep 0)."""
+    _require_cuda(hist, hist_offset, num_bins)
+    assert hist.dtype == torch.int32 and hist_offset.dtype == torch.int64 and num_bins.dtype == torch.int64
+    n_labels = int(num_bins.numel())
+    thresholds = torch.zeros(n_labels, dtype=torch.float64, device=hist.device)
+    ws = torch.empty(_lib().cb200_label_otsu_workspace_bytes(int(total_bins)), dtype=torch.uint8, device=hist.device)
+    rc = _lib().cb200_label_otsu(_ptr(hist), _ptr(hist_offset), _ptr(num_bins), _ptr(centre0), _ptr(centres),
+                                 _DTYPE_CODE[arithmetic_dtype], n_labels, int(total_bins), _ptr(thresholds), _ptr(ws),
+                                 _stream(hist))
+    check(rc, "cb200_label_otsu")
+    launch_counter["calls"] += 1
+    return thresholds
+
+
 def nucleus_fill(seg, raw, ids, thresholds, boxes, box_offset, total_box_voxels):
     """`cb200_nucleus_fill`: thresholded instance masks with their holes filled -> int32 label image."""
     _require_cuda(seg, raw)

@@ -2,8 +2,7 @@
 
 All three pixel-heavy steps run on the device: the grow / shrink of "cell" (`cb200_grow_shrink`: two
 thresholded Euclidean distance transforms), the per-instance Otsu + hole filling of "nucleus"
-(`cb200_label_stats`, `cb200_label_histogram`, `cb200_nucleus_fill`; only the O(bins) Otsu tail per instance
-is host arithmetic) and `size_filter` (`cb200_size_filter`, `utils/misc.py:11-25`).
+(`cb200_label_stats`, `cb200_label_histogram`, `cb200_label_otsu`, `cb200_nucleus_fill`) and `size_filter` (`cb200_size_filter`, `utils/misc.py:11-25`).
 """
 
 from __future__ import annotations
@@ -26,7 +25,6 @@ def nucleus(segmentation: np.ndarray, raw_image: np.ndarray, device="cuda") -> n
     import torch
 
     from cellulus_b200 import kernels as K
-    from cellulus_b200.detect import otsu_from_centers
 
     seg_np = np.ascontiguousarray(segmentation)
     out_dtype = seg_np.dtype
@@ -44,40 +42,41 @@ def nucleus(segmentation: np.ndarray, raw_image: np.ndarray, device="cuda") -> n
     ids = np.nonzero(box[:, 3] >= 0)[0]
     ids = ids[ids != 0]
     integer = np.issubdtype(raw_np.dtype, np.integer)
-    thresholds = np.empty(len(ids), np.float64)
+    present = np.zeros(max_label + 1, bool)
+    present[ids] = True
+    varied = present & (mn != mx)  # a constant instance: skimage returns that value (set below)
     if integer:  # skimage: one bin per value in [min, max] of the instance
-        span = np.zeros(max_label + 1, np.int64)
-        span[ids] = (mx[ids] - mn[ids]).astype(np.int64) + 1
-        offset = np.concatenate([[0], np.cumsum(span)[:-1]])
-        hist = torch.zeros(int(span.sum()), dtype=torch.int32, device=device)
-        K.label_histogram(seg, raw, max_label, hist, raw_min=mn_t,
-                          hist_offset=torch.from_numpy(offset).to(device))
-        counts = hist.cpu().numpy()
-        for n, i in enumerate(ids):
-            if mn[i] == mx[i]:
-                thresholds[n] = mn[i]  # constant: skimage returns that value
-            else:
-                thresholds[n] = otsu_from_centers(counts[offset[i]:offset[i] + span[i]],
-                                                  np.arange(int(mn[i]), int(mx[i]) + 1))
+        span = np.where(present, (mx - mn).astype(np.int64) + 1, 0)
+        offset = np.concatenate([[0], np.cumsum(span)[:-1]]).astype(np.int64)
+        total_bins = int(span.sum())
+        offset_t = torch.from_numpy(offset).to(device)
+        hist = torch.zeros(total_bins, dtype=torch.int32, device=device)
+        K.label_histogram(seg, raw, max_label, hist, raw_min=mn_t, hist_offset=offset_t)
+        thresholds_t = K.label_otsu(hist, offset_t, torch.from_numpy(span).to(device), total_bins, torch.float64,
+                                    centre0=mn_t)
     else:  # np.histogram, 256 bins over [min, max] of the instance, edges in the image's dtype
         nbins = 256
-        edges = np.zeros((max_label + 1, nbins + 1), np.float64)
-        for i in ids:
-            edges[i] = _bin_edges(mn[i], mx[i], raw_np.dtype, nbins)
+        dt = raw_np.dtype
+        edges = np.zeros((max_label + 1, nbins + 1), dt)
+        sel = np.nonzero(varied)[0]
+        if len(sel):
+            edges[sel] = np.linspace(mn[sel].astype(dt), mx[sel].astype(dt), nbins + 1, endpoint=True, dtype=dt, axis=-1)
+        centres = (edges[:, :-1] + edges[:, 1:]) / 2.0  # stays in the image's dtype, like skimage's bin centres
         hist = torch.zeros((max_label + 1) * nbins, dtype=torch.int32, device=device)
-        K.label_histogram(seg, raw, max_label, hist, edges=torch.from_numpy(edges).to(device), nbins=nbins)
-        counts = hist.cpu().numpy().reshape(max_label + 1, nbins)
-        for n, i in enumerate(ids):
-            if mn[i] == mx[i]:
-                thresholds[n] = mn[i]
-            else:
-                e = _bin_edges(mn[i], mx[i], raw_np.dtype, nbins)
-                thresholds[n] = otsu_from_centers(counts[i], (e[:-1] + e[1:]) / 2.0)
+        K.label_histogram(seg, raw, max_label, hist, edges=torch.from_numpy(edges.astype(np.float64)).to(device),
+                          nbins=nbins)
+        offset_t = torch.arange(max_label + 1, dtype=torch.int64, device=device) * nbins
+        num_bins = torch.from_numpy(np.where(varied, nbins, 0).astype(np.int64)).to(device)
+        thresholds_t = K.label_otsu(hist, offset_t, num_bins, (max_label + 1) * nbins,
+                                    torch.float32 if dt == np.float32 else torch.float64,
+                                    centres=torch.from_numpy(centres.astype(np.float64)).to(device))
+        thresholds_t = torch.where(torch.from_numpy(varied).to(device), thresholds_t, mn_t)
+    thresholds = thresholds_t[torch.from_numpy(ids).to(device)].contiguous()
     boxes = box[ids].astype(np.int32)
     volumes = np.prod(boxes[:, 3:].astype(np.int64) - boxes[:, :3] + 1, axis=1)
     box_offset = np.concatenate([[0], np.cumsum(volumes)]).astype(np.int64)
     out = K.nucleus_fill(seg, raw, torch.from_numpy(ids.astype(np.int32)).to(device),
-                         torch.from_numpy(thresholds).to(device), torch.from_numpy(boxes).to(device),
+                         thresholds, torch.from_numpy(boxes).to(device),
                          torch.from_numpy(box_offset).to(device), int(box_offset[-1]))
     return out.cpu().numpy().astype(out_dtype)
 

@@ -735,3 +735,16 @@ def test_evaluate_against_oracle_many_ids():
     IoU, SEG, n = compute_pairwise_IoU(pred, gt)
     rIoU, rSEG, rn = oeval.compute_pairwise_IoU(pred, gt)
     assert np.array_equal(IoU, rIoU) and SEG == rSEG and n == rn
+
+
+@pytest.mark.parametrize("shape", [(33, 47), (5, 9, 11), (1, 7)])
+def test_evaluate_odd_sizes(shape):
+    """Sizes that are not a multiple of the 16-byte vector width exercise the scalar tails."""
+    from cellulus_b200.evaluate import compute_pairwise_IoU
+
+    rng = np.random.default_rng(sum(shape))
+    gt = rng.integers(0, 6, size=shape).astype(np.uint16)
+    pred = rng.integers(0, 7, size=shape).astype(np.uint16) * 9
+    IoU, SEG, n = compute_pairwise_IoU(pred, gt)
+    rIoU, rSEG, rn = oeval.compute_pairwise_IoU(pred, gt)
+    assert np.array_equal(IoU, rIoU) and SEG == rSEG and n == rn

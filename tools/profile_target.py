@@ -59,3 +59,16 @@ if what in ("all", "brute", "greedy"):
             inst, n_obj, n_iter = K.greedy_cluster(d, mask, bench.DET_BW, 100)
             torch.cuda.synchronize()
             print(f"greedy: fg {int(mask.sum())} objects {n_obj} seeds tried {n_iter} total {time.time() - t0:.4f} s")
+
+if what in ("all", "post"):
+    from cellulus_b200.evaluate import compute_pairwise_IoU
+    from cellulus_b200.segment import nucleus
+
+    seg_np, raw_np = bench._label_scene((2048, 2048), 1200, 26, seed=3)
+    seg = torch.from_numpy(seg_np).to(dev)
+    for _ in range(2):
+        K.grow_shrink_(seg.clone(), 3, 6)
+        K.size_filter_(seg.clone(), 25)
+        nucleus(seg_np, raw_np)
+        compute_pairwise_IoU(seg_np.astype(np.uint16), np.roll(seg_np, (3, -2), axis=(0, 1)).astype(np.uint16))
+    torch.cuda.synchronize()
