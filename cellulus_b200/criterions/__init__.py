@@ -1,18 +1,9 @@
+"""Loss factory with the reference's call signature (`cellulus/criterions/__init__.py:4-17`)."""
+
 from cellulus_b200.criterions.oce_loss import GraphedLossStep, OCELoss, oce_loss_fused  # noqa: F401
 
 
-def get_loss(
-    temperature,
-    regularizer_weight,
-    density,
-    num_spatial_dims,
-    device,
-):
-    """Same factory as `cellulus/criterions/__init__.py:4-17`."""
-    return OCELoss(
-        temperature,
-        regularizer_weight,
-        density,
-        num_spatial_dims,
-        device,
-    )
+def get_loss(temperature, regularizer_weight, density, num_spatial_dims, device):
+    """`OCELoss` module; its `.fused(offsets, anchors, refs)` is the one-kernel form of the loss slice."""
+    settings = (temperature, regularizer_weight, density, num_spatial_dims, device)
+    return OCELoss(*settings)

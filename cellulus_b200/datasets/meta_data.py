@@ -1,67 +1,55 @@
-"""`DatasetMetaData` of `cellulus/datasets/meta_data.py`: the zarr layout contract -- arrays are
-`(s, c, [t,] [z,] y, x)` and carry an `axis_names` attribute."""
+"""`DatasetMetaData` (`cellulus/datasets/meta_data.py`): the zarr layout contract of the reference -- arrays
+are `(s, c, [t,] [z,] y, x)` and name their axes in an `axis_names` attribute."""
 
 from __future__ import annotations
 
 from typing import Tuple
 
 from cellulus_b200 import zarr_lite
-from cellulus_b200.configs import DatasetConfig
 
-_HELP = (
-    "The raw dataset should have shape (s, c, [t,] [z,] y, x), where s = # of samples, c = # of channels, "
-    "t = # of frames, and z/y/x are spatial extents. The dataset should have an \"axis_names\" attribute that "
-    'contains the names of the used axes, e.g., ["s", "c", "y", "x"] for a 2D dataset.'
-)
+_LAYOUT = ('expected layout: (s, c, [t,] [z,] y, x) = samples, channels, frames, spatial extents, with an '
+           '"axis_names" attribute such as ["s", "c", "y", "x"]')
+
+
+def _fail(what: str):
+    raise RuntimeError(f"{what}\n\n{_LAYOUT}")
 
 
 class DatasetMetaData:
+    """Axis bookkeeping: which axis holds samples / channels / time, and the spatial extents in array order."""
+
     def __init__(self, shape, axis_names):
+        position = {name: dim for dim, name in enumerate(axis_names)}
         self.num_dims = len(axis_names)
-        self.num_spatial_dims: int = 0
-        self.num_samples: int = 0
-        self.num_channels: int = 0
-        self.sample_dim = None
-        self.channel_dim = None
-        self.time_dim = None
-        self.spatial_array: Tuple[int, ...] = ()
-        for dim, name in enumerate(axis_names):
-            if name == "s":
-                self.sample_dim, self.num_samples = dim, shape[dim]
-            elif name == "c":
-                self.channel_dim, self.num_channels = dim, shape[dim]
-            elif name == "t":  # counted as spatial, not appended to spatial_array (reference quirk Q14)
-                self.num_spatial_dims += 1
-                self.time_dim = dim
-            elif name in ("z", "y", "x"):
-                self.num_spatial_dims += 1
-                self.spatial_array += (shape[dim],)
+        self.sample_dim = position.get("s")
+        self.channel_dim = position.get("c")
+        self.time_dim = position.get("t")
+        self.num_samples: int = shape[self.sample_dim] if self.sample_dim is not None else 0
+        self.num_channels: int = shape[self.channel_dim] if self.channel_dim is not None else 0
+        spatial = [dim for dim, name in enumerate(axis_names) if name in ("z", "y", "x")]
+        # 't' counts as a spatial dimension but contributes no extent (reference quirk Q14)
+        self.num_spatial_dims: int = len(spatial) + (1 if self.time_dim is not None else 0)
+        self.spatial_array: Tuple[int, ...] = tuple(shape[dim] for dim in spatial)
         if self.sample_dim is None:
-            raise RuntimeError("dataset does not have a sample dimension\n\n" + _HELP)
+            _fail("dataset does not have a sample dimension")
         if self.channel_dim is None:
-            raise RuntimeError("dataset does not have a channel dimension\n\n" + _HELP)
+            _fail("dataset does not have a channel dimension")
         if self.num_dims != len(shape):
-            raise RuntimeError(
-                f"dataset has {len(shape)} dimensions, but attribute axis_names has {self.num_dims} entries\n\n" + _HELP)
+            _fail(f"dataset has {len(shape)} dimensions, but attribute axis_names has {self.num_dims} entries")
 
     @staticmethod
-    def from_dataset_config(dataset_config: DatasetConfig) -> "DatasetMetaData":
+    def from_dataset_config(dataset_config) -> "DatasetMetaData":
+        where = f'"{dataset_config.dataset_name}" in {dataset_config.container_path}'
         container = zarr_lite.open(dataset_config.container_path, "r")
         try:
             data = container[dataset_config.dataset_name]
         except KeyError:
-            raise RuntimeError(
-                f"Zarr container {dataset_config.container_path} does not contain "
-                f'"{dataset_config.dataset_name}" dataset\n\n' + _HELP)
+            _fail(f"no dataset {where}")
         try:
             axis_names = data.attrs["axis_names"]
         except KeyError:
-            raise RuntimeError(
-                f'"{dataset_config.dataset_name}" dataset in {dataset_config.container_path} does not contain '
-                f'"axis_names" attribute\n\n' + _HELP)
+            _fail(f'dataset {where} has no "axis_names" attribute')
         try:
             return DatasetMetaData(data.shape, axis_names)
-        except RuntimeError as e:
-            raise RuntimeError(
-                f'"{dataset_config.dataset_name}" dataset in {dataset_config.container_path} has invalid meta-data'
-            ) from e
+        except RuntimeError as error:
+            raise RuntimeError(f"dataset {where} has invalid meta-data") from error

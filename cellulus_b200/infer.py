@@ -1,5 +1,6 @@
-"""`infer(experiment_config)` -- the reference's inference entry point (`cellulus/infer.py:16-80`):
-defaults from `object_size`, checkpoint loading, predict -> detect -> segment."""
+"""`infer(experiment_config)` -- the reference's inference entry point (`cellulus/infer.py:16-80`): defaults
+derived from `object_size`, checkpoint loading, then predict -> detect -> segment -> evaluate, each stage
+run when its dataset is configured."""
 
 from __future__ import annotations
 
@@ -18,48 +19,59 @@ from cellulus_b200.segment import segment
 torch.backends.cudnn.benchmark = True
 
 
-def infer(experiment_config):
-    print(experiment_config)
-    inference_config = experiment_config.inference_config
-    model_config = experiment_config.model_config
-    meta = DatasetMetaData.from_dataset_config(inference_config.dataset_config)
-    nd = meta.num_spatial_dims
+def _derive_defaults(inference_config, object_size: float, num_spatial_dims: int) -> None:
+    """Bandwidth = half the object size; minimum size = a tenth of a disc / ball of that diameter (`:28-39`)."""
+    if inference_config.bandwidth is None:
+        inference_config.bandwidth = 0.5 * object_size
+    if inference_config.min_size is None:
+        if num_spatial_dims == 2:
+            inference_config.min_size = int(0.1 * np.pi * object_size**2 / 4)
+        else:
+            inference_config.min_size = int(0.1 * 4.0 / 3.0 * np.pi * object_size**3 / 8)
 
-    if inference_config.bandwidth is None:  # infer.py:28-29
-        inference_config.bandwidth = 0.5 * experiment_config.object_size
-    if inference_config.min_size is None:  # infer.py:31-39
-        s = experiment_config.object_size
-        inference_config.min_size = int(0.1 * np.pi * s**2 / 4) if nd == 2 else int(0.1 * 4.0 / 3.0 * np.pi * s**3 / 8)
 
+def _device(inference_config) -> torch.device:
+    """The configured CUDA device, or this rank's GPU under torchrun (one process per GPU, NCCL)."""
     device = torch.device(inference_config.device)
     if device.type != "cuda" or not torch.cuda.is_available():
         raise RuntimeError(f"infer: device={device!s} -- cellulus_b200 has no CPU fallback; use a CUDA device")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1:
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         import torch.distributed as dist
 
         device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
         torch.cuda.set_device(device)
         if not dist.is_initialized():
             dist.init_process_group("nccl", device_id=device)
-    model = get_model(
-        in_channels=meta.num_channels, out_channels=nd, num_fmaps=model_config.num_fmaps,
-        fmap_inc_factor=model_config.fmap_inc_factor, features_in_last_layer=model_config.features_in_last_layer,
-        downsampling_factors=[tuple(f) for f in model_config.downsampling_factors], num_spatial_dims=nd)
-    model = model.to(device)
-    if model_config.checkpoint is not None and os.path.exists(model_config.checkpoint):
-        state = torch.load(model_config.checkpoint, map_location=device)
-        model.load_state_dict(state["model_state_dict"], strict=True)
-    else:
-        assert False, f"Model weights do not exist at this location :{model_config.checkpoint}!"
-    model.eval()
+    return device
 
-    rank = int(os.environ.get("RANK", "0"))
-    if inference_config.prediction_dataset_config is not None:
-        predict(model, inference_config, experiment_config.normalization_factor)
-    if inference_config.detection_dataset_config is not None:
-        detect(inference_config)
-    if inference_config.segmentation_dataset_config is not None and rank == 0:
-        segment(inference_config)
-    if inference_config.evaluation_dataset_config is not None and rank == 0:
-        evaluate(inference_config)
+
+def _restore_model(model_config, in_channels: int, num_spatial_dims: int, device: torch.device):
+    model = get_model(in_channels, num_spatial_dims, model_config.num_fmaps, model_config.fmap_inc_factor,
+                      model_config.features_in_last_layer, [tuple(f) for f in model_config.downsampling_factors],
+                      num_spatial_dims).to(device)
+    checkpoint = model_config.checkpoint
+    assert checkpoint is not None and os.path.exists(checkpoint), \
+        f"Model weights do not exist at this location :{checkpoint}!"
+    model.load_state_dict(torch.load(checkpoint, map_location=device)["model_state_dict"], strict=True)
+    return model.eval()
+
+
+def infer(experiment_config):
+    print(experiment_config)
+    inference_config = experiment_config.inference_config
+    meta = DatasetMetaData.from_dataset_config(inference_config.dataset_config)
+    _derive_defaults(inference_config, experiment_config.object_size, meta.num_spatial_dims)
+    model = _restore_model(experiment_config.model_config, meta.num_channels, meta.num_spatial_dims,
+                           _device(inference_config))
+    first_rank = int(os.environ.get("RANK", "0")) == 0
+    # (stage, its dataset, runs on every rank?) -- predict and detect shard their scan blocks / samples
+    stages = (
+        (lambda: predict(model, inference_config, experiment_config.normalization_factor),
+         inference_config.prediction_dataset_config, True),
+        (lambda: detect(inference_config), inference_config.detection_dataset_config, True),
+        (lambda: segment(inference_config), inference_config.segmentation_dataset_config, False),
+        (lambda: evaluate(inference_config), inference_config.evaluation_dataset_config, False),
+    )
+    for run, dataset, every_rank in stages:
+        if dataset is not None and (every_rank or first_rank):
+            run()

@@ -35,97 +35,102 @@ def _require_cuda(device: torch.device, what: str):
             "(there is no CPU fallback); set `device = \"cuda:0\"` in the config")
 
 
-def train(experiment_config):
-    print(experiment_config)
-    train_config = experiment_config.train_config
-    model_config = experiment_config.model_config
-    device = torch.device(train_config.device)
-    _require_cuda(device, "train")
-
-    import torch.distributed as dist
-
+def _join_ranks(device: torch.device):
+    """(device, rank, world): under torchrun every rank takes its local GPU and joins the NCCL group."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
     if world > 1:
+        import torch.distributed as dist
+
         device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
         torch.cuda.set_device(device)
         if not dist.is_initialized():
             dist.init_process_group("nccl", device_id=device)
     else:
         torch.cuda.set_device(device)
-    if rank == 0 and not os.path.exists("models"):
-        os.makedirs("models")
+    return device, int(os.environ.get("RANK", "0")), world
 
-    train_dataset = get_dataset(
-        dataset_config=train_config.train_data_config,
-        crop_size=tuple(train_config.crop_size),
-        elastic_deform=train_config.elastic_deform,
-        control_point_spacing=train_config.control_point_spacing,
-        control_point_jitter=train_config.control_point_jitter,
-        density=train_config.density,
-        kappa=train_config.kappa,
-        normalization_factor=experiment_config.normalization_factor,
-    )
-    train_dataset.sample_pairs = False  # pair lists are drawn on the device
-    train_dataloader = torch.utils.data.DataLoader(
-        dataset=train_dataset, batch_size=train_config.batch_size, drop_last=True,
-        num_workers=train_config.num_workers, pin_memory=True)
 
-    nd = train_dataset.get_num_spatial_dims()
-    model = get_model(
-        in_channels=train_dataset.get_num_channels(), out_channels=nd, num_fmaps=model_config.num_fmaps,
-        fmap_inc_factor=model_config.fmap_inc_factor, features_in_last_layer=model_config.features_in_last_layer,
-        downsampling_factors=[tuple(f) for f in model_config.downsampling_factors], num_spatial_dims=nd)
+class _Checkpoints:
+    """The reference's checkpoint dictionary (`train.py:129-157`): same keys, same file names under models/."""
+
+    def __init__(self, model, optimizer, logger):
+        self.model, self.optimizer, self.logger = model, optimizer, logger
+        self.lowest_loss = 1e6
+        self.first_iteration = 0
+
+    def resume(self, path, device):
+        print(f"Resuming model from {path}")
+        state = torch.load(path, map_location=device)
+        self.first_iteration = state["iteration"] + 1
+        self.lowest_loss = state["lowest_loss"]
+        self.model.load_state_dict(state["model_state_dict"], strict=True)
+        self.optimizer.load_state_dict(state["optim_state_dict"])
+        self.logger.data = state["logger_data"]
+
+    def save(self, iteration, is_lowest=False):
+        save_model({"iteration": iteration, "lowest_loss": self.lowest_loss,
+                    "model_state_dict": self.model.state_dict(), "optim_state_dict": self.optimizer.state_dict(),
+                    "logger_data": self.logger.data}, iteration, is_lowest)
+
+
+def train(experiment_config):
+    print(experiment_config)
+    cfg = experiment_config.train_config
+    model_config = experiment_config.model_config
+    device = torch.device(cfg.device)
+    _require_cuda(device, "train")
+    device, rank, world = _join_ranks(device)
+    main = rank == 0
+    if main:
+        os.makedirs("models", exist_ok=True)
+
+    dataset = get_dataset(cfg.train_data_config, tuple(cfg.crop_size), cfg.elastic_deform, cfg.control_point_spacing,
+                          cfg.control_point_jitter, cfg.density, cfg.kappa, experiment_config.normalization_factor)
+    dataset.sample_pairs = False  # the pair lists are drawn on the device, not by the DataLoader workers
+    loader = torch.utils.data.DataLoader(dataset=dataset, batch_size=cfg.batch_size, drop_last=True,
+                                         num_workers=cfg.num_workers, pin_memory=True)
+
+    nd = dataset.get_num_spatial_dims()
     memory_format = torch.channels_last if nd == 2 else torch.channels_last_3d
+    model = get_model(dataset.get_num_channels(), nd, model_config.num_fmaps, model_config.fmap_inc_factor,
+                      model_config.features_in_last_layer, [tuple(f) for f in model_config.downsampling_factors], nd)
     model = model.to(device).to(memory_format=memory_format)
-    if model_config.initialize:
-        for _name, layer in model.named_modules():
+    if model_config.initialize:  # train.py:57-61
+        for layer in model.modules():
             if isinstance(layer, torch.nn.modules.conv._ConvNd):
                 torch.nn.init.kaiming_normal_(layer.weight, nonlinearity="relu")
 
-    criterion = get_loss(regularizer_weight=train_config.regularizer_weight, temperature=train_config.temperature,
-                         density=train_config.density, num_spatial_dims=nd, device=device)
-    optimizer = torch.optim.Adam(model.parameters(), lr=train_config.initial_learning_rate, weight_decay=0.01)
+    criterion = get_loss(cfg.temperature, cfg.regularizer_weight, cfg.density, nd, device)
+    optimizer = torch.optim.Adam(model.parameters(), lr=cfg.initial_learning_rate, weight_decay=0.01)
     logger = get_logger(keys=["loss", "oce_loss"], title="loss")
-
-    start_iteration, lowest_loss, epoch_loss, num_iterations = 0, 1e6, 0, 0
+    checkpoints = _Checkpoints(model, optimizer, logger)
     if model_config.checkpoint is not None:
-        print(f"Resuming model from {model_config.checkpoint}")
-        state = torch.load(model_config.checkpoint, map_location=device)
-        start_iteration = state["iteration"] + 1
-        lowest_loss = state["lowest_loss"]
-        model.load_state_dict(state["model_state_dict"], strict=True)
-        optimizer.load_state_dict(state["optim_state_dict"])
-        logger.data = state["logger_data"]
+        checkpoints.resume(model_config.checkpoint, device)
 
-    net = model
-    if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[device.index])
-
-    def state_dict(iteration):
-        return {"iteration": iteration, "lowest_loss": lowest_loss, "model_state_dict": model.state_dict(),
-                "optim_state_dict": optimizer.state_dict(), "logger_data": logger.data}
-
-    for iteration, raw in zip(range(start_iteration, train_config.max_iterations), train_dataloader):
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[device.index]) if world > 1 else model
+    running, steps = 0.0, 0  # mean loss since the last "best model" check
+    for iteration, raw in zip(range(checkpoints.first_iteration, cfg.max_iterations), loader):
         loss, oce_loss, prediction = train_iteration(
-            raw, net, criterion, optimizer, device, train_dataset, memory_format,
+            raw, net, criterion, optimizer, device, dataset, memory_format,
             seed=1_000_003 * rank + iteration, grad_scale=float(world))
-        if rank == 0:
+        if main:
             print(f"===> loss: {loss:.6f}, oce loss: {oce_loss:.6f}")
             logger.add(key="loss", value=loss)
             logger.add(key="oce_loss", value=oce_loss)
             logger.write()
-        epoch_loss += loss
-        num_iterations += 1
-        if iteration % train_config.save_best_model_every == 0:
-            is_lowest = epoch_loss / num_iterations < lowest_loss
-            lowest_loss = min(epoch_loss / num_iterations, lowest_loss)
-            if is_lowest and rank == 0:
-                save_model(state_dict(iteration), iteration, is_lowest)
-            epoch_loss, num_iterations = 0, 0
-        if (iteration % train_config.save_model_every == 0 or iteration == train_config.max_iterations - 1) and rank == 0:
-            save_model(state_dict(iteration), iteration)
-        if iteration % train_config.save_snapshot_every == 0 and rank == 0:
+        running += loss
+        steps += 1
+        if iteration % cfg.save_best_model_every == 0:
+            mean_loss = running / steps
+            improved = mean_loss < checkpoints.lowest_loss
+            checkpoints.lowest_loss = min(mean_loss, checkpoints.lowest_loss)
+            if improved and main:
+                checkpoints.save(iteration, is_lowest=True)
+            running, steps = 0.0, 0
+        last = iteration == cfg.max_iterations - 1
+        if main and (iteration % cfg.save_model_every == 0 or last):
+            checkpoints.save(iteration)
+        if main and iteration % cfg.save_snapshot_every == 0:
             save_snapshot(raw, prediction, iteration)
 
 

@@ -80,7 +80,7 @@ def test_zarr_lite_layout_roundtrip(tmp_path):
     assert os.path.exists(tmp_path / "c.zarr" / ".zgroup") and os.path.exists(tmp_path / "c.zarr" / "raw" / "0.0.0.0")
     meta = DatasetMetaData.from_dataset_config(DatasetConfig(container_path=tmp_path / "c.zarr", dataset_name="raw"))
     assert (meta.num_samples, meta.num_channels, meta.num_spatial_dims, meta.spatial_array) == (3, 2, 2, (40, 50))
-    with pytest.raises(RuntimeError, match="does not contain"):
+    with pytest.raises(RuntimeError, match="no dataset"):
         DatasetMetaData.from_dataset_config(DatasetConfig(container_path=tmp_path / "c.zarr", dataset_name="nope"))
 
 
