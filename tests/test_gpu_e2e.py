@@ -170,12 +170,15 @@ def test_train_then_infer_end_to_end(tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)
     g = zarr_lite.open(tmp_path / "data.zarr")
     rng = np.random.default_rng(0)
+    truth = {}
     for name, n in [("train", 3), ("test", 2)]:
         a = g.create_dataset(name, shape=(n, 1, 120, 130), dtype=np.uint8)
         img = np.zeros((n, 1, 120, 130), np.uint8)
+        truth[name] = np.zeros((n, 1, 120, 130), np.uint16)
         for s in range(n):
             _, _, ids = synthetic.blob_scene((120, 130), 12, radius=7.0, seed=int(rng.integers(1000)))
             img[s, 0] = np.where(ids > 0, 200, 20) + rng.integers(0, 20, size=ids.shape)
+            truth[name][s, 0] = ids
         a[...] = img
         a.attrs["axis_names"] = ["s", "c", "y", "x"]
 
@@ -206,6 +209,51 @@ def test_train_then_infer_end_to_end(tmp_path, monkeypatch):
     assert np.array_equal(mask, e[:, 2] < 0.02)  # foreground mask: exact
     d = det[...]
     assert np.array_equal(d[:, 0] > 0, mask) and np.array_equal(d[:, 1] > 0, mask)
+
+    # segment(): "cell" post-processing + size filter, against the oracle on the stored detection
+    from oracle import evaluate as oeval
+    from oracle import post_process as opost
+    from oracle import size_filter as osize
+
+    min_size = cfg.inference_config.min_size
+    for sample in range(2):
+        for k in range(2):
+            ref = opost.grow_shrink(d[sample, k].copy(), 1, 2)
+            assert np.array_equal(seg[...][sample, k], osize.size_filter(ref, min_size).astype(np.uint16))
+
+    # second pass over the stored detection: "nucleus" post-processing and evaluate() against ground truth
+    from cellulus_b200.configs import DatasetConfig
+
+    gt = zarr_lite.open(tmp_path / "out.zarr").create_dataset("groundtruth", shape=(2, 1, 120, 130), dtype=np.uint16)
+    gt[...] = truth["test"]
+    ic = cfg.inference_config
+    ic.prediction_dataset_config = None
+    ic.detection_dataset_config = None
+    ic.post_processing = "nucleus"
+    ic.segmentation_dataset_config = DatasetConfig(container_path=tmp_path / "out.zarr", dataset_name="segmentation-nucleus",
+                                                   secondary_dataset_name="detection")
+    ic.evaluation_dataset_config = DatasetConfig(container_path=tmp_path / "out.zarr", dataset_name="groundtruth",
+                                                 secondary_dataset_name="segmentation-nucleus")
+    infer(cfg)
+    out = zarr_lite.open(tmp_path / "out.zarr", "r")
+    raw_test = zarr_lite.open(tmp_path / "data.zarr", "r")["test"][...]
+    nuc = out["segmentation-nucleus"][...]
+    for sample in range(2):
+        for k in range(2):
+            ref = opost.nucleus(d[sample, k].copy(), raw_test[sample, 0])
+            assert np.array_equal(nuc[sample, k], osize.size_filter(ref, min_size).astype(np.uint16))
+    for k in range(2):
+        lines = open(tmp_path / f"results_bandwidth-{k}.txt").read().splitlines()
+        assert lines[0] == "file index, F1, SEG, TP, FP, FN " and lines[1].startswith("+++")
+        tp = fp = fn = 0
+        seg_sum, n_ids = 0.0, 0
+        for sample in range(2):
+            IoU, SEG, n = oeval.compute_pairwise_IoU(nuc[sample, k], truth["test"][sample, 0])
+            F1, TP, FP, FN = oeval.compute_F1(IoU)
+            assert lines[2 + sample] == f"{sample}, {F1:.05f}, {SEG / n:.05f}, {TP}, {FP}, {FN}"
+            tp, fp, fn, seg_sum, n_ids = tp + TP, fp + FP, fn + FN, seg_sum + SEG, n_ids + n
+        assert lines[5] == f"F1 for complete dataset is {2 * tp / (2 * tp + fp + fn):.05f} "
+        assert lines[6] == f"SEG for complete dataset is {seg_sum / n_ids:.05f} "
 
 
 @pytest.mark.parametrize("case", ["2d", "3d"])
