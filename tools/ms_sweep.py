@@ -1,6 +1,6 @@
 """BASELINE configs[3]: mean-shift sweep on synthetic embeddings (disc / ball scenes sized to N foreground points).
 
-    python tools/ms_sweep.py [max_points_millions]
+    python tools/ms_sweep.py [max_points_millions [min_points_millions]]
 
 For each (D, N, bandwidth, seeding) prints one JSON line: time of threshold -> labels on the device, foreground
 points labelled per second, the kernels' pair-test counts where known.
@@ -19,12 +19,13 @@ from cellulus_b200 import synthetic  # noqa: E402
 from cellulus_b200.detect import detect_embeddings  # noqa: E402
 
 max_m = float(sys.argv[1]) if len(sys.argv) > 1 else 16
+min_m = float(sys.argv[2]) if len(sys.argv) > 2 else 0
 dev = torch.device("cuda:0")
 torch.cuda.set_device(dev)
 radius = 10.0
 for D in (2, 3):
     for n_m in (1, 4, 16, 64):
-        if n_m > max_m:
+        if n_m > max_m or n_m < min_m:
             continue
         shape, n_obj = synthetic.scene_for_points(int(n_m * 1e6), D, radius=radius)
         t0 = time.time()
