@@ -104,6 +104,62 @@ tta_aggregate_kernel(const float* __restrict__ stack, int T, int64_t n, int64_t 
   }
 }
 
+// Small blocks (a 496 x 496 scan block is 246 k pixels): even 8-byte granules leave the chip half empty and
+// every thread walks all T passes one after the other.  Here TWO adjacent lanes share a granule, each folds
+// one half of the passes (ceil(T/2) / floor(T/2)), and the halves are merged with the pairwise update of
+// Chan et al. (mean and M2 of the union from those of the parts) through one shuffle -- twice the threads,
+// half the dependent chain, and every warp load still covers two contiguous 128-byte runs.
+template <int C, int V>
+__global__ void __launch_bounds__(TTA_THREADS)
+tta_aggregate_split_kernel(const float* __restrict__ stack, int T, int64_t n, int64_t nv, float* __restrict__ out) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = tid >> 1;  // granule
+  const int half = (int)(tid & 1);
+  const bool live = i < nv;    // nv is padded so that whole warps stay together for the shuffle
+  const int t_split = (T + 1) / 2;
+  const int t0 = half ? t_split : 0, t1 = half ? T : t_split;
+  WelfordV<V> w[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) w[c].init();
+  if (live) {
+    constexpr int U = 8;
+    for (int t = t0; t < t1; t += U) {
+      Vec<V> x[U][C];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          if (t + u < t1) x[u][c] = ld_stream_vec<V>(stack + ((int64_t)(t + u) * C + c) * n + i * V);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (t + u < t1) {
+          const float inv = 1.0f / (float)(t + u - t0 + 1);
+#pragma unroll
+          for (int c = 0; c < C; ++c) w[c].push(x[u][c], inv);
+        }
+    }
+  }
+  // merge: the even lane receives the odd lane's half
+  const float na = (float)t_split, nb = (float)(T - t_split), inv_T = 1.0f / (float)T;
+  Vec<V> s;
+#pragma unroll
+  for (int j = 0; j < V; ++j) s.v[j] = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float mean_b = __shfl_down_sync(0xffffffffu, w[c].mean.v[j], 1);
+      const float m2_b = __shfl_down_sync(0xffffffffu, w[c].m2.v[j], 1);
+      const float delta = mean_b - w[c].mean.v[j];
+      w[c].mean.v[j] = fmaf(delta, nb * inv_T, w[c].mean.v[j]);
+      w[c].m2.v[j] = w[c].m2.v[j] + m2_b + delta * delta * (na * nb * inv_T);
+      s.v[j] += sqrtf(w[c].m2.v[j] * inv_T);
+    }
+    if (live && !half) st_stream_vec<V>(out + (int64_t)c * n + i * V, w[c].mean);
+  }
+  if (live && !half) st_stream_vec<V>(out + (int64_t)C * n + i * V, s);
+}
+
 // Generic scalar fallback: any C <= TTA_MAXC, any n / alignment; `first` = first pixel handled.
 __global__ void __launch_bounds__(TTA_THREADS)
 tta_aggregate_scalar_kernel(const float* __restrict__ stack, int T, int C, int64_t n, int64_t first,
@@ -209,8 +265,12 @@ int cb200_tta_aggregate(const float* stack, int num_passes, int channels, int64_
     const bool wide = n / 4 >= (int64_t)CB200_SM_COUNT * 1024;
     const int64_t nv = wide ? n / 4 : n / 2;
     const int blocks = grid_for(nv, TTA_THREADS, 1, 16);
+    const bool split = !wide && num_passes >= 4;  // small block: two lanes per granule, half the passes each
+    const int split_threads = 64;
+    const int64_t split_blocks = (2 * nv + split_threads - 1) / split_threads;
 #define CB200_TTA(CC)                                                                                      \
   if (wide) tta_aggregate_kernel<CC, 4><<<blocks, TTA_THREADS, 0, st>>>(stack, num_passes, n, nv, out);    \
+  else if (split) tta_aggregate_split_kernel<CC, 2><<<(unsigned)split_blocks, split_threads, 0, st>>>(stack, num_passes, n, nv, out); \
   else tta_aggregate_kernel<CC, 2><<<blocks, TTA_THREADS, 0, st>>>(stack, num_passes, n, nv, out);
     switch (channels) {
       case 1: CB200_TTA(1) break;
