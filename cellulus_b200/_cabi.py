@@ -12,7 +12,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CELLULUS_B200_LIB") or os.path.join(PKG, "libcellulus_b200.so")  # override: A/B builds
 
-OK, EINVAL, EUNSUPPORTED = 0, -1, -2
+OK, EINVAL, EUNSUPPORTED, ENOFIT, ENOCENTRE, ENOCONVERGE = 0, -1, -2, -3, -4, -5
 F32, BF16, F64, I64, I32, I16, U8, U16 = range(8)
 LAYOUT_PLANAR, LAYOUT_CHANNELS_LAST = 0, 1
 
@@ -27,6 +27,19 @@ class Grid(C.Structure):
         ("dims", C.c_int32 * 3),
         ("num_dims", C.c_int32),
         ("n_cells", C.c_int64),
+    ]
+
+
+class DetectInfo(C.Structure):
+    """`cb200_detect_info` (include/cellulus_b200.h)."""
+
+    _fields_ = [
+        ("n_foreground", C.c_int64),
+        ("n_fit", C.c_int64),
+        ("n_seeds", C.c_int64),
+        ("n_centres", C.c_int32),
+        ("suppress_calls", C.c_int32),
+        ("grid", Grid),
     ]
 
 
@@ -87,6 +100,8 @@ PROTOTYPES = {
     "cb200_edt_workspace_bytes": (_i64, [_i64]),
     "cb200_edt_within": (_i, [_p, _i, _pi64, _d, _p, _p, _p]),
     "cb200_grow_shrink": (_i, [_p, _i, _pi64, _d, _d, _p, _p]),
+    "cb200_detect_volume": (_i, [_p, _i, _i, _pi64, _d, _d, _d, _u64, _i, _p, _i, _p, _i, _p, _i64,
+                                 C.POINTER(DetectInfo), _p]),
     "cb200_label_presence": (_i, [_p, _i, _i64, _i, _p, _p]),
     "cb200_contingency": (_i, [_p, _p, _i, _i64, _p, _p, _i, _i, _p, _p]),
     "cb200_label_stats_workspace_bytes": (_i64, [_i]),

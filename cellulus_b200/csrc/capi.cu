@@ -14,6 +14,9 @@ const char* cb200_error_string(int code) {
   if (code == CB200_OK) return "ok";
   if (code == CB200_EINVAL) return "invalid argument";
   if (code == CB200_EUNSUPPORTED) return "unsupported dtype / dimensionality";
+  if (code == CB200_ENOFIT) return "the fit subset is empty";
+  if (code == CB200_ENOCENTRE) return "no point was within the bandwidth of any seed";
+  if (code == CB200_ENOCONVERGE) return "centre suppression did not reach its fix-point";
   if (code > 0) return cudaGetErrorString((cudaError_t)code);
   return "unknown error";
 }

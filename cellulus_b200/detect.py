@@ -50,7 +50,8 @@ def threshold_otsu(std: torch.Tensor, nbins: int = 256):
 
 
 def detect_embeddings(embeddings, bandwidth, threshold=None, num_bandwidths=1, reduction_probability=0.1,
-                      seeds=None, rng="numpy", method="auto", label_dtype=torch.uint16, return_info=False):
+                      seeds=None, rng="numpy", method="auto", label_dtype=torch.uint16, return_info=False,
+                      one_call=None):
     """Per-sample body of `detect.py:82-161` (`clustering="meanshift"`, `use_seeds=False`).
 
     embeddings : (D+1, *S) CUDA tensor, fp32 or fp64 (channel D = std), or a numpy array (uploaded)
@@ -62,11 +63,13 @@ def detect_embeddings(embeddings, bandwidth, threshold=None, num_bandwidths=1, r
     D = embeddings.shape[0] - 1
     if threshold is None:
         threshold = threshold_otsu(embeddings[D])
+    if one_call is None:  # per-seed details are only available from the step-by-step sequence
+        one_call = not return_info
     out, infos, mask = [], [], None
     for k in range(num_bandwidths):
         labels, info = MS.segment_embeddings_device(
             embeddings, bandwidth / (2**k), threshold, reduction_probability, seeds=seeds, rng=rng, method=method,
-            label_dtype=label_dtype, want_mask=(k == 0))
+            label_dtype=label_dtype, want_mask=(k == 0), one_call=one_call)
         if k == 0:
             mask = info.pop("mask")
         out.append(labels)

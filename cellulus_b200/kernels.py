@@ -726,3 +726,39 @@ def contingency(pred: torch.Tensor, gt: torch.Tensor, rank_pred: torch.Tensor, r
     check(rc, "cb200_contingency")
     launch_counter["calls"] += 1
     return table
+
+
+# --------------------------------------------------------------------------- one call per volume
+def detect_volume(emb: torch.Tensor, bandwidth: float, threshold: float, reduction_probability: float = 1.0,
+                  philox_seed: int = 0, max_iter: int = 300, label_dtype=torch.int32, want_mask: bool = False,
+                  centre_capacity: int = 0):
+    """`cb200_detect_volume`: threshold -> labels in ONE C-ABI call (scratch and the count reads are handled
+    inside the library).  Returns `(labels (*S), mask | None, centres (D, centre_capacity) | None, info dict)`.
+    Raises ValueError with scikit-learn's messages where `MeanShift.fit` would."""
+    _require_cuda(emb)
+    emb = emb.contiguous()
+    D = emb.shape[0] - 1
+    spatial = tuple(emb.shape[1:])
+    if len(spatial) != D or D not in (2, 3):
+        raise ValueError("emb must be (D+1, *S) with D spatial dims, D in {2, 3}")
+    dev = emb.device
+    labels = torch.empty(spatial, dtype=label_dtype, device=dev)
+    mask = torch.empty(spatial, dtype=torch.uint8, device=dev) if want_mask else None
+    centres = torch.zeros((D, centre_capacity), dtype=torch.float64, device=dev) if centre_capacity > 0 else None
+    info = _cabi.DetectInfo()
+    rc = _lib().cb200_detect_volume(
+        _ptr(emb), _code(emb, _FLOAT_DTYPES), D, spatial_array(spatial), float(threshold), float(bandwidth),
+        float(reduction_probability), int(philox_seed) & (2**64 - 1), int(max_iter), _ptr(labels),
+        _code(labels, (torch.int32, torch.uint16)), _ptr(mask), _DTYPE_CODE[torch.uint8] if want_mask else 0,
+        _ptr(centres), int(centre_capacity), C.byref(info), _stream(emb))
+    launch_counter["calls"] += 1
+    if rc == _cabi.ENOFIT:
+        raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required by MeanShift.")
+    if rc == _cabi.ENOCENTRE:
+        raise ValueError(
+            "No point was within bandwidth=%f of any seed. Try a different seeding strategy "
+            "                             or increase the bandwidth." % bandwidth)
+    check(rc, "cb200_detect_volume")
+    return labels, mask, centres, {"n_fg": int(info.n_foreground), "n_fit": int(info.n_fit),
+                                   "n_seeds": int(info.n_seeds), "k": int(info.n_centres), "method": "grid",
+                                   "grid_cells": int(info.grid.n_cells), "suppress_calls": int(info.suppress_calls)}

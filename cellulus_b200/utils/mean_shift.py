@@ -66,14 +66,24 @@ def cluster_points_device(points, n, fit_points, n_fit, bandwidth, seeds=None, m
 
 def segment_embeddings_device(emb, bandwidth, threshold, reduction_probability=1.0, seeds=None, rng="numpy",
                               fit_flags=None, method="auto", label_dtype=torch.int32, want_mask=False,
-                              philox_seed=0, assign="grid"):
+                              philox_seed=0, assign="grid", one_call=False):
     """threshold -> foreground points -> fit subset -> modes -> centres -> labels, all on the device.
 
     emb: (D+1, *S) CUDA tensor (fp32/fp64), channel D = std.  Returns `(labels (*S), info)`;
     labels are 0 for background and 1..K otherwise (`utils/mean_shift.py:57,101-104`).
     `rng`: "numpy" draws the fit subset exactly like the reference (`np.random.rand(N) < p`,
     :68-70, global RNG) and uploads the flags; "philox" draws it on the device.
+    `one_call`: run the identical sequence inside the library (`cb200_detect_volume`: one C-ABI call, no
+    interpreter between the kernels); needs the device RNG (or no subsampling) and the grid kernels, and
+    reports counts only (no per-seed modes / iterations in `info`).
     """
+    if one_call and seeds is None and fit_flags is None and method in ("auto", "grid") and assign == "grid" and (
+            rng == "philox" or reduction_probability >= 1.0):
+        labels, mask, _, info = K.detect_volume(emb, bandwidth, threshold, reduction_probability, philox_seed,
+                                               label_dtype=label_dtype, want_mask=want_mask)
+        if want_mask:
+            info["mask"] = mask
+        return labels, info
     D = emb.shape[0] - 1
     spatial = tuple(emb.shape[1:])
     dev = emb.device

@@ -37,6 +37,9 @@ extern "C" {
 #define CB200_OK 0
 #define CB200_EINVAL (-1)
 #define CB200_EUNSUPPORTED (-2)
+#define CB200_ENOFIT (-3)      /* the fit subset is empty (sklearn: "Found array with 0 sample(s)") */
+#define CB200_ENOCENTRE (-4)   /* no seed had a neighbour (sklearn: "No point was within bandwidth ...") */
+#define CB200_ENOCONVERGE (-5) /* centre suppression did not reach its fix-point */
 
 /* element types */
 #define CB200_F32 0
@@ -310,6 +313,31 @@ CB200_API int64_t cb200_assign_workspace_bytes(int64_t n_points, int n_centres, 
 CB200_API int cb200_assign_labels(const double* points, int64_t n_points, int64_t pts_stride, int num_dims,
                         const double* centres, int64_t centre_stride, int n_centres, const cb200_grid* grid,
                         const int32_t* pix_index, void* labels_out, int label_dtype, void* workspace, void* stream);
+
+/*
+ * The whole per-bandwidth sequence of `mean_shift_segmentation` (utils/mean_shift.py:6-45 + sklearn fit /
+ * predict) behind one call, for callers that do not need the intermediate results:
+ *   threshold -> foreground points -> fit subset (Bernoulli(reduction_probability) from the device Philox
+ *   stream; 1.0 = all points) -> cell grid -> modes -> centres -> labels (+1, 0 = background).
+ * Same kernels and results as the step-by-step entry points above.  Unlike them this one ALLOCATES its
+ * scratch (a library-owned arena per device, kept for the next call) and SYNCHRONISES the stream up to four times to read the
+ * data-dependent counts.  labels_out (n_pix, CB200_I32 / CB200_U16) is cleared by the call; mask_out optional
+ * (CB200_U8 / CB200_U16); centres_out optional device SoA (D x centre_capacity) receiving `cluster_centers_`.
+ * Returns CB200_ENOFIT / CB200_ENOCENTRE where scikit-learn raises ValueError.
+ */
+typedef struct cb200_detect_info {
+  int64_t n_foreground;
+  int64_t n_fit;
+  int64_t n_seeds;
+  int32_t n_centres;
+  int32_t suppress_calls;
+  cb200_grid grid;
+} cb200_detect_info;
+
+CB200_API int cb200_detect_volume(const void* emb, int dtype, int num_dims, const int64_t* spatial, double threshold,
+                        double bandwidth, double reduction_probability, uint64_t philox_seed, int max_iter,
+                        void* labels_out, int label_dtype, void* mask_out, int mask_dtype, double* centres_out,
+                        int64_t centre_capacity, cb200_detect_info* info /* host out */, void* stream);
 
 /*
  * Greedy seed-and-grow clustering, utils/greedy_cluster.py:46-120,176-253 (clustering = "greedy",

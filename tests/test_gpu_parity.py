@@ -748,3 +748,36 @@ def test_evaluate_odd_sizes(shape):
     IoU, SEG, n = compute_pairwise_IoU(pred, gt)
     rIoU, rSEG, rn = oeval.compute_pairwise_IoU(pred, gt)
     assert np.array_equal(IoU, rIoU) and SEG == rSEG and n == rn
+
+
+# ---------------------------------------------------------------------------------------------------
+# cb200_detect_volume: the step-by-step sequence behind one call -- identical labels
+@pytest.mark.parametrize("shape,objects,radius,bw,rp", [((96, 120), 14, 8.0, 4.0, 1.0), ((96, 120), 14, 8.0, 4.0, 0.3),
+                                                      ((40, 64, 72), 12, 7.0, 5.0, 0.2), ((40, 64, 72), 12, 7.0, 2.5, 1.0)])
+def test_detect_volume_matches_step_sequence(shape, objects, radius, bw, rp):
+    from cellulus_b200.utils.mean_shift import segment_embeddings_device
+
+    emb, _, _ = synthetic.blob_scene(shape, objects, radius=radius, seed=5)
+    d = torch.from_numpy(emb).to(_dev())
+    kw = dict(bandwidth=bw, threshold=0.5, reduction_probability=rp, rng="philox", philox_seed=11, want_mask=True)
+    for label_dtype in (torch.int32, torch.uint16):
+        ref, ref_info = segment_embeddings_device(d, label_dtype=label_dtype, **kw)
+        got, info = segment_embeddings_device(d, label_dtype=label_dtype, one_call=True, **kw)
+        assert torch.equal(got, ref) and got.dtype == label_dtype
+        assert torch.equal(info["mask"], ref_info["mask"])
+        assert (info["n_fg"], info["n_fit"], info["k"]) == (ref_info["n_fg"], ref_info["n_fit"], ref_info["k"])
+    labels, mask, centres, info = K.detect_volume(d, bw, 0.5, rp, philox_seed=11, centre_capacity=ref_info["k"] + 3)
+    assert torch.equal(centres[:, : info["k"]], ref_info["centres"])
+
+
+def test_detect_volume_edge_cases():
+    emb, _, _ = synthetic.blob_scene((48, 56), 5, radius=6.0, seed=2)
+    d = torch.from_numpy(emb).to(_dev())
+    labels, mask, _, info = K.detect_volume(d, 3.0, -1.0, 1.0, want_mask=True)  # nothing below the threshold
+    assert info["n_fg"] == 0 and int(labels.abs().sum()) == 0 and int(mask.sum()) == 0
+    with pytest.raises(ValueError, match="0 sample"):  # a fit subset that selects nothing
+        K.detect_volume(d, 3.0, 0.5, 0.0)
+    d64 = d.double()
+    a, _, _, _ = K.detect_volume(d64, 3.0, 0.5, 1.0)
+    b, _, _, _ = K.detect_volume(d, 3.0, 0.5, 1.0)
+    assert torch.equal(a, b)  # float64 storage of float32 values: same result
