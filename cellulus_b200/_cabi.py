@@ -102,6 +102,7 @@ PROTOTYPES = {
     "cb200_grow_shrink": (_i, [_p, _i, _pi64, _d, _d, _p, _p]),
     "cb200_detect_volume": (_i, [_p, _i, _i, _pi64, _d, _d, _d, _u64, _i, _p, _i, _p, _i, _p, _i64,
                                  C.POINTER(DetectInfo), _p]),
+    "cb200_release_scratch": (_i, []),
     "cb200_label_presence": (_i, [_p, _i, _i64, _i, _p, _p]),
     "cb200_contingency": (_i, [_p, _p, _i, _i64, _p, _p, _i, _i, _p, _p]),
     "cb200_label_stats_workspace_bytes": (_i64, [_i]),

@@ -72,6 +72,18 @@ struct ArenaScope {  // one call's view of the arena
 
 using namespace cb200;
 
+extern "C" int cb200_release_scratch(void) {
+  int device = 0;
+  CB200_CUDA_TRY(cudaGetDevice(&device));
+  if (device < 0 || device >= 64) return CB200_EUNSUPPORTED;
+  DeviceArena& a = g_arena[device];
+  std::lock_guard<std::mutex> guard(a.lock);
+  CB200_CUDA_TRY(cudaDeviceSynchronize());  // the last call's kernels may still be reading the arena
+  for (Chunk& c : a.chunks) cudaFree(c.base);
+  a.chunks.clear();
+  return CB200_OK;
+}
+
 #define CB200_TRY_RC(expr)        \
   do {                            \
     const int _rc = (expr);       \

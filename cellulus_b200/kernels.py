@@ -762,3 +762,9 @@ def detect_volume(emb: torch.Tensor, bandwidth: float, threshold: float, reducti
     return labels, mask, centres, {"n_fg": int(info.n_foreground), "n_fit": int(info.n_fit),
                                    "n_seeds": int(info.n_seeds), "k": int(info.n_centres), "method": "grid",
                                    "grid_cells": int(info.grid.n_cells), "suppress_calls": int(info.suppress_calls)}
+
+
+def release_scratch(device=None) -> None:
+    """`cb200_release_scratch`: give back the arena `detect_volume` keeps on `device` (default: current)."""
+    with torch.cuda.device(device if device is not None else torch.cuda.current_device()):
+        check(_lib().cb200_release_scratch(), "cb200_release_scratch")

@@ -339,6 +339,9 @@ CB200_API int cb200_detect_volume(const void* emb, int dtype, int num_dims, cons
                         void* labels_out, int label_dtype, void* mask_out, int mask_dtype, double* centres_out,
                         int64_t centre_capacity, cb200_detect_info* info /* host out */, void* stream);
 
+/* Frees the scratch arena cb200_detect_volume keeps on the current device (synchronises the device first). */
+CB200_API int cb200_release_scratch(void);
+
 /*
  * Greedy seed-and-grow clustering, utils/greedy_cluster.py:46-120,176-253 (clustering = "greedy",
  * detect.py:162-192): one persistent cooperative kernel runs the whole sequential loop on the device.

@@ -779,5 +779,9 @@ def test_detect_volume_edge_cases():
         K.detect_volume(d, 3.0, 0.5, 0.0)
     d64 = d.double()
     a, _, _, _ = K.detect_volume(d64, 3.0, 0.5, 1.0)
+    K.release_scratch()  # the arena is rebuilt on demand
     b, _, _, _ = K.detect_volume(d, 3.0, 0.5, 1.0)
     assert torch.equal(a, b)  # float64 storage of float32 values: same result
+    free_before = torch.cuda.mem_get_info()[0]
+    K.release_scratch()
+    assert torch.cuda.mem_get_info()[0] >= free_before
