@@ -104,7 +104,7 @@ PROTOTYPES = {
                                  C.POINTER(DetectInfo), _p]),
     "cb200_release_scratch": (_i, []),
     "cb200_label_presence": (_i, [_p, _i, _i64, _i, _p, _p]),
-    "cb200_contingency": (_i, [_p, _p, _i, _i64, _p, _p, _i, _i, _p, _p]),
+    "cb200_contingency": (_i, [_p, _p, _i, _i64, _p, _p, _i, _i, _i, _p, _p]),
     "cb200_label_stats_workspace_bytes": (_i64, [_i]),
     "cb200_label_stats": (_i, [_p, _p, _i, _i, _pi64, _i, _p, _p, _p, _p, _p]),
     "cb200_label_histogram": (_i, [_p, _p, _i, _i64, _i, _p, _p, _p, _i, _p, _p]),

@@ -46,10 +46,17 @@ label_presence_kernel(const T* __restrict__ labels, int64_t n, int64_t nvec, int
 template <typename T>
 __global__ void __launch_bounds__(256)
 contingency_kernel(const T* __restrict__ pred, const T* __restrict__ gt, int64_t n, int64_t nvec,
-                   const int32_t* __restrict__ rank_p, const int32_t* __restrict__ rank_g, int cols,
+                   const int32_t* __restrict__ rank_p, const int32_t* __restrict__ rank_g, int max_value, int cols,
                    unsigned int* __restrict__ table) {
   constexpr int N = LabelVec<T>::N;
   constexpr unsigned NONE = 0xffffffffu;
+  // a label outside [0, max_value] has no entry in the rank tables: it counts as background
+  auto key_of = [&](T p, T g) {
+    const int pv = (int)p, gv = (int)g;
+    const unsigned rp = (pv >= 0 && pv <= max_value) ? (unsigned)rank_p[pv] : 0u;
+    const unsigned rg = (gv >= 0 && gv <= max_value) ? (unsigned)rank_g[gv] : 0u;
+    return rp * (unsigned)cols + rg;
+  };
   const int64_t gs = (int64_t)gridDim.x * blockDim.x;
   const unsigned lane = threadIdx.x & 31;
   const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,7 +67,7 @@ contingency_kernel(const T* __restrict__ pred, const T* __restrict__ gt, int64_t
     int count0 = 0;
     if (i < nvec) {
       const LabelVec<T> p = load_labels<T>(pred, i), g = load_labels<T>(gt, i);
-      unsigned key = (unsigned)rank_p[(int)p.v[0]] * (unsigned)cols + (unsigned)rank_g[(int)g.v[0]];
+      unsigned key = key_of(p.v[0], g.v[0]);
       int count = 1;
       bool in_first = true;
       key0 = key;
@@ -73,7 +80,7 @@ contingency_kernel(const T* __restrict__ pred, const T* __restrict__ gt, int64_t
         if (in_first) count0 = count;
         else atomicAdd(table + key, (unsigned)count);
         in_first = false;
-        key = (unsigned)rank_p[(int)p.v[k]] * (unsigned)cols + (unsigned)rank_g[(int)g.v[k]];
+        key = key_of(p.v[k], g.v[k]);
         count = 1;
       }
       if (in_first) count0 = count;
@@ -84,7 +91,7 @@ contingency_kernel(const T* __restrict__ pred, const T* __restrict__ gt, int64_t
     if (key0 != NONE && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(table + key0, (unsigned)total);
   }
   for (int64_t i = nvec * N + first; i < n; i += gs)  // tail
-    atomicAdd(table + (unsigned)rank_p[(int)pred[i]] * (unsigned)cols + (unsigned)rank_g[(int)gt[i]], 1u);
+    atomicAdd(table + key_of(pred[i], gt[i]), 1u);
 }
 
 }  // namespace cb200
@@ -113,8 +120,9 @@ int cb200_label_presence(const void* labels, int dtype, int64_t n, int max_value
 }
 
 int cb200_contingency(const void* pred, const void* gt, int dtype, int64_t n, const int32_t* rank_pred,
-                      const int32_t* rank_gt, int rows, int cols, unsigned int* table, void* stream) {
-  if (!pred || !gt || !rank_pred || !rank_gt || !table || n < 0 || rows <= 0 || cols <= 0) return CB200_EINVAL;
+                      const int32_t* rank_gt, int max_value, int rows, int cols, unsigned int* table, void* stream) {
+  if (!pred || !gt || !rank_pred || !rank_gt || !table || n < 0 || max_value < 0 || rows <= 0 || cols <= 0)
+    return CB200_EINVAL;
   if ((int64_t)rows * cols >= 0xffffffffll) return CB200_EUNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   CB200_CUDA_TRY(cudaMemsetAsync(table, 0, sizeof(unsigned int) * (size_t)rows * cols, st));
@@ -123,11 +131,11 @@ int cb200_contingency(const void* pred, const void* gt, int dtype, int64_t n, co
   if (dtype == CB200_U16) {
     const int64_t nvec = aligned ? n / 8 : 0;
     contingency_kernel<uint16_t><<<grid_for(nvec + 256, 256, 2, 8), 256, 0, st>>>(
-        (const uint16_t*)pred, (const uint16_t*)gt, n, nvec, rank_pred, rank_gt, cols, table);
+        (const uint16_t*)pred, (const uint16_t*)gt, n, nvec, rank_pred, rank_gt, max_value, cols, table);
   } else if (dtype == CB200_I32) {
     const int64_t nvec = aligned ? n / 4 : 0;
     contingency_kernel<int32_t><<<grid_for(nvec + 256, 256, 2, 8), 256, 0, st>>>(
-        (const int32_t*)pred, (const int32_t*)gt, n, nvec, rank_pred, rank_gt, cols, table);
+        (const int32_t*)pred, (const int32_t*)gt, n, nvec, rank_pred, rank_gt, max_value, cols, table);
   } else {
     return CB200_EUNSUPPORTED;
   }

@@ -721,8 +721,10 @@ def contingency(pred: torch.Tensor, gt: torch.Tensor, rank_pred: torch.Tensor, r
     assert pred.dtype == gt.dtype and pred.shape == gt.shape and pred.is_contiguous() and gt.is_contiguous()
     assert rank_pred.dtype == torch.int32 and rank_gt.dtype == torch.int32
     table = torch.empty((rows, cols), dtype=torch.int32, device=pred.device)
+    assert rank_pred.numel() == rank_gt.numel()
     rc = _lib().cb200_contingency(_ptr(pred), _ptr(gt), _code(pred, _LABEL_DTYPES), pred.numel(), _ptr(rank_pred),
-                                  _ptr(rank_gt), int(rows), int(cols), _ptr(table), _stream(pred))
+                                  _ptr(rank_gt), int(rank_pred.numel()) - 1, int(rows), int(cols), _ptr(table),
+                                  _stream(pred))
     check(rc, "cb200_contingency")
     launch_counter["calls"] += 1
     return table

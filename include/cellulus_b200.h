@@ -431,12 +431,13 @@ CB200_API int cb200_nucleus_fill(const int32_t* seg, const void* raw, int raw_dt
  *   cb200_label_presence: present[v] = 1 for every value v in [0, max_value] that occurs in `labels`
  *                         (CB200_U16 or CB200_I32; values outside the range are ignored)
  *   cb200_contingency   : table[rank_pred[pred[i]] * cols + rank_gt[gt[i]]]++ over all pixels; the rank
- *                         tables map a label value to its row / column (0 = background); `table` is zeroed
+ *                         tables (max_value + 1 entries each) map a label value to its row / column
+ *                         (0 = background; values outside [0, max_value] count as background); `table` is zeroed
  *                         by the call.  Intersections are the entries, areas the row / column sums.
  */
 CB200_API int cb200_label_presence(const void* labels, int dtype, int64_t n, int max_value, uint8_t* present, void* stream);
 CB200_API int cb200_contingency(const void* pred, const void* gt, int dtype, int64_t n, const int32_t* rank_pred,
-                      const int32_t* rank_gt, int rows, int cols, unsigned int* table, void* stream);
+                      const int32_t* rank_gt, int max_value, int rows, int cols, unsigned int* table, void* stream);
 
 #ifdef __cplusplus
 }

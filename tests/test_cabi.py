@@ -56,6 +56,29 @@ def test_host_only_entry_points(lib):
     assert lib.cb200_grid_plan(lo, hi, 4, 5.0, 0, ctypes.byref(g)) == _cabi.EINVAL
 
 
+def test_arguments_are_validated_before_any_device_work(lib):
+    """Bad arguments come back as status codes (never exceptions, never a launch): checked here without a GPU."""
+    sp2 = (ctypes.c_int64 * 2)(16, 16)
+    sp4 = (ctypes.c_int64 * 4)(2, 2, 2, 2)
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    info = _cabi.DetectInfo()
+    assert lib.cb200_edt_within(None, 2, sp2, 3.0, p, p, None) == _cabi.EINVAL
+    assert lib.cb200_edt_within(p, 4, sp4, 3.0, p, p, None) == _cabi.EUNSUPPORTED
+    assert lib.cb200_grow_shrink(None, 2, sp2, 3.0, 6.0, p, None) == _cabi.EINVAL
+    assert lib.cb200_label_stats(p, p, _cabi.F32, 1, sp2, 5, p, p, p, p, None) == _cabi.EUNSUPPORTED
+    assert lib.cb200_label_otsu(p, p, p, None, None, _cabi.F64, 3, 10, p, p, None) == _cabi.EINVAL
+    assert lib.cb200_contingency(p, p, _cabi.U16, 10, p, p, -1, 2, 2, p, None) == _cabi.EINVAL
+    assert lib.cb200_detect_volume(p, _cabi.F32, 2, sp2, 0.5, 0.0, 1.0, 0, 300, p, _cabi.I32, None, 0, None, 0,
+                                   ctypes.byref(info), None) == _cabi.EINVAL  # bandwidth must be positive
+    assert lib.cb200_detect_volume(p, _cabi.F32, 4, sp4, 0.5, 3.0, 1.0, 0, 300, p, _cabi.I32, None, 0, None, 0,
+                                   ctypes.byref(info), None) == _cabi.EUNSUPPORTED
+    assert lib.cb200_sample_pairs(p, p, _cabi.F32, 1, 2, sp2, 3.0, 4, 4, 0, 0, None) == _cabi.EUNSUPPORTED
+    assert lib.cb200_error_string(_cabi.ENOFIT) == b"the fit subset is empty"
+    assert lib.cb200_nucleus_fill_workspace_bytes(1000, 7) >= 4 * 1007
+    assert lib.cb200_edt_workspace_bytes(1 << 20) >= 9 << 20
+
+
 def test_sass_is_sm100a_with_bulk_copy():
     """The library holds sm_100a code only, and the n-body kernel really uses the bulk async copy engine."""
     import shutil

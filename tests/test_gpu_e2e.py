@@ -142,7 +142,7 @@ crop_size = [{crop}, {crop}]
 num_infer_iterations = 2
 num_bandwidths = 2
 threshold = 0.02
-reduction_probability = 0.5
+reduction_probability = 1.0
 grow_distance = 1
 shrink_distance = 2
 device = "cuda:0"
@@ -167,6 +167,10 @@ def test_train_then_infer_end_to_end(tmp_path, monkeypatch):
     from cellulus_b200.infer import infer
     from cellulus_b200.train import train
 
+    # The network is barely trained here (3 iterations on random crops), so the foreground it predicts is
+    # arbitrary -- possibly a handful of pixels.  reduction_probability = 1.0 keeps the run free of the
+    # ValueError scikit-learn (and this build) raises when a random fit subset comes out empty.
+    torch.manual_seed(0)
     monkeypatch.chdir(tmp_path)
     g = zarr_lite.open(tmp_path / "data.zarr")
     rng = np.random.default_rng(0)
