@@ -131,3 +131,52 @@ def test_entry_points_refuse_cpu(tmp_path):
     cfg.train_config.device = "cpu"
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         train(cfg)
+
+
+# ---------------------------------------------------------------------------------------------------
+# host-side pieces of the post-processing / evaluation mirrors (pure numpy: no device needed)
+def test_evaluate_host_tail_matches_reference_golden(golden):
+    from cellulus_b200.evaluate import _ranks, compute_F1
+
+    g = golden("evaluate")
+    for case in ("2d", "3d"):
+        F1, TP, FP, FN = compute_F1(g[f"{case}_IoU"])
+        assert np.array_equal(np.array([F1, TP, FP, FN], dtype=np.float64), g[f"{case}_scalars"][2:])
+    present = np.zeros(65536, np.uint8)
+    present[[0, 7, 300, 65535]] = 1
+    ids, rank = _ranks(present)
+    assert ids.tolist() == [7, 300, 65535] and rank[7] == 1 and rank[300] == 2 and rank[65535] == 3 and rank[0] == 0
+    assert rank.dtype == np.int32 and rank.sum() == 6
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_bin_edges_are_numpy_histogram_edges(dtype):
+    from cellulus_b200.segment import _bin_edges
+
+    rng = np.random.default_rng(4)
+    for _ in range(20):
+        values = (rng.random(500) * rng.uniform(0.1, 1e4) + rng.uniform(-50, 50)).astype(dtype)
+        _, edges = np.histogram(values, 256)
+        mine = _bin_edges(float(values.min()), float(values.max()), np.dtype(dtype))
+        assert mine.dtype == edges.dtype and np.array_equal(mine, edges)
+    # the vectorised form used for all instances at once gives the same numbers as one call per instance
+    lo = rng.random(9).astype(dtype)
+    hi = (lo + rng.random(9) + 0.1).astype(dtype)
+    rows = np.linspace(lo, hi, 257, endpoint=True, dtype=dtype, axis=-1)
+    for k in range(9):
+        assert np.array_equal(rows[k], _bin_edges(float(lo[k]), float(hi[k]), np.dtype(dtype)))
+
+
+def test_otsu_tail_of_the_product_equals_the_oracle():
+    from cellulus_b200.detect import otsu_from_centers, otsu_from_histogram
+    from oracle import otsu as ootsu
+
+    rng = np.random.default_rng(9)
+    for dtype in (np.float32, np.float64):
+        img = np.concatenate([rng.normal(0.2, 0.05, 3000), rng.normal(0.8, 0.1, 2000)]).astype(dtype)
+        counts, edges = np.histogram(img, 256)
+        assert otsu_from_histogram(counts, edges) == ootsu.threshold_otsu(img)
+    ints = np.concatenate([rng.integers(5, 60, 4000), rng.integers(140, 250, 1500)]).astype(np.uint16)
+    lo, hi = int(ints.min()), int(ints.max())
+    counts = np.bincount(ints.astype(np.int64) - lo, minlength=hi - lo + 1)
+    assert otsu_from_centers(counts, np.arange(lo, hi + 1)) == ootsu.threshold_otsu(ints)
