@@ -14,15 +14,20 @@ the product path has no CPU fallback.
 Pinning status (see DESIGN.md "Oracle"):
 
 * loss / gather / pair sampler / TTA aggregate / mean-shift segmentation /
-  greedy centre NMS / nearest-mode predict: **pinned** against outputs of the
-  reference itself, executed in the authoring container by
+  greedy centre NMS / nearest-mode predict / greedy clustering / the "cell"
+  post-processing of `segment()` / `compute_pairwise_IoU` + `compute_F1`:
+  **pinned** against outputs of the reference itself, executed in the authoring container by
   `tests/golden/make_golden.py` (imports `/root/reference` with stubs for the
   missing third-party I/O libraries) and committed as `tests/golden/*.npz`.
 * `threshold_otsu`, `measure.label` (scikit-image, unpinned dependency of the
   reference, not installed here, source not under `/root/reference`):
   **parity unpinned** -- restated from the published algorithm; anchored only
   on the reference's call sites (`detect.py:88-94`, `utils/misc.py:11-25`) and
-  on `np.histogram` / `scipy.ndimage.label`, which are present.
+  on `np.histogram` / `scipy.ndimage.label`, which are present.  The "nucleus"
+  post-processing golden was written by the reference's own `segment()` with
+  `threshold_otsu` replaced by this restatement: bounding boxes, hole filling
+  (scipy's `binary_fill_holes`, installed) and write order are pinned, the
+  Otsu values are not.  `peak_local_max` (seed finder): restated, unpinned.
 """
 
 ORACLE_IS_TEST_INFRASTRUCTURE = True
