@@ -427,6 +427,20 @@ def run_b200(args):
     ms_i16 = timed(steps_i16, args.steps, warm)
     del steps_i16
     algo_i16 = B * P * D * 2 * 2 + N_PX * D * 4 * 2
+    # (2d) fused-sampling mode (north_star: "the loss fuses sampling, neighbour gather and the per-pair terms
+    # into one pass"): the pairs are drawn inside the kernel, no coordinate list exists; SURVEY 8d: 31.5 MB
+    def make_sampled(memory_format):
+        return [GraphedLossStep(torch.randn(B, D, *OUT, device=dev).contiguous(memory_format=memory_format), None, None,
+                                TEMP, REGW, sampled=dict(kappa=KAPPA, num_anchors=N_ANCHORS, num_references=N_REFS,
+                                                         seed=4321 + 17 * rank + i, extent_xyz=(OUT[1], OUT[0])))
+                for i in range(N_SETS)]
+
+    steps_s = make_sampled(torch.channels_last)
+    ms_sampled = timed(steps_s, args.steps, warm)
+    steps_s = make_sampled(torch.contiguous_format)
+    ms_sampled_planar = timed(steps_s, args.steps, warm)
+    del steps_s
+    algo_sampled = N_PX * D * 4 * 2
     peak, peak_src = measured_peak_gbs()
     achieved = ALGO_BYTES / (ms_per_step * 1e-3) / 1e9
     achieved_planar = ALGO_BYTES / (ms_planar * 1e-3) / 1e9
@@ -534,6 +548,17 @@ def run_b200(args):
                           "roofline": {"bound": "hbm", "achieved": algo_i16 / (ms_i16 * 1e-3) / 1e9, "peak": peak,
                                        "unit": "GB/s", "frac": algo_i16 / (ms_i16 * 1e-3) / 1e9 / peak,
                                        "algorithmic_bytes_per_launch": algo_i16}},
+            "fused_sampling": {"value": world * N_PX / (ms_sampled * 1e-3), "unit": "px/s", "ms_per_step": ms_sampled,
+                               "pairs_per_s": world * B * P / (ms_sampled * 1e-3),
+                               "planar_ms_per_step": ms_sampled_planar,
+                               "note": "cb200_oce_loss_sampled: pairs drawn inside the kernel (device pair stream), no "
+                                       "coordinate list in HBM; replaces sampler + list kernel of the training step",
+                               "roofline": {"bound": "hbm", "achieved": algo_sampled / (ms_sampled * 1e-3) / 1e9,
+                                            "peak": peak, "unit": "GB/s",
+                                            "frac": algo_sampled / (ms_sampled * 1e-3) / 1e9 / peak,
+                                            "algorithmic_bytes_per_launch": algo_sampled,
+                                            "note": "31.5 MB: at this size the kernel is issue / L2-latency bound "
+                                                    "(SURVEY 8d), the fraction is reported for completeness"}},
             "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_value, "unit": "px/s",
                     "h2d_bytes_per_step": int(h_off.numel() * 4 + h_anc.numel() * 8 + h_ref.numel() * 8),

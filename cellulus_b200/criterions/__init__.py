@@ -1,6 +1,11 @@
 """Loss factory with the reference's call signature (`cellulus/criterions/__init__.py:4-17`)."""
 
-from cellulus_b200.criterions.oce_loss import GraphedLossStep, OCELoss, oce_loss_fused  # noqa: F401
+from cellulus_b200.criterions.oce_loss import (  # noqa: F401
+    GraphedLossStep,
+    OCELoss,
+    oce_loss_fused,
+    oce_loss_fused_sampled,
+)
 
 
 def get_loss(temperature, regularizer_weight, density, num_spatial_dims, device):

@@ -115,6 +115,64 @@ def oce_loss_fused(offsets, anchor_coordinates, reference_coordinates, temperatu
     return loss, oce, reg
 
 
+class _SampledLoss(torch.autograd.Function):
+    """The loss slice on the device pair stream (cb200_oce_loss_sampled): sampling + gather + loss + backward."""
+
+    @staticmethod
+    def forward(ctx, offsets, kappa, num_anchors, num_references, seed, sequence, temperature,
+                regularization_weight, extent_xyz):
+        ctx.set_materialize_grads(False)
+        need = ctx.needs_input_grad[0]
+        out, grad, _ = K.oce_loss_sampled(offsets, kappa, num_anchors, num_references, seed, sequence, temperature,
+                                          regularization_weight, extent_xyz, want_grad=need)
+        ctx.args = (kappa, num_anchors, num_references, seed, sequence, temperature, regularization_weight, extent_xyz)
+        ctx.in_dtype = offsets.dtype
+        ctx.save_for_backward(grad, offsets)
+        ctx.mark_non_differentiable(out)
+        return out[0], out[1], out[2], out
+
+    @staticmethod
+    def backward(ctx, g_loss, g_oce, g_reg, _g_out):
+        grad, offsets = ctx.saved_tensors
+        kappa, na, nr, seed, seq, T, w, ext = ctx.args
+        none = (None,) * 8
+        if grad is None:
+            return (None,) + none
+
+        def recompute(ww):  # the stream is a pure function of (seed, sequence): same pairs again
+            return K.oce_loss_sampled(offsets, kappa, na, nr, seed, seq, T, ww, ext, want_grad=True)[1]
+
+        if g_oce is None and g_reg is None and g_loss is not None:
+            if getattr(ctx, "consumed", False):  # second backward through a retained graph
+                grad = recompute(w)
+            ctx.consumed = True
+            total = K.scale_inplace(grad, g_loss.detach().to(torch.float32).reshape(1).contiguous())
+        else:
+            total = _combine(grad, g_loss, g_oce, g_reg, recompute)
+        return (total.to(ctx.in_dtype),) + none
+
+
+def oce_loss_fused_sampled(offsets, kappa, num_anchors, num_references, seed, sequence, temperature,
+                           regularizer_weight, extent_xyz=None, return_raw: bool = False):
+    """The whole loss slice of a training step INCLUDING the pair sampler, in one kernel:
+
+        anchors, refs = dataset.sample_coordinates()              # zarr_dataset.py:198-242, per sample
+        ea = model.select_and_add_coordinates(offsets, anchors)   # train.py:169-176
+        er = model.select_and_add_coordinates(offsets, refs)
+        loss, oce_loss, regularization_loss = criterion(ea, er)
+
+    The pairs are those of the device pair stream `(seed, sequence)` -- the lists
+    `kernels.sample_pairs(..., seed, sequence)` would write; `oce_loss_fused` fed those lists returns the same
+    values.  No coordinate list ever exists in memory.  `extent_xyz` are the sampling extents in column order
+    (default: the reversed spatial shape of `offsets`)."""
+    loss, oce, reg, raw = _SampledLoss.apply(offsets, float(kappa), int(num_anchors), int(num_references), int(seed),
+                                             int(sequence), float(temperature), float(regularizer_weight),
+                                             None if extent_xyz is None else tuple(int(e) for e in extent_xyz))
+    if return_raw:
+        return loss, oce, reg, raw
+    return loss, oce, reg
+
+
 class GraphedLossStep:
     """One fused loss step (zero-fill + gather + loss + backward) captured in a CUDA graph.
 
@@ -125,10 +183,14 @@ class GraphedLossStep:
     (`d loss / d offsets`, in the memory layout of `offsets`).
     """
 
-    def __init__(self, offsets, anchor_coordinates, reference_coordinates, temperature, regularizer_weight):
+    def __init__(self, offsets, anchor_coordinates, reference_coordinates, temperature, regularizer_weight,
+                 sampled=None):
+        """`sampled`: dict(kappa, num_anchors, num_references, seed[, sequence, extent_xyz]) captures the
+        sampled-loss kernel instead (the coordinate arguments are then None; the stream is fixed per graph)."""
         self.offsets = offsets.detach()
         self.anchors = anchor_coordinates
         self.refs = reference_coordinates
+        self.sampled = sampled
         self.temperature = float(temperature)
         self.regularizer_weight = float(regularizer_weight)
         dev = self.offsets.device
@@ -144,6 +206,12 @@ class GraphedLossStep:
         self.loss, self.oce_loss, self.regularization_loss = self.raw[0], self.raw[1], self.raw[2]
 
     def _run(self):
+        if self.sampled is not None:
+            sp = self.sampled
+            out, grad, _ = K.oce_loss_sampled(self.offsets, sp["kappa"], sp["num_anchors"], sp["num_references"],
+                                              sp["seed"], sp.get("sequence", 0), self.temperature,
+                                              self.regularizer_weight, sp.get("extent_xyz"), want_grad=True)
+            return out, grad
         return K.oce_loss_fwd_bwd(self.offsets, self.anchors, self.refs, self.temperature, self.regularizer_weight,
                                   want_grad=True)
 
@@ -183,6 +251,12 @@ class OCELoss(nn.Module):  # type: ignore
         """(B, P, D) x 2 -> (loss, oce_loss, regularization_loss), all sums (:53-63)."""
         return _PairLoss.apply(anchor_embedding, reference_embedding, float(self.temperature),
                                float(self.regularization_weight))
+
+    def fused_sampled(self, offsets, kappa, num_anchors, num_references, seed, sequence=0, extent_xyz=None,
+                      return_raw=False):
+        """`fused` with the pair sampler inside the kernel (`oce_loss_fused_sampled`)."""
+        return oce_loss_fused_sampled(offsets, kappa, num_anchors, num_references, seed, sequence, self.temperature,
+                                      self.regularization_weight, extent_xyz, return_raw)
 
     def fused(self, offsets, anchor_coordinates, reference_coordinates):
         """The whole loss slice of `train_iteration` in one kernel."""

@@ -17,67 +17,11 @@
 // through warp shuffles, shared memory and one fp64 atomic per block.
 #include <cstdlib>
 
-#include "common.cuh"
+#include "loss_common.cuh"
 #include <cstdio>
 #include <cstdlib>
 
 namespace cb200 {
-
-struct LossWorkspace {
-  double acc[2];            // sum(1 - exp(-d^2/T)), sum(||ea||)
-  unsigned long long bad;   // pairs skipped: coordinate out of range
-  unsigned int ticket;      // blocks finished
-  unsigned int pad;
-};
-
-template <int D>
-struct Shape {
-  int ext[D];      // extent per COLUMN (x, y[, z]) = reversed tensor axes
-  int64_t npix;    // product
-};
-
-template <int D, typename CT>
-__device__ __forceinline__ void load_coord(const CT* __restrict__ base, int64_t pair, int (&c)[D]) {
-  if constexpr (D == 2 && sizeof(CT) == 8) {
-    const longlong2 v = ld_stream_ll2(base + pair * 2);
-    c[0] = (int)v.x;
-    c[1] = (int)v.y;
-  } else if constexpr (D == 2 && sizeof(CT) == 4) {
-    const int2 v = __ldg(reinterpret_cast<const int2*>(base) + pair);
-    c[0] = v.x;
-    c[1] = v.y;
-  } else if constexpr (D == 2 && sizeof(CT) == 2) {
-    const short2 v = __ldg(reinterpret_cast<const short2*>(base) + pair);
-    c[0] = v.x;
-    c[1] = v.y;
-  } else if constexpr (sizeof(CT) == 8) {
-#pragma unroll
-    for (int k = 0; k < D; ++k) c[k] = (int)ld_stream_ll(base + pair * D + k);
-  } else {
-#pragma unroll
-    for (int k = 0; k < D; ++k) c[k] = (int)__ldg(base + pair * D + k);
-  }
-}
-
-// torch advanced indexing wraps negative indices once; anything else is an error
-template <int D>
-__device__ __forceinline__ bool wrap_and_check(const int (&c)[D], int (&wrapped)[D], const Shape<D>& s) {
-  bool ok = true;
-#pragma unroll
-  for (int k = 0; k < D; ++k) {
-    const int v = c[k];
-    const int w = v < 0 ? v + s.ext[k] : v;
-    ok = ok && (w >= 0) && (w < s.ext[k]);
-    wrapped[k] = w;
-  }
-  return ok;
-}
-
-template <int D>
-__device__ __forceinline__ int pixel_of(const int (&c)[D], const Shape<D>& s) {
-  if constexpr (D == 2) return c[1] * s.ext[0] + c[0];
-  return (c[2] * s.ext[1] + c[1]) * s.ext[0] + c[0];
-}
 
 #define CB200_LOSS_UNROLL 1
 #ifndef CB200_LOSS_MIN_BLOCKS
@@ -86,55 +30,6 @@ __device__ __forceinline__ int pixel_of(const int (&c)[D], const Shape<D>& s) {
 constexpr int LOSS_THREADS = 256;
 constexpr int LOSS_UNROLL = CB200_LOSS_UNROLL;
 constexpr int LOSS_MIN_BLOCKS = CB200_LOSS_MIN_BLOCKS;
-
-constexpr int LOSS_MAX_WARPS = 16;
-__device__ __forceinline__ void block_reduce_to_workspace(float oce, float nrm, int bad, LossWorkspace* ws,
-                                                          float w, float* out) {
-  __shared__ double s_acc[2][LOSS_MAX_WARPS];
-  __shared__ int s_bad[LOSS_MAX_WARPS];
-  __shared__ bool s_last;
-  double a = warp_sum((double)oce), b = warp_sum((double)nrm);
-  int c = warp_sum(bad);
-  const int warp = threadIdx.x >> 5;
-  if (lane_id() == 0) {
-    s_acc[0][warp] = a;
-    s_acc[1][warp] = b;
-    s_bad[warp] = c;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double ta = 0, tb = 0;
-    int tc = 0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
-      ta += s_acc[0][i];
-      tb += s_acc[1][i];
-      tc += s_bad[i];
-    }
-    atomicAdd(&ws->acc[0], ta);
-    atomicAdd(&ws->acc[1], tb);
-    if (tc) atomicAdd(&ws->bad, (unsigned long long)tc);
-    __threadfence();
-    const unsigned t = atomicAdd(&ws->ticket, 1u);
-    s_last = (t == gridDim.x * gridDim.y - 1);
-  }
-  __syncthreads();
-  if (s_last && threadIdx.x == 0) {
-    __threadfence();
-    const double oce_sum = atomicAdd(&ws->acc[0], 0.0);
-    const double nrm_sum = atomicAdd(&ws->acc[1], 0.0);
-    const unsigned long long nbad = atomicAdd(&ws->bad, 0ull);
-    const float oce_f = (float)oce_sum;
-    const float reg_f = w * (float)nrm_sum;  // criterions/oce_loss.py:59-61
-    out[0] = oce_f + reg_f;                  // :62
-    out[1] = oce_f;
-    out[2] = reg_f;
-    out[3] = (float)nbad;
-    ws->acc[0] = 0.0;  // leave the workspace zeroed for the next call
-    ws->acc[1] = 0.0;
-    ws->bad = 0ull;
-    ws->ticket = 0u;
-  }
-}
 
 // ---- raw coordinate registers: what the load returns, converted only at first use, so that the
 // software prefetch of the NEXT iteration's coordinates never stalls on its own loads ----------
@@ -174,61 +69,6 @@ struct RawCoord<3, CT> {
   __device__ __forceinline__ void zero() { v[0] = v[1] = v[2] = 0; }
   __device__ __forceinline__ int get(int k) const { return (int)v[k]; }
 };
-
-__device__ __forceinline__ float ex2_approx(float x) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float rsqrt_approx(float x) {
-  float r;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-
-// pixel gather: PLANAR = (B, D, *S) contiguous; interleaved = channels-last (B, *S, D) contiguous.
-// `first` = index of the sample's first pixel in the whole tensor (b * npix); all element indices are 32-bit
-// (the launcher refuses tensors of 2^31 elements or more), so one address costs one IMAD.WIDE on the
-// kernel-parameter base instead of a rebuilt 64-bit per-sample pointer.
-template <int D, typename OT, bool IL>
-__device__ __forceinline__ void gather_pixel(const OT* __restrict__ base, unsigned npix, unsigned first, unsigned pix,
-                                             float (&o)[D]) {
-  if constexpr (!IL) {
-    const unsigned e = first * D + pix;
-#pragma unroll
-    for (int k = 0; k < D; ++k) o[k] = load_as_float<OT>(base, e + k * npix);
-  } else if constexpr (D == 2 && sizeof(OT) == 4) {
-    const float2 v = __ldg(reinterpret_cast<const float2*>(base) + (first + pix));
-    o[0] = v.x;
-    o[1] = v.y;
-  } else if constexpr (D == 2 && sizeof(OT) == 2) {
-    const __nv_bfloat162 v = __ldg(reinterpret_cast<const __nv_bfloat162*>(base) + (first + pix));
-    o[0] = __low2float(v);
-    o[1] = __high2float(v);
-  } else {
-    const unsigned e = (first + pix) * D;
-#pragma unroll
-    for (int k = 0; k < D; ++k) o[k] = load_as_float<OT>(base, e + k);
-  }
-}
-
-template <int D, bool IL>
-__device__ __forceinline__ void scatter_pixel(float* __restrict__ gbase, unsigned npix, unsigned first, unsigned pix,
-                                              const float (&g)[D]) {
-  if constexpr (!IL) {
-    const unsigned e = first * D + pix;
-#pragma unroll
-    for (int k = 0; k < D; ++k) atomicAdd(gbase + (e + k * npix), g[k]);
-  } else if constexpr (D == 2) {
-    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(reinterpret_cast<float2*>(gbase) + (first + pix)),
-                 "f"(g[0]), "f"(g[1])
-                 : "memory");
-  } else {
-    const unsigned e = (first + pix) * D;
-#pragma unroll
-    for (int k = 0; k < D; ++k) atomicAdd(gbase + (e + k), g[k]);
-  }
-}
 
 // ---- one chunk = 32 consecutive pairs of one sample, one pair per lane -----------------------------
 template <int D>
@@ -396,7 +236,7 @@ __global__ void __launch_bounds__(256) zero_fill_kernel(float4* __restrict__ p, 
   for (; i < n4; i += stride) p[i] = z;
   if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) tail[threadIdx.x] = 0.f;
 }
-static int zero_fill(float* p, int64_t n, cudaStream_t st) {
+int zero_fill(float* p, int64_t n, cudaStream_t st) {
   if (n <= 0) return CB200_OK;
   if (reinterpret_cast<uintptr_t>(p) & 15) {
     CB200_CUDA_TRY(cudaMemsetAsync(p, 0, sizeof(float) * (size_t)n, st));
@@ -526,22 +366,8 @@ pair_loss_kernel(const float* __restrict__ ea_p, const float* __restrict__ er_p,
   block_reduce_to_workspace(acc_oce, acc_nrm, 0, ws, w, out);
 }
 
-template <int D>
-static bool make_shape(const int64_t* spatial, Shape<D>& s) {
-  int64_t npix = 1;
-  for (int k = 0; k < D; ++k) {
-    const int64_t e = spatial[D - 1 - k];  // column k = tensor axis D-1-k
-    if (e <= 0 || e > INT32_MAX) return false;
-    s.ext[k] = (int)e;
-    npix *= e;
-  }
-  if (npix * D > INT32_MAX) return false;  // element offsets are 32-bit per sample
-  s.npix = npix;
-  return true;
-}
-
 // programmatic dependent launch of the fused kernel behind the zero-fill (A/B switch: CB200_LOSS_PDL=0)
-static const bool g_loss_pdl = [] {
+const bool g_loss_pdl = [] {
   const char* e = getenv("CB200_LOSS_PDL");
   return !(e && e[0] == '0');
 }();

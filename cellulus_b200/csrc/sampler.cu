@@ -1,112 +1,75 @@
-// Device pair sampler for sm_100a -- the B200-native counterpart of
-// ZarrDataset.sample_coordinates / sample_offsets_within_radius
-// (datasets/zarr_dataset.py:177-251).  Counter-based Philox4x32-10: every pair
-// derives its anchor from (sample, anchor index) and its offset from the pair
-// index, so no state is shared and the lists never exist on the host.
+// Device pair sampler for sm_100a: writes the pair stream of pair_stream.cuh out as coordinate lists -- the
+// B200-native counterpart of ZarrDataset.sample_coordinates / sample_offsets_within_radius
+// (datasets/zarr_dataset.py:177-251) for callers that want the lists (the fused kernel of oce_sampled.cu
+// consumes the same stream without them).
 //
 // Distribution (identical to the reference's):
 //   anchor column k ~ U{trunc(kappa) .. extent_k - trunc(kappa)}  (np.random.randint(kappa, out-kappa+1))
 //   offset ~ uniform over integer o in [-trunc(kappa), trunc(kappa)]^D with sum o^2 < kappa^2, o != 0
-//            (rejection sampling = what `in_circle` / `not_zero` filtering of i.i.d. draws yields)
+//            (what `in_circle` / `not_zero` filtering of i.i.d. draws yields), drawn by ONE bounded index into
+//            the table of admissible offsets -- no rejection loop, one Philox block per four pairs
 //   each anchor repeated num_references times consecutively (np.repeat, :236)
-#include "common.cuh"
+#include "pair_stream.cuh"
 
 namespace cb200 {
 
-// one pair's coordinates as a single store where the type allows it
-template <int D, typename CT>
-__device__ __forceinline__ void store_coord(CT* __restrict__ base, size_t pair, const int (&c)[D]) {
-  if constexpr (D == 2 && sizeof(CT) == 8) {
-    reinterpret_cast<longlong2*>(base)[pair] = make_longlong2(c[0], c[1]);
-  } else if constexpr (D == 2 && sizeof(CT) == 4) {
-    reinterpret_cast<int2*>(base)[pair] = make_int2(c[0], c[1]);
-  } else if constexpr (D == 2 && sizeof(CT) == 2) {
-    reinterpret_cast<short2*>(base)[pair] = make_short2((short)c[0], (short)c[1]);
-  } else {
-#pragma unroll
-    for (int k = 0; k < D; ++k) base[pair * D + k] = (CT)c[k];
-  }
-}
-
-// The kernel is issue-bound (Philox rounds and the rejection loop run once per WARP until its slowest lane
-// accepts), so: index arithmetic in 32 bits whenever the pair count allows (IT = unsigned), every Philox block
-// of the offset stream serves as many attempts as it has words for (two in 2-D), one vector store per pair.
+// One thread per pair, coalesced vector stores.  The four pairs that share an offset block recompute it (the
+// kernel writes 8 - 32 bytes per pair and is bound by those stores once the rejection loop is gone).
 template <int D, typename CT, typename IT>
 __global__ void __launch_bounds__(256)
-sample_pairs_kernel(CT* __restrict__ anchors, CT* __restrict__ refs, int batch, IT num_anchors, IT num_refs,
-                    int lo, int ext0, int ext1, int ext2, int kap, double kappa2, uint64_t seed, uint64_t sequence) {
-  const Philox rng(seed);
-  const IT P = num_anchors * num_refs;
-  const IT total = (IT)batch * P;
+sample_pairs_kernel(CT* __restrict__ anchors, CT* __restrict__ refs, PairStreamParams p) {
+  extern __shared__ uint32_t s_table[];
+  build_offset_table<D>(s_table, p);
+  const Philox rng(p.seed);
+  const unsigned b = blockIdx.y;  // one grid row per sample: pair indices inside a sample fit IT
+  const IT P = (IT)p.num_anchors * p.num_refs;
   const IT gs = (IT)gridDim.x * blockDim.x;
-  const int ext[3] = {ext0, ext1, ext2};
-  const int k2 = (int)ceil(kappa2) - 1;  // integer s2 < kappa^2  <=>  s2 <= ceil(kappa^2) - 1
-  constexpr int ATTEMPTS = 4 / D;        // attempts served by one 4-word Philox block
-  for (IT g = (IT)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gs) {
-    const IT b = g / P;
-    const IT a = (g - b * P) / num_refs;
-    // anchor: one Philox block per (sample, anchor)
-    const uint4 ra = rng((uint64_t)b * (uint64_t)num_anchors + (uint64_t)a, sequence * 2);
-    const uint32_t rr[4] = {ra.x, ra.y, ra.z, ra.w};
-    int anc[D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-      const int span = ext[k] - 2 * lo + 1;  // inclusive range [lo, ext - lo]
-      anc[k] = lo + (int)bounded(rr[k], (uint32_t)span);
-    }
-    // offset: rejection sampling over the words of successive Philox blocks
-    int off[D];
-    bool accepted = false;
-    for (uint32_t block = 0; !accepted; ++block) {
-      const uint4 ro = rng((uint64_t)g, sequence * 2 + 1 + ((uint64_t)block << 32));
-      const uint32_t r4[4] = {ro.x, ro.y, ro.z, ro.w};
-#pragma unroll
-      for (int t = 0; t < ATTEMPTS; ++t) {
-        int cand[D], s2 = 0, s1 = 0;
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-          cand[k] = (int)bounded(r4[t * D + k], (uint32_t)(2 * kap + 1)) - kap;
-          s2 += cand[k] * cand[k];
-          s1 |= cand[k];
-        }
-        if (!accepted && s2 <= k2 && s1 != 0) {
-          accepted = true;
-#pragma unroll
-          for (int k = 0; k < D; ++k) off[k] = cand[k];
-        }
-      }
-    }
-    int ref[D];
+  for (IT q = (IT)blockIdx.x * blockDim.x + threadIdx.x; q < P; q += gs) {
+    const unsigned a = (unsigned)(q / p.num_refs);
+    const unsigned t = (unsigned)(q - (IT)a * p.num_refs);
+    int anc[D], off[D], ref[D];
+    stream_anchor<D>(rng, p, b, a, anc);
+    const uint4 ro = stream_offset_block(rng, p, b, a, t >> 2);
+    stream_offset<D>(s_table, p, pick_word(ro, t & 3), off);
 #pragma unroll
     for (int k = 0; k < D; ++k) ref[k] = anc[k] + off[k];
-    store_coord<D, CT>(anchors, (size_t)g, anc);
-    store_coord<D, CT>(refs, (size_t)g, ref);
+    const size_t g = (size_t)b * (size_t)P + (size_t)q;
+    store_coord<D, CT>(anchors, g, anc);
+    store_coord<D, CT>(refs, g, ref);
   }
 }
 
 template <int D, typename CT>
 static int launch_sampler(void* anchors, void* refs, int batch, const int64_t* extent, double kappa,
                           int64_t num_anchors, int num_refs, uint64_t seed, uint64_t sequence, cudaStream_t st) {
-  const int kap = (int)kappa;  // numpy truncates the float bounds
-  int ext[3] = {1, 1, 1};
-  for (int k = 0; k < D; ++k) {
-    if (extent[k] - 2 * (int64_t)kap + 1 <= 0 || extent[k] > INT32_MAX) return CB200_EINVAL;
-    ext[k] = (int)extent[k];
-  }
-  if (kap < 1 || !(kappa * kappa > 1.0)) return CB200_EINVAL;  // the ball must contain a non-zero offset
+  PairStreamParams p;
+  if (!pair_stream_plan(p, D, extent, kappa, num_anchors, num_refs)) return CB200_EINVAL;
+  const size_t table_bytes = (size_t)p.n_table * sizeof(uint32_t);
+  if (table_bytes > PAIR_TABLE_MAX_BYTES) return CB200_EUNSUPPORTED;
+  p.seed = seed;
+  p.sequence = sequence;
   const int64_t total = (int64_t)batch * num_anchors * num_refs;
   if (total == 0) return CB200_OK;
   const bool aligned = (reinterpret_cast<uintptr_t>(anchors) | reinterpret_cast<uintptr_t>(refs)) % (2 * sizeof(CT)) == 0;
   if (D == 2 && !aligned) return CB200_EINVAL;  // vector stores of (x, y)
-  const int blocks = grid_for(total, 256, 2, 16);
-  if (total < ((int64_t)1 << 31))
-    sample_pairs_kernel<D, CT, unsigned><<<blocks, 256, 0, st>>>(
-        (CT*)anchors, (CT*)refs, batch, (unsigned)num_anchors, (unsigned)num_refs, kap, ext[0], ext[1], ext[2], kap,
-        kappa * kappa, seed, sequence);
-  else
-    sample_pairs_kernel<D, CT, unsigned long long><<<blocks, 256, 0, st>>>(
-        (CT*)anchors, (CT*)refs, batch, (unsigned long long)num_anchors, (unsigned long long)num_refs, kap, ext[0],
-        ext[1], ext[2], kap, kappa * kappa, seed, sequence);
+  if (batch > 65535) return CB200_EUNSUPPORTED;
+  const int64_t P = num_anchors * (int64_t)num_refs;
+  // every block builds the table once: few, long-lived blocks, about one wave of them over the batch
+  int blocks = grid_for(P, 256, 8, 8);
+  const int per_sample_cap = (CB200_SM_COUNT * 8 + batch - 1) / batch;
+  if (blocks > per_sample_cap) blocks = per_sample_cap;
+  const dim3 grid((unsigned)blocks, (unsigned)batch);
+  if (P < ((int64_t)1 << 32)) {
+    auto kernel = sample_pairs_kernel<D, CT, unsigned>;
+    if (table_bytes > 48 * 1024)
+      CB200_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
+    kernel<<<grid, 256, table_bytes, st>>>((CT*)anchors, (CT*)refs, p);
+  } else {
+    auto kernel = sample_pairs_kernel<D, CT, unsigned long long>;
+    if (table_bytes > 48 * 1024)
+      CB200_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
+    kernel<<<grid, 256, table_bytes, st>>>((CT*)anchors, (CT*)refs, p);
+  }
   CB200_LAUNCH_CHECK();
   return CB200_OK;
 }

@@ -16,6 +16,7 @@ import os
 from cellulus_b200 import kernels as K
 from cellulus_b200 import sharding, zarr_lite
 from cellulus_b200.utils import mean_shift as MS
+from cellulus_b200.utils.device import resolve_device
 
 
 def otsu_from_histogram(counts: np.ndarray, edges: np.ndarray):
@@ -88,10 +89,7 @@ def detect(inference_config) -> None:
     meta = DatasetMetaData.from_dataset_config(inference_config.dataset_config)
     nd = meta.num_spatial_dims
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    device = torch.device(inference_config.device)
-    if world > 1:
-        device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-    torch.cuda.set_device(device)
+    device = resolve_device(inference_config.device, "detect")
     cfg = inference_config.detection_dataset_config
     f = zarr_lite.open(cfg.container_path)
     ds = f[cfg.secondary_dataset_name]

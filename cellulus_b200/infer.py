@@ -32,14 +32,12 @@ def _derive_defaults(inference_config, object_size: float, num_spatial_dims: int
 
 def _device(inference_config) -> torch.device:
     """The configured CUDA device, or this rank's GPU under torchrun (one process per GPU, NCCL)."""
-    device = torch.device(inference_config.device)
-    if device.type != "cuda" or not torch.cuda.is_available():
-        raise RuntimeError(f"infer: device={device!s} -- cellulus_b200 has no CPU fallback; use a CUDA device")
+    from cellulus_b200.utils.device import resolve_device
+
+    device = resolve_device(inference_config.device, "infer")
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         import torch.distributed as dist
 
-        device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-        torch.cuda.set_device(device)
         if not dist.is_initialized():
             dist.init_process_group("nccl", device_id=device)
     return device

@@ -202,6 +202,40 @@ def sample_pairs(batch, extent_xyz, kappa, num_anchors, num_references, seed, se
     return anchors, refs
 
 
+def oce_loss_sampled(offsets, kappa, num_anchors, num_references, seed, sequence, temperature,
+                     regularization_weight, extent_xyz=None, want_grad=True, dump_dtype=None):
+    """`cb200_oce_loss_sampled`: the loss on the pair stream (seed, sequence), pairs drawn inside the kernel.
+    Returns `(out4, grad, (anchors, refs) | None)`; the lists are only written when `dump_dtype` is given."""
+    _require_cuda(offsets)
+    if offsets.ndim not in (4, 5) or offsets.shape[1] != offsets.ndim - 2:
+        raise ValueError("offsets must be (B, D, *S) with one offset channel per spatial dim")
+    B, D = offsets.shape[0], offsets.ndim - 2
+    offsets, layout = _offsets_layout(offsets)
+    spatial = tuple(offsets.shape[2:])
+    if extent_xyz is None:
+        extent_xyz = spatial[::-1]
+    if len(extent_xyz) != D:
+        raise ValueError(f"extent_xyz must have {D} entries (x, y[, z])")
+    odt = _code(offsets, _OFFSET_DTYPES)
+    out = torch.empty(4, dtype=torch.float32, device=offsets.device)
+    grad = torch.empty_like(offsets, dtype=torch.float32) if want_grad else None
+    ws = _zero_workspace("loss", _lib().cb200_oce_loss_workspace_bytes(), offsets.device)
+    lists, ddt = None, 0
+    if dump_dtype is not None:
+        P = int(num_anchors) * int(num_references)
+        lists = (torch.empty((B, P, D), dtype=dump_dtype, device=offsets.device),
+                 torch.empty((B, P, D), dtype=dump_dtype, device=offsets.device))
+        ddt = _code(lists[0], _COORD_DTYPES)
+    rc = _lib().cb200_oce_loss_sampled(
+        _ptr(offsets), odt, layout, B, D, spatial_array(spatial), spatial_array(extent_xyz), float(kappa),
+        int(num_anchors), int(num_references), int(seed) & (2**64 - 1), int(sequence), float(temperature),
+        float(regularization_weight), _ptr(grad), _ptr(out), _ptr(ws), _ptr(lists[0] if lists else None),
+        _ptr(lists[1] if lists else None), ddt, _stream(offsets))
+    check(rc, "cb200_oce_loss_sampled")
+    launch_counter["calls"] += 1
+    return out, grad, lists
+
+
 # --------------------------------------------------------------------------- TTA
 def tta_aggregate(stack: torch.Tensor) -> torch.Tensor:
     """(T, C, *S) fp32 -> (C+1, *S) fp32 (`models/unet.py:90-98`)."""

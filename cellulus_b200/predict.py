@@ -15,6 +15,7 @@ import os
 import numpy as np
 import torch
 
+from cellulus_b200.utils.device import resolve_device
 from cellulus_b200 import sharding, zarr_lite
 from cellulus_b200.datasets.meta_data import DatasetMetaData
 
@@ -28,12 +29,9 @@ def _normalize(data: np.ndarray, factor):
 def predict(model: torch.nn.Module, inference_config, normalization_factor) -> None:
     dataset_config = inference_config.dataset_config
     meta = DatasetMetaData.from_dataset_config(dataset_config)
-    device = torch.device(inference_config.device)
+    device = resolve_device(inference_config.device, "predict")
     nd = meta.num_spatial_dims
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1:
-        device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-    torch.cuda.set_device(device)
     model.set_infer(p_salt_pepper=inference_config.p_salt_pepper,
                     num_infer_iterations=inference_config.num_infer_iterations, device=device)
     crop = tuple(inference_config.crop_size)

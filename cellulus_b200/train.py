@@ -23,30 +23,22 @@ from cellulus_b200 import zarr_lite
 from cellulus_b200.criterions import get_loss
 from cellulus_b200.datasets import get_dataset
 from cellulus_b200.models import get_model
+from cellulus_b200.utils.device import resolve_device
 from cellulus_b200.utils.logger import get_logger
 
 torch.backends.cudnn.benchmark = True
 
 
-def _require_cuda(device: torch.device, what: str):
-    if device.type != "cuda" or not torch.cuda.is_available():
-        raise RuntimeError(
-            f"{what}: device={device!s} -- cellulus_b200 runs its loss / detection kernels on a CUDA device only "
-            "(there is no CPU fallback); set `device = \"cuda:0\"` in the config")
-
-
-def _join_ranks(device: torch.device):
-    """(device, rank, world): under torchrun every rank takes its local GPU and joins the NCCL group."""
+def _join_ranks(spec):
+    """(device, rank, world): the configured device with its index resolved (`"cuda"` -> current device); under
+    torchrun every rank takes its local GPU and joins the NCCL group."""
+    device = resolve_device(spec, "train")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
         import torch.distributed as dist
 
-        device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-        torch.cuda.set_device(device)
         if not dist.is_initialized():
             dist.init_process_group("nccl", device_id=device)
-    else:
-        torch.cuda.set_device(device)
     return device, int(os.environ.get("RANK", "0")), world
 
 
@@ -77,9 +69,7 @@ def train(experiment_config):
     print(experiment_config)
     cfg = experiment_config.train_config
     model_config = experiment_config.model_config
-    device = torch.device(cfg.device)
-    _require_cuda(device, "train")
-    device, rank, world = _join_ranks(device)
+    device, rank, world = _join_ranks(cfg.device)
     main = rank == 0
     if main:
         os.makedirs("models", exist_ok=True)

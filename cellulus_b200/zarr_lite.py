@@ -108,7 +108,12 @@ class Array:
     def _write_chunk(self, idx, data):
         raw = np.ascontiguousarray(data, dtype=self.dtype).tobytes()
         if self._comp is not None:
-            raw = zlib.compress(raw, int(self._comp.get("level", 1)))
+            level = int(self._comp.get("level", 1))
+            if self._comp.get("id") == "gzip":  # numcodecs GZip.decode needs a gzip container, not a bare zlib stream
+                co = zlib.compressobj(level, zlib.DEFLATED, 31)
+                raw = co.compress(raw) + co.flush()
+            else:
+                raw = zlib.compress(raw, level)
         with _fopen(self._chunk_path(idx), "wb") as fh:
             fh.write(raw)
 

@@ -129,14 +129,40 @@ CB200_API int cb200_oce_pair_loss(const float* ea, const float* er, int64_t n_pa
  * (datasets/zarr_dataset.py:177-251): anchors uniform in [kappa, extent-kappa]
  * per column, each repeated num_references times consecutively; offsets
  * uniform over the integer points of the open ball sum o^2 < kappa^2 minus
- * the origin.  Same distribution as the reference, different RNG stream.
+ * the origin (one bounded index into the table of admissible offsets -- the
+ * distribution the reference's rejection filter produces).  Same distribution
+ * as the reference, a counter-based stream instead of numpy's global generator;
+ * the stream is specified in csrc/pair_stream.cuh and restated in numpy in
+ * oracle/device_sampler.py.
  *  extent       host, num_dims ints in COLUMN order (x, y[, z]) -- the
  *               reference draws column d from output_shape[d] (quirk Q4)
  *  anchors/refs (B, num_anchors*num_references, D), CB200_I64 / I32 / I16
+ *  kappa        trunc(kappa) <= 127 and the offset table must fit in shared memory
+ *               (kappa <= 120 in 2-D, <= 21 in 3-D), else CB200_EUNSUPPORTED
  */
 CB200_API int cb200_sample_pairs(void* anchors, void* refs, int coord_dtype, int batch, int num_dims,
                        const int64_t* extent, double kappa, int64_t num_anchors, int num_references,
                        uint64_t seed, uint64_t sequence, void* stream);
+
+/*
+ * The loss slice with the sampling INSIDE the kernel: draws the pairs of the stream (seed, sequence) --
+ * exactly the lists cb200_sample_pairs would write -- gathers, evaluates OCELoss forward + backward and
+ * never materialises a coordinate list.  Replaces, per training step, the DataLoader-side sampler
+ * (datasets/zarr_dataset.py:198-242), its two host->device list copies (train.py:162-166) and
+ * train.py:169-178.  One lane owns one anchor: its num_references pairs accumulate their gradient in
+ * registers and issue a single reduction.  HBM traffic = offsets once + gradient once.
+ *  offsets/grad/out/workspace  as for cb200_oce_loss_fwd_bwd
+ *  spatial      host, tensor-axis order ([z,] y, x);  extent: host, sampling extents in COLUMN order
+ *               (normally the reversed `spatial`; the reference's quirk Q4 feeds output_shape unreversed).
+ *               Pairs that fall outside the tensor are skipped and counted in out[3].
+ *  dump_anchors/dump_refs  optional (both or neither): (B, num_anchors*num_references, D) lists of
+ *               dump_dtype (CB200_I64 / I32 / I16) receiving the pairs this call used (test / debug)
+ */
+CB200_API int cb200_oce_loss_sampled(const void* offsets, int offsets_dtype, int offsets_layout, int batch, int num_dims,
+                           const int64_t* spatial, const int64_t* extent, double kappa, int64_t num_anchors,
+                           int num_references, uint64_t seed, uint64_t sequence, float temperature,
+                           float regularization_weight, float* grad, float* out, void* workspace,
+                           void* dump_anchors, void* dump_refs, int dump_dtype, void* stream);
 
 /* ===================================================================== *
  *  Detect slice (inference)                                             *

@@ -303,6 +303,145 @@ def test_device_sampler_distribution():
         assert np.array_equal(a2.cpu().numpy(), a) and not np.array_equal(a3.cpu().numpy(), a)
 
 
+@pytest.mark.parametrize("nd,ext,kappa,na,nr,dtype,seq", [
+    (2, (236, 236), 10.0, 700, 31, torch.int64, 0), (2, (90, 120), 6.5, 333, 7, torch.int16, 3),
+    (3, (64, 48, 40), 5.0, 500, 31, torch.int32, 1), (3, (40, 40, 40), 3.0, 64, 1, torch.int64, 2 ** 33 + 5)])
+def test_device_sampler_bit_exact_to_stream_oracle(nd, ext, kappa, na, nr, dtype, seq):
+    """`cb200_sample_pairs` writes exactly the pairs the numpy restatement of the device stream names
+    (oracle/device_sampler.py: Philox4x32-10 checked against the Random123 known answers on the CPU side)."""
+    from oracle import device_sampler as ods
+
+    B, seed = 3, 0x1234_5678_9ABC_DEF0
+    a, r = K.sample_pairs(B, ext, kappa, na, nr, seed=seed, sequence=seq, device=_dev(), dtype=dtype)
+    a_ref, r_ref = ods.sample_pairs(B, ext, kappa, na, nr, seed, seq)
+    assert np.array_equal(a.cpu().numpy().astype(np.int64), a_ref)
+    assert np.array_equal(r.cpu().numpy().astype(np.int64), r_ref)
+
+
+@pytest.mark.parametrize("nd,layout,odt", [(2, "planar", torch.float32), (2, "cl", torch.float32),
+                                           (2, "cl", torch.bfloat16), (3, "planar", torch.float32),
+                                           (3, "cl", torch.float32)])
+def test_sampled_loss_matches_oracle_on_its_own_pairs(nd, layout, odt):
+    """Fused-sampling mode: the pairs the kernel drew (dump mode) are the stream oracle's, and loss + gradient
+    equal the reference arithmetic (oracle.oce_loss) on exactly those pairs, and the explicit-list kernel."""
+    from cellulus_b200.criterions import oce_loss_fused, oce_loss_fused_sampled
+    from oracle import device_sampler as ods
+
+    dev = _dev()
+    if nd == 2:
+        S, kappa, na, nr, B = (70, 90), 10.0, 1003, 31, 3  # na not a multiple of 32, nr not of 4
+    else:
+        S, kappa, na, nr, B = (24, 30, 36), 4.0, 777, 13, 2
+    ext = S[::-1]
+    seed, seq, T, w = 99, 4, 10.0, 1e-3
+    offsets = torch.from_numpy(synthetic.loss_offsets(B, nd, S, seed=3)).to(odt)
+    fmt = torch.contiguous_format if layout == "planar" else (torch.channels_last if nd == 2 else torch.channels_last_3d)
+    off_d = offsets.to(dev).contiguous(memory_format=fmt)
+    out, grad, lists = K.oce_loss_sampled(off_d, kappa, na, nr, seed, seq, T, w, dump_dtype=torch.int64)
+    a_ref, r_ref = ods.sample_pairs(B, ext, kappa, na, nr, seed, seq)
+    assert np.array_equal(lists[0].cpu().numpy(), a_ref) and np.array_equal(lists[1].cpu().numpy(), r_ref)
+    l_ref, o_ref, g_reg, g_ref = oloss.loss_step(offsets.float(), torch.from_numpy(a_ref), torch.from_numpy(r_ref), T, w)
+    assert abs(out[0].item() - l_ref.item()) <= LOSS_RTOL * abs(l_ref.item())
+    assert abs(out[1].item() - o_ref.item()) <= LOSS_RTOL * abs(o_ref.item())
+    assert abs(out[2].item() - g_reg.item()) <= LOSS_RTOL * abs(g_reg.item())
+    assert out[3].item() == 0
+    assert _rel(grad.cpu().numpy(), g_ref.numpy()) <= LOSS_RTOL
+    # without the dump (the production variant), through autograd, vs the explicit-list kernel on the same lists
+    o1 = off_d.clone().requires_grad_(True)
+    loss, oce, reg = oce_loss_fused_sampled(o1, kappa, na, nr, seed, seq, T, w)
+    (3.0 * loss).backward()
+    o2 = off_d.clone().requires_grad_(True)
+    loss2, _, _ = oce_loss_fused(o2, lists[0], lists[1], T, w)
+    (3.0 * loss2).backward()
+    assert abs(loss.item() - loss2.item()) <= LOSS_RTOL * abs(loss2.item())
+    tol = LOSS_RTOL if odt == torch.float32 else 2 ** -7
+    assert _rel(o1.grad.float().cpu().numpy(), o2.grad.float().cpu().numpy()) <= tol
+    assert o1.grad.dtype == odt and o1.grad.is_contiguous(memory_format=fmt)
+
+
+def test_sampled_loss_edges_and_autograd():
+    from cellulus_b200.criterions import oce_loss_fused_sampled
+    from oracle import device_sampler as ods
+
+    dev = _dev()
+    S = (40, 52)
+    offsets = torch.from_numpy(synthetic.loss_offsets(2, 2, S, seed=8))
+    # nothing to draw -> zero loss, zero gradient
+    for na, nr in [(0, 31), (5, 0)]:
+        o = offsets.to(dev).requires_grad_(True)
+        loss, _, _ = oce_loss_fused_sampled(o, 10.0, na, nr, 1, 0, 10.0, 1e-5)
+        loss.backward()
+        assert loss.item() == 0.0 and o.grad.abs().max().item() == 0.0
+    # sampling extents that exceed the tensor (the reference's quirk Q4 on a non-square crop): pairs outside
+    # the tensor are skipped and counted, the rest equals the oracle on the in-range pairs
+    ext = (S[0] + 12, S[1])  # x drawn from a wider range than the tensor has
+    out, grad, lists = K.oce_loss_sampled(offsets.to(dev), 10.0, 400, 31, 5, 0, 10.0, 1e-2, extent_xyz=ext,
+                                          dump_dtype=torch.int32)
+    a, r = lists[0].cpu().numpy().astype(np.int64), lists[1].cpu().numpy().astype(np.int64)
+    a_ref, r_ref = ods.sample_pairs(2, ext, 10.0, 400, 31, 5, 0)
+    assert np.array_equal(a, a_ref) and np.array_equal(r, r_ref)
+    lim = np.array(S[::-1])
+    inside = ((a >= 0) & (a < lim) & (r >= 0) & (r < lim)).all(-1)
+    assert out[3].item() == float((~inside).sum()) and (~inside).sum() > 0
+    l_tot, g_tot = 0.0, torch.zeros_like(offsets)
+    for b in range(2):
+        sel = inside[b]
+        l, _, _, g = oloss.loss_step(offsets[b:b + 1], torch.from_numpy(a[b][sel])[None], torch.from_numpy(r[b][sel])[None],
+                                     10.0, 1e-2)
+        l_tot += l.item()
+        g_tot[b] = g[0]
+    assert abs(out[0].item() - l_tot) <= LOSS_RTOL * abs(l_tot)
+    assert _rel(grad.cpu().numpy(), g_tot.numpy()) <= LOSS_RTOL
+    # autograd: separate terms, a weighted mix, a second backward through a retained graph
+    a_ref, r_ref = ods.sample_pairs(2, S[::-1], 10.0, 300, 31, 11, 2)
+
+    def oracle_grad(wl, wo, wr):
+        o = offsets.clone().requires_grad_(True)
+        ea = oloss.select_and_add_coordinates(o, torch.from_numpy(a_ref))
+        er = oloss.select_and_add_coordinates(o, torch.from_numpy(r_ref))
+        loss, oce, reg = oloss.oce_loss(ea, er, 10.0, 1e-2)
+        (wl * loss + wo * oce + wr * reg).backward()
+        return o.grad.numpy()
+
+    for wl, wo, wr in [(0.0, 1.0, 0.0), (0.0, 0.0, 1.0), (0.5, 2.0, -1.0)]:
+        o = offsets.to(dev).requires_grad_(True)
+        loss, oce, reg = oce_loss_fused_sampled(o, 10.0, 300, 31, 11, 2, 10.0, 1e-2)
+        (wl * loss + wo * oce + wr * reg).backward()
+        assert _rel(o.grad.cpu().numpy(), oracle_grad(wl, wo, wr)) <= 2e-5, (wl, wo, wr)
+    o = offsets.to(dev).requires_grad_(True)
+    loss, _, _ = oce_loss_fused_sampled(o, 10.0, 300, 31, 11, 2, 10.0, 1e-2)
+    loss.backward(retain_graph=True)
+    loss.backward()
+    assert _rel(o.grad.cpu().numpy(), 2.0 * oracle_grad(1.0, 0.0, 0.0)) <= LOSS_RTOL
+    # kappa whose offset table does not fit in shared memory is refused, not mis-sampled
+    with pytest.raises(Exception):
+        K.oce_loss_sampled(torch.zeros(1, 3, 80, 80, 80, device=dev), 30.0, 10, 31, 1, 0, 10.0, 1e-5)
+
+
+def test_loss_full_size_config1_against_oracle():
+    """BASELINE configs[1] at FULL size (8 x 702 367 pairs on (8, 2, 496, 496)): both kernels against the
+    float64 oracle arithmetic on the same pairs -- the explicit-list kernel on the reference-format int64
+    lists, the fused-sampling kernel on the pairs it draws itself (stream oracle)."""
+    from oracle import device_sampler as ods
+
+    dev = _dev()
+    B, S, kappa, T, w = 8, (496, 496), 10.0, 10.0, 1e-5
+    na, nr = int(0.1 * (S[0] - 20) * (S[1] - 20)), 31
+    assert (na, nr) == (22657, 31)
+    a_ref, r_ref = ods.sample_pairs(B, S[::-1], kappa, na, nr, seed=2024, sequence=1)
+    offsets = torch.from_numpy(synthetic.loss_offsets(B, 2, S, seed=0))
+    exact = oloss.loss_step_float64(offsets, torch.from_numpy(a_ref), torch.from_numpy(r_ref), T, w)
+    for layout in (torch.contiguous_format, torch.channels_last):
+        off_d = offsets.to(dev).contiguous(memory_format=layout)
+        out_l, g_l = K.oce_loss_fwd_bwd(off_d, torch.from_numpy(a_ref).to(dev), torch.from_numpy(r_ref).to(dev), T, w)
+        out_s, g_s, _ = K.oce_loss_sampled(off_d, kappa, na, nr, 2024, 1, T, w)
+        for out, g in ((out_l, g_l), (out_s, g_s)):
+            for i in range(3):
+                assert abs(out[i].item() - exact[i].item()) <= LOSS_RTOL * abs(exact[i].item())
+            assert out[3].item() == 0
+            assert _rel(g.cpu().numpy(), exact[3].numpy()) <= LOSS_RTOL
+
+
 # ----------------------------------------------------------------------------- TTA
 @pytest.mark.parametrize("case", ["2d", "3d"])
 def test_tta_matches_reference_golden(golden, case):

@@ -275,3 +275,53 @@ def test_evaluate_without_ground_truth(golden):
     g = golden("evaluate")
     assert bool(g["empty_gt_none"])
     assert oeval.compute_pairwise_IoU(g["empty_gt_prediction"], g["empty_gt_groundtruth"]) is None
+
+
+# ----------------------------------------------------------------------------- device pair stream (restated)
+def test_philox_known_answers():
+    """Random123's published known-answer vectors for philox4x32-10 (kat_vectors: zero, all-ones, pi digits)."""
+    from oracle import device_sampler as ods
+
+    w = ods.philox4x32_10(np.array([0], dtype=np.uint64), 0, 0)[0]
+    assert [int(x) for x in w] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    full = 0xFFFFFFFFFFFFFFFF
+    w = ods.philox4x32_10(np.array([full], dtype=np.uint64), full, full)[0]
+    assert [int(x) for x in w] == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    w = ods.philox4x32_10(np.array([0x85A308D3243F6A88], dtype=np.uint64), 0x0370734413198A2E, 0x299F31D0A4093822)[0]
+    assert [int(x) for x in w] == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+@pytest.mark.parametrize("nd,out_shape,kappa", [(2, (236, 236), 10.0), (3, (40, 48, 64), 5.0)])
+def test_device_stream_has_the_reference_samplers_distribution(nd, out_shape, kappa):
+    """The device stream against the restated reference sampler (itself bit-exact to the reference golden):
+    identical support for anchors and offsets, np.repeat run structure, and two-sample chi-square agreement
+    of the offset histograms."""
+    from oracle import device_sampler as ods
+
+    na, nr = 4000, 31
+    a, r = ods.sample_pairs(1, out_shape, kappa, na, nr, seed=3)
+    a, r = a[0], r[0]
+    np.random.seed(0)
+    big_density = na / ((out_shape[0] - 2 * kappa) * (out_shape[1] - 2 * kappa)) * 1.0001
+    a_ref, r_ref = osampler.sample_coordinates(out_shape, kappa, big_density, nd)
+    a_ref, r_ref = a_ref[: (len(a_ref) // 31) * 31], r_ref[: (len(a_ref) // 31) * 31]
+    runs = a.reshape(na, nr, nd)
+    assert (runs == runs[:, :1]).all()
+    k = int(kappa)
+    for d in range(nd):
+        assert a[:, d].min() == a_ref[:, d].min() == k
+        assert a[:, d].max() == a_ref[:, d].max() == out_shape[d] - k
+    off, off_ref = r - a, r_ref - a_ref
+    side = 2 * k + 1
+    code = lambda o: ((o + k) * side ** np.arange(nd)).sum(1)  # noqa: E731
+    h = np.bincount(code(off), minlength=side**nd).astype(np.float64)
+    h_ref = np.bincount(code(off_ref), minlength=side**nd).astype(np.float64)
+    assert ((h > 0) == (h_ref > 0)).all() or nd == 3  # 3-D: 4138 cells need more draws than this to all be hit
+    table = ods.offset_table(kappa, nd)
+    assert set(np.flatnonzero(h > 0)) <= set(code(table)) and set(np.flatnonzero(h_ref > 0)) <= set(code(table))
+    sup = code(table)
+    x, y = h[sup], h_ref[sup]
+    k1, k2 = np.sqrt(y.sum() / x.sum()), np.sqrt(x.sum() / y.sum())
+    chi2 = (((k1 * x - k2 * y) ** 2) / np.maximum(x + y, 1)).sum()
+    dof = len(sup) - 1
+    assert chi2 < dof + 6 * np.sqrt(2 * dof)

@@ -25,6 +25,14 @@ if what in ("all", "loss"):
     for _ in range(3):
         K.oce_loss_fwd_bwd(off_cl, anchors, refs, bench.TEMP, bench.REGW)
     torch.cuda.synchronize()
+if what in ("all", "sampled"):
+    offsets = torch.randn(bench.B, bench.D, *bench.OUT, device=dev)
+    off_cl = offsets.contiguous(memory_format=torch.channels_last)
+    for o in (off_cl, offsets):
+        for i in range(3):
+            K.oce_loss_sampled(o, bench.KAPPA, bench.N_ANCHORS, bench.N_REFS, 5, i, bench.TEMP, bench.REGW,
+                               extent_xyz=(bench.OUT[1], bench.OUT[0]))
+    torch.cuda.synchronize()
 if what in ("all", "tta"):
     stack = torch.randn(32, 2, 496, 496, device=dev)
     for _ in range(3):
