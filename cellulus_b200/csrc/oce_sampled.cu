@@ -23,10 +23,6 @@
 namespace cb200 {
 
 constexpr int SMP_THREADS = 256;
-#ifndef CB200_SMP_BATCH
-#define CB200_SMP_BATCH 2
-#endif
-constexpr int SMP_BATCH = CB200_SMP_BATCH;  // gathers in flight per lane (1, 2 or 4)
 constexpr int SMP_MIN_BLOCKS = 5;  // 709 blocks of 8 anchor-warps at configs[1]: one wave needs 5 per SM
 
 template <int D, typename OT, bool IL, bool BWD, bool DUMP>
@@ -79,65 +75,90 @@ oce_loss_sampled_kernel(const OT* __restrict__ offsets, PairStreamParams p, Shap
     }
     int n_ok = 0;
 
-    for (unsigned tg = 0; tg < p.n_tg; ++tg) {
-      const uint4 ro = stream_offset_block(rng, p, b, a, tg);
-      const uint32_t r4[4] = {ro.x, ro.y, ro.z, ro.w};
-      // two half-blocks: issue two gathers, then their math (four in flight per lane costs registers that the
-      // one-wave occupancy of 40 warps per SM does not have)
+    float fa[D];  // the anchor coordinate as a float: (float)(anc + off) == fa + (float)off exactly (small integers)
 #pragma unroll
-      for (int h = 0; h < 4; h += SMP_BATCH) {
-        int ref[SMP_BATCH][D];
-        float orf[SMP_BATCH][D];
-        bool ok[SMP_BATCH];
+    for (int k = 0; k < D; ++k) fa[k] = (float)anc[k];
+
+    // Software pipeline over ROUNDS of four pairs (the four words of a Philox block; a block gives `draws`
+    // rounds).  Four slots stay in flight per lane -- packed offset + D gathered floats each -- and every slot
+    // is refilled with the next round's gather right after its math, so a warp always has 3-4 gathers
+    // outstanding.  (Left to the compiler, the gathers of a round were serialised behind each other's math.)
+    uint32_t pk[4];
+    float orf[4][D];
+    unsigned okm = 0;  // bit j: slot j holds a live pair
+    unsigned t_next = 0;
+    auto issue = [&](int j, uint32_t word) {
+      const unsigned t = t_next + j;
+      pk[j] = s_table[bounded(word, p.n_table)];
+      int ref[D];
+      unpack_offset<D>(pk[j], ref);
+      const bool want = ok_a && (t < p.num_refs);
+      bool ok = want;
 #pragma unroll
-        for (int j = 0; j < SMP_BATCH; ++j) {
-          const unsigned t = tg * 4 + h + j;
-          int off[D];
-          stream_offset<D>(s_table, p, r4[h + j], off);
-          const bool want = ok_a && (t < p.num_refs);
-          ok[j] = want;
+      for (int k = 0; k < D; ++k) {
+        ref[k] += anc[k];
+        ok = ok && ((unsigned)ref[k] < (unsigned)shape.ext[k]);
+      }
+      if (want && !ok) ++bad;
+      okm = ok ? (okm | (1u << j)) : (okm & ~(1u << j));
+      if (ok) {
+        gather_pixel<D, OT, IL>(offsets, npix, first, (unsigned)pixel_of<D>(ref, shape), orf[j]);
+      } else {
 #pragma unroll
-          for (int k = 0; k < D; ++k) {
-            ref[j][k] = anc[k] + off[k];
-            ok[j] = ok[j] && ((unsigned)ref[j][k] < (unsigned)shape.ext[k]);
-          }
-          if (want && !ok[j]) ++bad;
-          if (ok[j]) {
-            gather_pixel<D, OT, IL>(offsets, npix, first, (unsigned)pixel_of<D>(ref[j], shape), orf[j]);
-          } else {
-#pragma unroll
-            for (int k = 0; k < D; ++k) orf[j][k] = 0.f;
-          }
-          if constexpr (DUMP) {  // debug / test mode: the lists this call used
-            if (owns && t < p.num_refs) {
-              const size_t pair = ((size_t)b * p.num_anchors + a) * p.num_refs + t;
-              store_coord_dyn<D>(dump_anchors, dump_dtype, pair, anc);
-              store_coord_dyn<D>(dump_refs, dump_dtype, pair, ref[j]);
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < SMP_BATCH; ++j) {
-          float diff[D], d2 = 0.f;
-#pragma unroll
-          for (int k = 0; k < D; ++k) {
-            const float er = __fadd_rn(orf[j][k], (float)ref[j][k]);
-            diff[k] = ea[k] - er;
-            d2 = fmaf(diff[k], diff[k], d2);
-          }
-          const float e = ex2_approx(d2 * neg_log2e_over_t);  // exp(-d^2 / T)
-          if (ok[j]) {
-            acc_oce += 1.0f - e;
-            ++n_ok;
-            if constexpr (BWD) {
-              const float ge = two_over_t * e;
-#pragma unroll
-              for (int k = 0; k < D; ++k) g[k] = fmaf(ge, diff[k], g[k]);
-            }
-          }
+        for (int k = 0; k < D; ++k) orf[j][k] = 0.f;
+      }
+      if constexpr (DUMP) {  // debug / test mode: the lists this call used
+        if (owns && t < p.num_refs) {
+          const size_t pair = ((size_t)b * p.num_anchors + a) * p.num_refs + t;
+          store_coord_dyn<D>(dump_anchors, dump_dtype, pair, anc);
+          store_coord_dyn<D>(dump_refs, dump_dtype, pair, ref);
         }
       }
+    };
+    auto math = [&](int j) {
+      int off[D];
+      unpack_offset<D>(pk[j], off);
+      float diff[D], d2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        const float er = __fadd_rn(orf[j][k], fa[k] + (float)off[k]);  // reference embedding + its coordinate
+        diff[k] = ea[k] - er;
+        d2 = fmaf(diff[k], diff[k], d2);
+      }
+      const float e = ex2_approx(d2 * neg_log2e_over_t);  // exp(-d^2 / T)
+      if (okm & (1u << j)) {
+        acc_oce += 1.0f - e;
+        ++n_ok;
+        if constexpr (BWD) {
+          const float ge = two_over_t * e;
+#pragma unroll
+          for (int k = 0; k < D; ++k) g[k] = fmaf(ge, diff[k], g[k]);
+        }
+      }
+    };
+
+    uint4 ro = stream_offset_block(rng, p, b, a, 0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) issue(j, pick_word(ro, j));
+    const unsigned n_rounds = p.n_tg * p.draws;
+    unsigned h = 1, tg = 0;  // position of the round being issued: draw h of block tg
+#pragma unroll 1
+    for (unsigned r = 1; r < n_rounds; ++r, ++h) {
+      t_next += 4;
+      if (h == p.draws) {
+        h = 0;
+        ro = stream_offset_block(rng, p, b, a, ++tg);
+      } else {  // second draw of every word: the low half of the first product is the next uniform word
+        ro.x *= p.n_table; ro.y *= p.n_table; ro.z *= p.n_table; ro.w *= p.n_table;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        math(j);
+        issue(j, pick_word(ro, j));
+      }
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) math(j);
     // the regulariser depends on the anchor only: n_ok pairs contribute ||ea|| each (criterions/oce_loss.py:59-61)
     const float rs = n2 > 0.f ? rsqrt_approx(n2) : 0.f;  // 1 / ||ea||, 0 at the origin (torch's norm backward)
     const float fn = (float)n_ok;

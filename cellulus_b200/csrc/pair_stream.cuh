@@ -7,9 +7,12 @@
 //   anchor (b, a), a < A:    r = Philox4x32-10(key = seed, counter = b*A + a, stream = 2*sequence)
 //                            column k = trunc(kappa) + mulhi(r[k], extent_k - 2 trunc(kappa) + 1)
 //                            = np.random.randint(kappa, extent_k - kappa + 1)            (:203-218)
-//   offset of pair (b, a, t), t < R:
-//                            r = Philox4x32-10(key = seed, counter = (b*A + a)*ceil(R/4) + t/4, stream = 2*sequence + 1)
-//                            offset = TABLE[mulhi(r[t % 4], |TABLE|)]
+//   offset of pair (b, a, t), t < R: one Philox block serves 4q pairs, q = 2 when |TABLE| <= 1024, else 1:
+//                            r = Philox4x32-10(key = seed, counter = (b*A + a)*ceil(R/(4q)) + t/(4q), stream = 2*sequence + 1)
+//                            u = t % (4q); w = r[u % 4]; if u >= 4: w = lo32(w * |TABLE|)
+//                            offset = TABLE[mulhi(w, |TABLE|)]
+//                            (the low half of the first product is a fresh uniform word up to a bias of
+//                             |TABLE|^2 / 2^32 < 2.5e-4: two bounded draws from one 32-bit word)
 //   TABLE = the integer points o of [-trunc(kappa), trunc(kappa)]^D with sum o^2 < kappa^2 and o != 0,
 //           enumerated with column 0 fastest.  A uniform draw from TABLE is exactly what the reference's
 //           rejection filter (`in_circle`, `not_zero`, :179-196) leaves of its i.i.d. uniform candidates.
@@ -27,7 +30,8 @@ namespace cb200 {
 struct PairStreamParams {
   unsigned num_anchors;   // A
   unsigned num_refs;      // R
-  unsigned n_tg;          // ceil(R / 4): Philox blocks per anchor in the offset stream
+  unsigned n_tg;          // ceil(R / (4 q)): Philox blocks per anchor in the offset stream
+  unsigned draws;         // q: bounded draws taken from one 32-bit word (2 for small tables, else 1)
   unsigned n_table;       // admissible offsets
   unsigned n_cand;        // (2 kap + 1)^D candidates the table is filtered from
   int kap;                // trunc(kappa)
@@ -70,52 +74,56 @@ inline bool pair_stream_plan(PairStreamParams& p, int num_dims, const int64_t* e
   p.n_table = (unsigned)n_table;
   p.num_anchors = (unsigned)num_anchors;
   p.num_refs = (unsigned)num_refs;
-  p.n_tg = (unsigned)((num_refs + 3) / 4);
+  p.draws = n_table <= 1024 ? 2u : 1u;
+  p.n_tg = (unsigned)((num_refs + 4 * p.draws - 1) / (4 * p.draws));
   return true;
 }
 
 constexpr size_t PAIR_TABLE_MAX_BYTES = 160 * 1024;  // dynamic shared memory the table may take
 
-// ordered compaction of the admissible offsets into shared memory (every thread of the block calls this)
+// ordered compaction of the admissible offsets into shared memory (every thread of the block calls this):
+// every warp owns a contiguous range of candidates, counts its admissible ones, and after one block-wide
+// exchange of the counts writes them behind those of the warps in front
 template <int D>
-__device__ __forceinline__ void build_offset_table(uint32_t* __restrict__ table, const PairStreamParams& p) {
-  __shared__ int s_warp_total[32];
-  __shared__ int s_base;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = (blockDim.x + 31) >> 5;
-  const int side = 2 * p.kap + 1;
-  if (tid == 0) s_base = 0;
-  __syncthreads();
-  for (unsigned c0 = 0; c0 < p.n_cand; c0 += blockDim.x) {
-    const unsigned c = c0 + tid;
-    bool ok = false;
-    uint32_t packed = 0;
-    if (c < p.n_cand) {
-      unsigned rest = c;
-      int s2 = 0, any = 0;
+__device__ __forceinline__ bool offset_candidate(unsigned c, const PairStreamParams& p, uint32_t& packed) {
+  const unsigned side = 2u * (unsigned)p.kap + 1u;
+  unsigned rest = c;
+  int s2 = 0, any = 0;
+  packed = 0;
 #pragma unroll
-      for (int k = 0; k < D; ++k) {
-        const int o = (int)(rest % (unsigned)side) - p.kap;
-        rest /= (unsigned)side;
-        s2 += o * o;
-        any |= o;
-        packed |= ((uint32_t)o & 0xffu) << (8 * k);
-      }
-      ok = s2 <= p.k2 && any != 0;
-    }
-    const unsigned vote = __ballot_sync(FULL, ok);
-    if (lane == 0) s_warp_total[warp] = __popc(vote);
-    __syncthreads();
-    int base = s_base;
-    for (int w = 0; w < warp; ++w) base += s_warp_total[w];
-    if (ok) table[base + __popc(vote & ((1u << lane) - 1u))] = packed;
-    __syncthreads();
-    if (tid == 0) {
-      int total = 0;
-      for (int w = 0; w < n_warps; ++w) total += s_warp_total[w];
-      s_base += total;
-    }
-    __syncthreads();
+  for (int k = 0; k < D; ++k) {
+    const int o = (int)(rest % side) - p.kap;
+    rest /= side;
+    s2 += o * o;
+    any |= o;
+    packed |= ((uint32_t)o & 0xffu) << (8 * k);
   }
+  return c < p.n_cand && s2 <= p.k2 && any != 0;
+}
+template <int D>
+__device__ __noinline__ void build_offset_table(uint32_t* __restrict__ table, const PairStreamParams& p) {
+  __shared__ int s_warp_total[32];
+  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, n_warps = (blockDim.x + 31u) >> 5;
+  const unsigned per_warp = ((p.n_cand + n_warps - 1u) / n_warps + 31u) & ~31u;
+  const unsigned c_begin = warp * per_warp, c_end = min(c_begin + per_warp, (p.n_cand + 31u) & ~31u);
+  uint32_t packed;
+  int count = 0;
+#pragma unroll 1
+  for (unsigned c = c_begin + lane; c < c_end; c += 32u)
+    count += __popc(__ballot_sync(FULL, offset_candidate<D>(c, p, packed)));
+  if (lane == 0) s_warp_total[warp] = count;
+  __syncthreads();
+  int base = 0;
+#pragma unroll 1
+  for (unsigned w = 0; w < warp; ++w) base += s_warp_total[w];
+#pragma unroll 1
+  for (unsigned c = c_begin + lane; c < c_end; c += 32u) {
+    const bool ok = offset_candidate<D>(c, p, packed);
+    const unsigned vote = __ballot_sync(FULL, ok);
+    if (ok) table[base + __popc(vote & ((1u << lane) - 1u))] = packed;
+    base += __popc(vote);
+  }
+  __syncthreads();
 }
 
 template <int D>
@@ -127,7 +135,7 @@ __device__ __forceinline__ void stream_anchor(const Philox& rng, const PairStrea
   for (int k = 0; k < D; ++k) anc[k] = p.kap + (int)bounded(rr[k], (uint32_t)p.span[k]);
 }
 
-// the Philox block that holds the offset words of pairs t = 4 tg .. 4 tg + 3 of anchor (b, a)
+// the Philox block that holds the offset words of pairs t = 4q tg .. 4q tg + 4q - 1 of anchor (b, a)
 __device__ __forceinline__ uint4 stream_offset_block(const Philox& rng, const PairStreamParams& p, unsigned b, unsigned a,
                                                      unsigned tg) {
   return rng(((uint64_t)b * p.num_anchors + a) * p.n_tg + tg, p.sequence * 2 + 1);
@@ -137,10 +145,15 @@ __device__ __forceinline__ uint32_t pick_word(const uint4& r, unsigned j) {
   return j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w;
 }
 
+// packed table entry of pair t (u = t % (4q) inside its block): second draws reuse the low product half
+__device__ __forceinline__ uint32_t stream_offset_packed(const uint32_t* __restrict__ table, const PairStreamParams& p,
+                                                         const uint4& block, unsigned u) {
+  uint32_t w = pick_word(block, u & 3);
+  if (u >= 4) w *= p.n_table;
+  return table[bounded(w, p.n_table)];
+}
 template <int D>
-__device__ __forceinline__ void stream_offset(const uint32_t* __restrict__ table, const PairStreamParams& p,
-                                              uint32_t word, int (&off)[D]) {
-  const uint32_t packed = table[bounded(word, p.n_table)];
+__device__ __forceinline__ void unpack_offset(uint32_t packed, int (&off)[D]) {
 #pragma unroll
   for (int k = 0; k < D; ++k) off[k] = (int)(signed char)(packed >> (8 * k));
 }

@@ -7,13 +7,13 @@
 //   anchor column k ~ U{trunc(kappa) .. extent_k - trunc(kappa)}  (np.random.randint(kappa, out-kappa+1))
 //   offset ~ uniform over integer o in [-trunc(kappa), trunc(kappa)]^D with sum o^2 < kappa^2, o != 0
 //            (what `in_circle` / `not_zero` filtering of i.i.d. draws yields), drawn by ONE bounded index into
-//            the table of admissible offsets -- no rejection loop, one Philox block per four pairs
+//            the table of admissible offsets -- no rejection loop, one Philox block per four (eight) pairs
 //   each anchor repeated num_references times consecutively (np.repeat, :236)
 #include "pair_stream.cuh"
 
 namespace cb200 {
 
-// One thread per pair, coalesced vector stores.  The four pairs that share an offset block recompute it (the
+// One thread per pair, coalesced vector stores.  The pairs that share an offset block recompute it (the
 // kernel writes 8 - 32 bytes per pair and is bound by those stores once the rejection loop is gone).
 template <int D, typename CT, typename IT>
 __global__ void __launch_bounds__(256)
@@ -29,8 +29,9 @@ sample_pairs_kernel(CT* __restrict__ anchors, CT* __restrict__ refs, PairStreamP
     const unsigned t = (unsigned)(q - (IT)a * p.num_refs);
     int anc[D], off[D], ref[D];
     stream_anchor<D>(rng, p, b, a, anc);
-    const uint4 ro = stream_offset_block(rng, p, b, a, t >> 2);
-    stream_offset<D>(s_table, p, pick_word(ro, t & 3), off);
+    const unsigned per_block = 4 * p.draws, tg = t / per_block;
+    const uint4 ro = stream_offset_block(rng, p, b, a, tg);
+    unpack_offset<D>(stream_offset_packed(s_table, p, ro, t - tg * per_block), off);
 #pragma unroll
     for (int k = 0; k < D; ++k) ref[k] = anc[k] + off[k];
     const size_t g = (size_t)b * (size_t)P + (size_t)q;

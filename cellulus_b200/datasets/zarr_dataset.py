@@ -1,7 +1,8 @@
 """Random-crop dataset over a zarr container (`cellulus/datasets/zarr_dataset.py`).
 
 The reference builds a gunpowder graph (ZarrSource + RandomLocation + Normalize [+ ElasticAugment]); that
-I/O library is out of scope (and not installed), so crops are cut directly from the array.  What IS on the hot
+I/O library is out of scope (and not installed), so crops are cut directly from the array and the elastic
+augmentation (rotation 0..pi/2, scale 0.9..1.1, control-point jitter) is applied by datasets/augment.py.  What IS on the hot
 path -- the anchor / reference pair sampler (`:177-251`) -- is provided twice: `sample_coordinates()` is the
 host sampler with the reference's exact RNG call order (what its DataLoader workers run), and
 `sample_coordinates_device()` draws the same distribution on the GPU (`cb200_sample_pairs`), so the two
@@ -10,7 +11,6 @@ host sampler with the reference's exact RNG call order (what its DataLoader work
 
 from __future__ import annotations
 
-import warnings
 from typing import Tuple
 
 import numpy as np
@@ -20,6 +20,7 @@ from torch.utils.data import IterableDataset
 from cellulus_b200 import zarr_lite
 from cellulus_b200.configs import DatasetConfig
 
+from .augment import elastic_crop
 from .meta_data import DatasetMetaData
 
 
@@ -57,28 +58,35 @@ class ZarrDataset(IterableDataset):  # type: ignore
         self.kappa = kappa
         self.output_shape = tuple(int(c - 16) for c in self.crop_size)  # hard-coded in the reference (:94)
         self.unbiased_shape = tuple(int(o - (2 * self.kappa)) for o in self.output_shape)
-        if elastic_deform:
-            warnings.warn("elastic_deform is a gunpowder augmentation and is not part of this build; crops are "
-                          "served un-deformed")
 
     def __iter__(self):
         return iter(self._yield_sample())
 
-    def _normalize(self, data: np.ndarray) -> np.ndarray:
+    def _normalize(self, data: np.ndarray, stored_dtype=None) -> np.ndarray:
         factor = self.normalization_factor
-        if factor is None:  # gp.Normalize(factor=None): by dtype
-            factor = {np.dtype(np.uint8): 1.0 / 255, np.dtype(np.uint16): 1.0 / 65535}.get(data.dtype, 1.0)
+        if factor is None:  # gp.Normalize(factor=None): by the dtype the array is stored in
+            factor = {np.dtype(np.uint8): 1.0 / 255, np.dtype(np.uint16): 1.0 / 65535}.get(
+                np.dtype(stored_dtype if stored_dtype is not None else data.dtype), 1.0)
         return data.astype(np.float32) * np.float32(factor)
+
+    def _crop(self, array, rng) -> np.ndarray:
+        """One normalised crop `(C, *crop_size)`: a random location (gp.RandomLocation), elastically deformed when
+        the config asks for it (`:122-131`; see datasets/augment.py)."""
+        s = int(rng.integers(0, self.num_samples))
+        if self.elastic_deform:
+            data = elastic_crop(array, s, self.crop_size, self.spatial_array, self.control_point_spacing,
+                                self.control_point_jitter, rng)
+            return self._normalize(data, array.dtype)
+        start = [int(rng.integers(0, n - c + 1)) for n, c in zip(self.spatial_array, self.crop_size)]
+        key = (s, slice(None)) + tuple(slice(a, a + c) for a, c in zip(start, self.crop_size))
+        return self._normalize(array[key])
 
     def _yield_sample(self):
         array = zarr_lite.open(self.dataset_config.container_path, "r")[self.dataset_config.dataset_name]
         rng = np.random.default_rng()
         while True:
             while True:  # reject all-zero crops (:138-151)
-                s = int(rng.integers(0, self.num_samples))
-                start = [int(rng.integers(0, n - c + 1)) for n, c in zip(self.spatial_array, self.crop_size)]
-                key = (s, slice(None)) + tuple(slice(a, a + c) for a, c in zip(start, self.crop_size))
-                crop = self._normalize(array[key])
+                crop = self._crop(array, rng)
                 if np.max(crop) > 0.0:
                     break
             if self.sample_pairs:
@@ -107,6 +115,12 @@ class ZarrDataset(IterableDataset):  # type: ignore
         anchor_samples = np.repeat(np.stack(cols, axis=1), num_references, axis=0)
         reference_samples = anchor_samples + self.sample_offsets_within_radius(self.kappa, len(anchor_samples))
         return anchor_samples, reference_samples
+
+    def pair_stream(self):
+        """Parameters of the device pair stream for this dataset's crops: what `criterion.fused_sampled` needs to
+        draw the pairs inside the loss kernel (quirk Q4: column d is drawn from output_shape[d])."""
+        return dict(kappa=self.kappa, num_anchors=self.get_num_anchors(), num_references=self.get_num_references(),
+                    extent_xyz=tuple(self.output_shape[: self.num_spatial_dims]))
 
     def sample_coordinates_device(self, batch_size, device, seed, sequence=0, dtype=None):
         """The same distribution drawn on the GPU: (B, P, D) anchors and references.

@@ -1,10 +1,10 @@
 """`train(experiment_config)` -- the reference's training entry point (`cellulus/train.py:16-157`) with the
 loss slice of `train_iteration` (`:160-180`) on the B200 kernels.
 
-Per iteration: raw crops come from the DataLoader (host), the (anchor, reference) pair lists are drawn ON THE
-DEVICE (`cb200_sample_pairs`; the reference ships two int64 lists per step over PCIe), the U-Net runs in
-channels-last so its output is already in the layout the fused kernel gathers from, and gather x2 + OCE loss
-+ backward-to-offsets is one kernel (`oce_loss_fused`).  Checkpoints keep the reference's keys
+Per iteration: raw crops come from the DataLoader (host), the U-Net runs in channels-last so its output is
+already in the layout the loss kernel gathers from, and the (anchor, reference) pair sampling, gather x2, OCE loss
+and backward-to-offsets are ONE kernel (`cb200_oce_loss_sampled`: the pairs are drawn inside it from a counter-based
+stream; the reference samples them in DataLoader workers and ships two int64 lists per step over PCIe).  Checkpoints keep the reference's keys
 (`iteration, lowest_loss, model_state_dict, optim_state_dict, logger_data`) and state-dict names.
 
 Multi-GPU: launch with torchrun; every rank trains on its own crops (shard by batch), parameter gradients
@@ -127,10 +127,15 @@ def train(experiment_config):
 def train_iteration(raw, model, criterion, optimizer, device, dataset, memory_format, seed, grad_scale=1.0):
     """`train.py:160-180`; returns `(loss, oce_loss, offsets)` like the reference."""
     raw = raw.to(device, non_blocking=True).contiguous(memory_format=memory_format)
-    anchors, refs = dataset.sample_coordinates_device(raw.shape[0], device, seed)
     model.train()
     offsets = model(raw)
-    loss, oce_loss, _ = criterion.fused(offsets, anchors, refs)  # gather x2 + OCE loss + backward in one kernel
+    if tuple(offsets.shape[2:]) != tuple(dataset.output_shape):
+        # the sampler draws pairs for `crop - 16` (hard-coded in the reference, zarr_dataset.py:94); with other
+        # downsampling factors the reference fails with an IndexError in its gather -- fail as loudly here
+        raise IndexError(f"the model's output shape {tuple(offsets.shape[2:])} differs from the shape the pair "
+                         f"sampler assumes {tuple(dataset.output_shape)} (crop_size - 16)")
+    # pair sampling + gather x2 + OCE loss + backward in ONE kernel: the lists never exist
+    loss, oce_loss, _ = criterion.fused_sampled(offsets, seed=seed, **dataset.pair_stream())
     optimizer.zero_grad()
     (loss * grad_scale if grad_scale != 1.0 else loss).backward()
     optimizer.step()

@@ -67,8 +67,9 @@ def sample_pairs(batch: int, extent_xyz, kappa: float, num_anchors: int, num_ref
     D = len(extent_xyz)
     kap = int(kappa)
     A, R = int(num_anchors), int(num_references)
-    n_tg = (R + 3) // 4
     table = offset_table(kappa, D)
+    q = 2 if len(table) <= 1024 else 1  # bounded draws per 32-bit word (pair_stream.cuh)
+    n_tg = (R + 4 * q - 1) // (4 * q)
     b = np.repeat(np.arange(batch, dtype=np.uint64), A)
     a = np.tile(np.arange(A, dtype=np.uint64), batch)
     ba = b * np.uint64(A) + a
@@ -76,7 +77,11 @@ def sample_pairs(batch: int, extent_xyz, kappa: float, num_anchors: int, num_ref
     anchors = np.stack([kap + _mulhi(words[:, k], int(extent_xyz[k]) - 2 * kap + 1) for k in range(D)], axis=1)
     tg = np.arange(n_tg, dtype=np.uint64)
     counters = (ba[:, None] * np.uint64(n_tg) + tg[None, :]).reshape(-1)
-    ow = philox4x32_10(counters, 2 * sequence + 1, seed).reshape(batch * A, n_tg * 4)[:, :R]
+    ow = philox4x32_10(counters, 2 * sequence + 1, seed).reshape(batch * A, n_tg, 4)
+    if q == 2:  # second draw of a word: the low half of the first product is the next uniform word
+        second = ((ow.astype(np.uint64) * np.uint64(len(table))) & _MASK).astype(np.uint32)
+        ow = np.concatenate([ow, second], axis=2)
+    ow = ow.reshape(batch * A, n_tg * 4 * q)[:, :R]
     offs = table[_mulhi(ow.reshape(-1), len(table))].reshape(batch * A, R, D)
     anchors_rep = np.repeat(anchors[:, None, :], R, axis=1)
     refs = anchors_rep + offs

@@ -108,6 +108,74 @@ def test_dataset_crops_and_host_sampler_match_reference_order(tmp_path):
     assert np.array_equal(anchors, a_ref) and np.array_equal(refs, r_ref)
 
 
+def test_elastic_augmentation(tmp_path):
+    """`elastic_deform=True` (the reference default, zarr_dataset.py:122-131) deforms the crops: identity
+    parameters reproduce the array (bilinear on a linear ramp is exact), a quarter turn is `np.rot90`, the
+    jittered transform is deterministic under its generator, and the dataset serves normalised deformed crops."""
+    import math
+
+    from cellulus_b200.datasets.augment import elastic_crop
+
+    yy, xx = np.mgrid[:80, :90].astype(np.float32)
+    ramp = (3.0 * yy + xx)[None, None]  # (s, c, y, x)
+    out = elastic_crop(ramp, 0, (24, 24), (80, 90), 8, 0.0, np.random.default_rng(4), (0.0, 0.0), (1.0, 1.0))
+    d = np.diff(out[0], axis=0), np.diff(out[0], axis=1)
+    assert out.shape == (1, 24, 24) and np.allclose(d[0], 3.0, atol=1e-3) and np.allclose(d[1], 1.0, atol=1e-3)
+    rnd = np.random.default_rng(0).random((1, 1, 80, 90)).astype(np.float32)
+    o0 = elastic_crop(rnd, 0, (21, 21), (80, 90), 8, 0.0, np.random.default_rng(5), (0.0, 0.0), (1.0, 1.0))
+    o90 = elastic_crop(rnd, 0, (21, 21), (80, 90), 8, 0.0, np.random.default_rng(5), (math.pi / 2, math.pi / 2), (1.0, 1.0))
+    assert np.allclose(np.rot90(o0[0], -1), o90[0], atol=1e-5)
+    a = elastic_crop(rnd, 0, (32, 32), (80, 90), 8, 2.0, np.random.default_rng(6))
+    b = elastic_crop(rnd, 0, (32, 32), (80, 90), 8, 2.0, np.random.default_rng(6))
+    assert np.array_equal(a, b) and not np.allclose(a, elastic_crop(rnd, 0, (32, 32), (80, 90), 8, 2.0, np.random.default_rng(7)))
+    vol = np.random.default_rng(1).random((1, 2, 20, 40, 40)).astype(np.float32)
+    assert elastic_crop(vol, 0, (12, 24, 24), (20, 40, 40), 8, 2.0, np.random.default_rng(8)).shape == (2, 12, 24, 24)
+    _make_container(tmp_path / "a.zarr")
+    ds = get_dataset(DatasetConfig(container_path=tmp_path / "a.zarr", dataset_name="train"), crop_size=(60, 60),
+                     elastic_deform=True, control_point_spacing=32, control_point_jitter=2.0, density=0.1, kappa=10.0,
+                     normalization_factor=None)
+    crop, anchors, refs = next(iter(ds))
+    assert crop.shape == (1, 60, 60) and crop.dtype == np.float32 and 0 < crop.max() <= 1.0
+    assert ds.pair_stream() == dict(kappa=10.0, num_anchors=int(0.1 * 24 * 24), num_references=31, extent_xyz=(44, 44))
+
+
+def test_device_strings_are_resolved():
+    """`device = "cuda"` (no index) is a valid config value in the reference; the kernels need a concrete index."""
+    from cellulus_b200.utils.device import resolve_device
+
+    assert resolve_device("cuda", set_current=False) == torch.device("cuda", 0)
+    assert resolve_device("cuda:3", set_current=False) == torch.device("cuda", 3)
+    os.environ["WORLD_SIZE"], os.environ["LOCAL_RANK"] = "4", "2"
+    try:
+        assert resolve_device("cuda:0", set_current=False) == torch.device("cuda", 2)  # the rank's own GPU wins
+    finally:
+        del os.environ["WORLD_SIZE"], os.environ["LOCAL_RANK"]
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        resolve_device("cpu")
+
+
+@pytest.mark.parametrize("codec", [None, "zlib", "gzip"])
+def test_zarr_lite_compressor_roundtrip(tmp_path, codec):
+    """Chunks are written in the container format the array's compressor id names (numcodecs' GZip.decode needs a
+    gzip member, Zlib.decode a zlib stream)."""
+    import gzip
+    import zlib
+
+    g = zarr_lite.open(tmp_path / "z.zarr")
+    x = np.random.default_rng(2).integers(0, 9, size=(2, 1, 20, 24)).astype(np.uint16)
+    comp = None if codec is None else {"id": codec, "level": 1}
+    a = g.create_dataset("x", shape=x.shape, dtype=np.uint16, chunks=(1, 1, 20, 24), compressor=comp)
+    a[...] = x
+    assert np.array_equal(zarr_lite.open(tmp_path / "z.zarr", "r")["x"][...], x)
+    raw = open(tmp_path / "z.zarr" / "x" / "0.0.0.0", "rb").read()
+    if codec == "gzip":
+        assert raw[:2] == b"\x1f\x8b" and np.array_equal(np.frombuffer(gzip.decompress(raw), np.uint16), x[0].ravel())
+    elif codec == "zlib":
+        assert np.array_equal(np.frombuffer(zlib.decompress(raw), np.uint16), x[0].ravel())
+    else:
+        assert raw == x[0].tobytes()
+
+
 def test_unet_stand_in_geometry_and_checkpoint_keys():
     m = get_model(in_channels=1, out_channels=2, num_fmaps=12, fmap_inc_factor=2, features_in_last_layer=64,
                   downsampling_factors=[(2, 2)], num_spatial_dims=2)
