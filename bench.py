@@ -13,11 +13,17 @@ shards by batch, no data-path collective: weak scaling).  The same line carries
   roofline      achieved algorithmic HBM GB/s of the fused kernel vs the measured peak
   cpu_baseline  the oracle port of the reference path timed on this box's host cores
   e2e           the same metric through the public API from pinned HOST buffers
-  detect        secondary metric: mean-shift detection Mpx/s on BASELINE config #3
-                (128 x 256 x 256 volume, 3-D embeddings), with its own cpu_baseline
+  multi_gpu     (every N) wall-clock jobs that exercise the multi-GPU inference paths: ONE volume split by
+                seed over the ranks (two all-gathers, N-rank result asserted equal to the 1-rank result) and
+                BASELINE configs[4] blockwise inference (scan blocks dealt round-robin)
+  detect        second half of BASELINE's metric, LAST in the line: mean-shift detection Mpx/s on
+                BASELINE configs[2] (128 x 256 x 256 volume, 3-D embeddings) with its own roofline
+                (distance tests of the hill-climb kernel vs the measured FP64 FMA peak), cpu_baseline, e2e
+                and a label-for-label comparison with the reference's own output (tests/golden/)
 
-`--impl reference` times the oracle port (torch CPU, all host threads) on rank 0.
-Nothing here reads /root/reference.
+`--impl reference` times the oracle port (torch CPU, all host threads) on rank 0; at N = 1 it also runs the
+reference detect path (oracle port of mean_shift_segmentation, scikit-learn underneath) ONCE on the full
+configs[2] volume (~4 min).  Nothing here reads /root/reference.
 """
 
 from __future__ import annotations
@@ -45,8 +51,17 @@ P = N_ANCHORS * N_REFS  # 702 367
 N_PX = B * OUT[0] * OUT[1]  # 1 968 128
 # algorithmic bytes per step: both int64 coordinate lists once, offsets once, dense gradient once
 ALGO_BYTES = B * P * D * 8 * 2 + N_PX * D * 4 + N_PX * D * 4
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu capture (profiles/), or None
-TRAFFIC_NCU = 208_558_848  # profiles/r01_loss_ncu_full_summary.txt: 204.45 MB read + 4.11 MB written
+
+
+def ncu_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the
+    same kernel (profiles/ncu_traffic.json, written by tools/ncu_summary.py from the .ncu-rep), or None."""
+    try:
+        rec = json.load(open(os.path.join(REPO, "profiles", "ncu_traffic.json")))[kernel_key]
+        return int(rec["dram_bytes_read"] + rec["dram_bytes_write"])
+    except Exception:
+        return None
+
 WORKLOAD = "configs[1]: OCELoss fwd+bwd, offsets (8,2,496,496) f32, 8x702367 pairs, int64 coords, kappa=10, density=0.1"
 
 # ---- BASELINE config #3 (secondary: detect) ----------------------------------------------
@@ -136,6 +151,25 @@ def cpu_loss_step_time(batch, steps, warmup, seed=0):
     return (time.perf_counter() - t0) / max(steps, 1)
 
 
+def cpu_detect(shape, objects, what):
+    """Oracle port of `mean_shift_segmentation` (cellulus/utils/mean_shift.py:6-45; scikit-learn MeanShift, hill
+    climb on ONE core as shipped, `predict` on all cores) on a scene of the bench family."""
+    from cellulus_b200 import synthetic
+    from oracle import mean_shift as oms
+
+    emb, _, _ = synthetic.blob_scene(shape, objects, radius=DET_RADIUS, seed=0)
+    emb64 = emb.astype(np.float64)
+    np.random.seed(0)
+    t0 = time.perf_counter()
+    labels = oms.mean_shift_segmentation(emb64[np.newaxis, :3].copy(), emb64[3], DET_BW, 0, DET_RP, DET_THR, None)
+    dt = time.perf_counter() - t0
+    n = int(np.prod(shape))
+    return {"value": n / dt / 1e6, "unit": "Mpx/s", "cores": 1, "kind": "port", "seconds": dt,
+            "centres": int(labels.max()),
+            "sample": f"{what}: {shape[0]}x{shape[1]}x{shape[2]}, {objects} balls, {int((labels > 0).sum())} fg voxels, "
+                      f"{dt:.1f} s; sklearn hill climb is single-core (n_jobs=None), predict uses OpenMP"}, labels
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -150,6 +184,12 @@ def run_reference(args):
     px = batch * OUT[0] * OUT[1]
     value = px / t
     sample = f"{batch}/{B} samples of the batch per step ({batch * P} pairs), {args.steps} steps"
+    detect = None
+    if args.gpus == 1 and not args.skip_detect:
+        # the reference detect path on the FULL configs[2] volume, once (a few minutes of one host core)
+        detect, labels = cpu_detect(DET_SHAPE, DET_OBJECTS, "full configs[2] volume")
+        detect.update({"metric": "detect Mpx/s (mean-shift)", "impl": "reference",
+                       "labels_equal_committed_golden": golden_labels_equal(labels)})
     line = {
         "impl": "reference", "metric": "OCELoss fwd+bwd px/s", "value": value, "unit": "px/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
@@ -159,25 +199,66 @@ def run_reference(args):
                          "pairs_per_s": batch * P / t},
         "e2e": {"value": value, "unit": "px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "detect": detect,
     }
     print(json.dumps(line), flush=True)
 
 
-# ------------------------------------------------------------------------------- B200 arm
-def bench_detect(dev, windows):
-    """Secondary metric: threshold -> labels on BASELINE config #3, inputs resident in HBM."""
+def golden_labels_equal(labels):
+    """Label-for-label comparison with the REFERENCE's own output on the configs[2] bench volume
+    (tests/golden/config2_labels.npz, written by tests/golden/make_golden_config2.py); None without the file."""
+    path = os.path.join(REPO, "tests", "golden", "config2_labels.npz")
+    if not os.path.exists(path):
+        return None
+    gold = np.load(path)["labels"]
+    got = labels.cpu().numpy() if isinstance(labels, torch.Tensor) else np.asarray(labels)
+    return bool(np.array_equal(got.reshape(gold.shape).astype(np.int64), gold.astype(np.int64)))
+
+
+# ------------------------------------------------------------------------------- B200 arm: detect
+def bench_detect(dev, windows, with_cpu):
+    """Second half of the metric: threshold -> labels on BASELINE configs[2], inputs resident in HBM."""
     from cellulus_b200 import kernels as K
     from cellulus_b200 import synthetic
     from cellulus_b200.detect import detect_embeddings
+    from cellulus_b200.utils.mean_shift import segment_embeddings_device
 
     emb_np, _, ids = synthetic.blob_scene(DET_SHAPE, DET_OBJECTS, radius=DET_RADIUS, seed=0)
     emb = torch.from_numpy(emb_np).to(dev)
     n_vox = int(np.prod(DET_SHAPE))
     fg = int((ids > 0).sum())
     kw = dict(bandwidth=DET_BW, threshold=DET_THR, reduction_probability=DET_RP, rng="philox")
+    # (a) parity at full size: the fit subset drawn like the reference (np.random under seed 0), labels compared
+    #     one for one with the reference's own output on this volume
+    np.random.seed(0)
+    labels_np_rng, _, _ = detect_embeddings(emb.double(), DET_BW, DET_THR, 1, DET_RP, rng="numpy", label_dtype=torch.int32)
+    equal_golden = golden_labels_equal(labels_np_rng[0])
+    # (b) the hill-climb kernel alone, step-by-step path: its time, its distance tests, its share
     for _ in range(2):
-        labels, _, _, infos = detect_embeddings(emb, return_info=True, **kw)
-    for _ in range(3):  # warm-up of the path that is timed (one C-ABI call per volume; its scratch arena grows here)
+        labels, info = segment_embeddings_device(emb, DET_BW, DET_THR, DET_RP, rng="philox", method="grid",
+                                                 label_dtype=torch.uint16)
+    n_fit, n_seeds = int(info["n_fit"]), int(info["n_seeds"])
+    grid = info["grid"]
+    pts, _, n, _ = K.fg_compact(emb, DET_THR)
+    fit_pts, n_fit2 = K.select_points(pts, n, K.bernoulli_flags(n, DET_RP, 0, dev))
+    sorted_pts, cell_start, _ = K.grid_build(fit_pts, n_fit2, grid)
+    kernel_ms = []
+    for _ in range(5):
+        seeds = fit_pts.clone()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        K.ms_grid_modes(sorted_pts, n_fit2, grid, cell_start, seeds, n_fit2, DET_BW)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        kernel_ms.append(e0.elapsed_time(e1))
+    k_ms = float(np.median(kernel_ms[1:]))
+    tests, steps = K.grid_modes_distance_tests(), K.grid_modes_climb_steps()
+    flop_per_test = 3 * 3 + 2  # SURVEY 8d: D sub, D mul/fma, 1 compare, D + 1 predicated adds
+    fp64_peak = K.fma_peak_tflops(torch.float64, dev)
+    fp32_peak = K.fma_peak_tflops(torch.float32, dev)
+    achieved_tf = tests * flop_per_test / (k_ms * 1e-3) / 1e12
+    # (c) the timed path: one C-ABI call per volume (its scratch arena grows during the warm-up)
+    for _ in range(3):
         detect_embeddings(emb, **kw)
     torch.cuda.synchronize(dev)
     reps = 10
@@ -192,27 +273,48 @@ def bench_detect(dev, windows):
     windows.append((w0, time.time()))
     ms = e0.elapsed_time(e1) / reps
     calls = (K.launch_counter["calls"] - c0) // reps
-    # e2e: pinned host volume in, uint16 labels out
+    # (d) e2e: pinned host volume in, uint16 labels out, wall clock per volume (median of 10)
     host = torch.from_numpy(emb_np).pin_memory()
     out_host = torch.empty((1, *DET_SHAPE), dtype=torch.uint16).pin_memory()
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    for _ in range(3):
+    e2e = []
+    for _ in range(12):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
         d = host.to(dev, non_blocking=True)
         labels, _, _ = detect_embeddings(d, **kw)
         out_host.copy_(labels, non_blocking=True)
         torch.cuda.synchronize(dev)
-    e2e_s = (time.perf_counter() - t0) / 3
-    info = infos[0]
+        e2e.append(time.perf_counter() - t0)
+    e2e_s = float(np.median(e2e[2:]))
+    cpu = None
+    if with_cpu:  # bounded sample of the same scene family (the full volume runs in the --impl reference arm)
+        cpu, _ = cpu_detect((40, 128, 128), 31, "sub-volume at the object density of configs[2]")
+        cpu.pop("centres")
     return {
         "metric": "detect Mpx/s (mean-shift)", "value": n_vox / ms / 1e3, "unit": "Mpx/s", "ms_per_volume": ms,
         "config": {"workload": "configs[2]: 128x256x256 volume, 3-D embeddings, 400 balls r=10, bw=7, threshold=0.5, "
                                "reduction_probability=0.1, seeds=all fit points",
-                   "foreground_voxels": fg, "fit_points": int(info["n_fit"]), "centres": int(info["k"]),
-                   "method": info["method"]},
-        "e2e": {"value": n_vox / e2e_s / 1e6, "unit": "Mpx/s", "h2d_bytes_per_step": host.numel() * 4,
-                "d2h_bytes_per_step": out_host.numel() * 2},
+                   "foreground_voxels": fg, "fit_points": n_fit, "seeds": n_seeds, "centres": int(info["k"]),
+                   "method": "grid hash (cells of edge >= bandwidth), one warp per seed"},
         "abi_calls_per_volume": int(calls),
+        "labels_equal_reference_golden": equal_golden,
+        "roofline": {"bound": "fp64-pipe", "kernel": "ms_grid_modes_kernel<3>", "kernel_ms": k_ms,
+                     "kernel_share_of_volume": k_ms / ms,
+                     "distance_tests_per_launch": tests, "flop_per_test": flop_per_test,
+                     "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
+                     "peak_source": "measured in this run (cb200_fma_peak, DFMA chains, CUDA events)",
+                     "fp32_fma_peak_tflops": fp32_peak,
+                     "distance_tests_per_s": tests / (k_ms * 1e-3),
+                     "climb_steps": steps, "brute_force_tests": steps * n_fit2,
+                     "pruning_ratio": steps * n_fit2 / max(tests, 1),
+                     "gathered_GBps": tests * 3 * 8 / (k_ms * 1e-3) / 1e9,
+                     "traffic": None,
+                     "note": "arithmetic is float64 without FMA contraction (the in/out decisions are the reference "
+                             "KD-tree's); the gathered cell ranges are L1/L2 hits (DRAM ~0: profiles/)"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": n_vox / e2e_s / 1e6, "unit": "Mpx/s", "ms_per_volume": e2e_s * 1e3,
+                "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 2,
+                "note": "median wall clock of 10 volumes: pinned host volume in, uint16 labels out"},
     }
 
 
@@ -328,28 +430,9 @@ def bench_post(dev, with_cpu):
     return out
 
 
-def cpu_detect_baseline():
-    """Oracle port of `mean_shift_segmentation` (scikit-learn MeanShift, hill climb on ONE core as shipped)
-    on a bounded sub-volume of the same scene family."""
-    from cellulus_b200 import synthetic
-    from oracle import mean_shift as oms
-
-    shape, objects = (24, 96, 96), 11  # same object density as config #3
-    emb, _, _ = synthetic.blob_scene(shape, objects, radius=DET_RADIUS, seed=0)
-    emb64 = emb.astype(np.float64)
-    np.random.seed(0)
-    t0 = time.perf_counter()
-    labels = oms.mean_shift_segmentation(emb64[np.newaxis, :3].copy(), emb64[3], DET_BW, 0, DET_RP, DET_THR, None)
-    dt = time.perf_counter() - t0
-    n = int(np.prod(shape))
-    return {"value": n / dt / 1e6, "unit": "Mpx/s", "cores": 1, "kind": "port",
-            "sample": f"{shape[0]}x{shape[1]}x{shape[2]} sub-volume, {objects} balls, {int((labels > 0).sum())} fg voxels, "
-                      f"{dt:.1f} s; sklearn hill climb is single-core (n_jobs=None), predict uses OpenMP"}
-
-
 def run_b200(args):
     from cellulus_b200 import kernels as K
-    from cellulus_b200.criterions import GraphedLossStep, oce_loss_fused
+    from cellulus_b200.criterions import GraphedLossStep, oce_loss_fused, oce_loss_fused_sampled
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -414,6 +497,12 @@ def run_b200(args):
     launches = (K.launch_counter["calls"] - c0 - warm) * 2  # zero-fill + fused kernel per replay
     value = world * N_PX / (ms_per_step * 1e-3)
     loss_value = steps_cl[0].loss.item()
+    loss_oracle = None
+    if rank == 0 and world == 1 and not args.skip_cpu:  # the same batch through the float64 oracle arithmetic
+        from oracle import oce_loss as oloss
+
+        loss_oracle = oloss.loss_step_float64(steps_cl[0].offsets.cpu().contiguous(), steps_cl[0].anchors.cpu(),
+                                              steps_cl[0].refs.cpu(), TEMP, REGW)[0].item()
     # (2) same op on the planar NCHW tensor the reference's model emits
     steps_pl = make_steps(torch.contiguous_format)
     ms_planar = timed(steps_pl, args.steps, warm)
@@ -447,70 +536,95 @@ def run_b200(args):
     offsets, anchors, refs = steps_pl[0].offsets, steps_pl[0].anchors, steps_pl[0].refs
     del steps_pl
 
-    # (3) end to end through the public API from pinned host buffers
+    # (3) end to end through the public API from pinned HOST buffers: every step copies that step's offsets and
+    # both int64 pair lists (the format the reference's DataLoader delivers, train.py:162-166) host -> device,
+    # runs loss + backward and reads the loss back.  Double-buffered: the copy of step i + 1 runs on a second
+    # stream while step i computes; the pinned buffers are allocated after this rank's CPU affinity has been
+    # narrowed to the NUMA node of its GPU (first touch places them there).
+    numa = bind_to_gpu_numa_node(local)
     h_off = offsets.detach().cpu().contiguous().pin_memory()
     h_anc, h_ref = anchors.cpu().pin_memory(), refs.cpu().pin_memory()
     e2e_steps = max(3, min(args.steps, 20))
+    copy_stream = torch.cuda.Stream(device=dev)
 
-    def e2e_step():
-        o = h_off.to(dev, non_blocking=True).requires_grad_(True)
-        a = h_anc.to(dev, non_blocking=True)
-        r = h_ref.to(dev, non_blocking=True)
-        loss, _, _ = oce_loss_fused(o, a, r, TEMP, REGW)
-        loss.backward()
-        return loss.item()  # device -> host read of the step's result (train.py:180)
+    def e2e_run(lists, n_steps):
+        """`lists`: pinned (anchors, refs) or None (pairs drawn inside the kernel).  Returns seconds per step."""
+        bufs = []
+        for _ in range(2):
+            bufs.append([torch.empty_like(h_off, device=dev)] +
+                        ([torch.empty_like(t, device=dev) for t in lists] if lists else []))
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        main_stream = torch.cuda.current_stream(dev)
 
-    for _ in range(2):
-        e2e_step()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
+        def upload(i):
+            slot = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done[slot])  # the step that last used this slot has finished
+                bufs[slot][0].copy_(h_off, non_blocking=True)
+                if lists:
+                    bufs[slot][1].copy_(lists[0], non_blocking=True)
+                    bufs[slot][2].copy_(lists[1], non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        for ev in done:
+            ev.record(main_stream)
+        upload(0)
+        t0 = None
+        for i in range(n_steps + 2):
+            if i == 2:  # two untimed warm-up steps
+                torch.cuda.synchronize(dev)
+                if dist is not None:
+                    dist.barrier()
+                t0 = time.perf_counter()
+            upload(i + 1)
+            slot = i % 2
+            main_stream.wait_event(ready[slot])
+            o = bufs[slot][0].requires_grad_(True)
+            if lists:
+                loss, _, _ = oce_loss_fused(o, bufs[slot][1], bufs[slot][2], TEMP, REGW)
+            else:
+                loss, _, _ = oce_loss_fused_sampled(o, KAPPA, N_ANCHORS, N_REFS, 77 + rank, i, TEMP, REGW,
+                                                    extent_xyz=(OUT[1], OUT[0]))
+            loss.backward()
+            done[slot].record(main_stream)
+            bufs[slot][0] = o.detach()
+            loss.item()  # device -> host read of the step's result (train.py:180)
+        torch.cuda.synchronize(dev)
+        sec = torch.tensor([(time.perf_counter() - t0) / n_steps], device=dev)
+        if dist is not None:
+            dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+        return sec.item()
+
     w0 = time.time()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize(dev)
-    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=dev)
+    e2e_s = e2e_run((h_anc, h_ref), e2e_steps)
     windows.append((w0, time.time()))
-    if dist is not None:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * N_PX / e2e_s.item()
+    e2e_value = world * N_PX / e2e_s
+    h2d_bytes = int(h_off.numel() * 4 + h_anc.numel() * 8 + h_ref.numel() * 8)
+    # (3b) the same step with the lists narrowed to int16 by the DataLoader workers (ZarrDataset(coordinate_dtype=
+    # "int16"): a quarter of the PCIe bytes) and (3c) with the pairs drawn inside the kernel: only the offsets cross
+    h_anc16, h_ref16 = h_anc.to(torch.int16).pin_memory(), h_ref.to(torch.int16).pin_memory()
+    e2e_i16_s = e2e_run((h_anc16, h_ref16), e2e_steps)
+    e2e_sampled_s = e2e_run(None, e2e_steps)
+    del h_anc16, h_ref16
 
-    # (3b) the same step when the pair lists are drawn ON THE DEVICE (cb200_sample_pairs replaces the
-    # DataLoader-side sampler of zarr_dataset.py:198-242): only the offsets cross PCIe
-    def e2e_sampled_step(i):
-        o = h_off.to(dev, non_blocking=True).requires_grad_(True)
-        a, r = K.sample_pairs(B, (OUT[1], OUT[0]), KAPPA, N_ANCHORS, N_REFS, seed=99, sequence=i, device=dev,
-                                  dtype=torch.int16)  # the training loop's list format
-        loss, _, _ = oce_loss_fused(o, a, r, TEMP, REGW)
-        loss.backward()
-        return loss.item()
-
-    for i in range(2):
-        e2e_sampled_step(i)
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        e2e_sampled_step(i)
-    torch.cuda.synchronize(dev)
-    e2e_sampled_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=dev)
-    if dist is not None:
-        dist.all_reduce(e2e_sampled_s, op=dist.ReduceOp.MAX)
+    # (4) multi-GPU inference jobs, wall clock, every rank takes part (also run at N = 1: the scaling baseline)
+    multi = None
+    if not args.skip_detect:
+        multi = bench_multi_gpu(dev, rank, world, dist)
 
     detect = None
     cpu_base = None
     if rank == 0:
         if not args.skip_detect:
-            detect = bench_detect(dev, windows)
-            detect["tta_aggregate"] = bench_tta(dev, windows)
-            detect["post_processing"] = bench_post(dev, with_cpu=(world == 1 and not args.skip_cpu))
+            tta = bench_tta(dev, windows)
+            post = bench_post(dev, with_cpu=(world == 1 and not args.skip_cpu))
+            detect = bench_detect(dev, windows, with_cpu=(world == 1 and not args.skip_cpu))
         if world == 1 and not args.skip_cpu:
             t_cpu = cpu_loss_step_time(B, 3, 1)
             cpu_base = {"value": N_PX / t_cpu, "unit": "px/s", "cores": torch.get_num_threads(), "kind": "port",
                         "sample": f"full configs[1] batch ({B * P} pairs), 3 steps after 1 warm-up, {t_cpu * 1e3:.0f} ms/step",
                         "pairs_per_s": B * P / t_cpu}
-            if detect is not None:
-                detect["cpu_baseline"] = cpu_detect_baseline()
     if dist is not None:
         dist.barrier()
     if rank == 0:
@@ -524,11 +638,15 @@ def run_b200(args):
                        "l2": f"inputs larger than L2: {N_SETS} distinct input sets of 211 MB visited round-robin "
                              "(126 MB L2), no explicit flush",
                        "step": "CUDA-graph replay of zero-fill + fused gather/loss/backward kernel",
+                       "pairs": "device pair stream (cb200_sample_pairs: the reference sampler's distribution, "
+                                "oracle/device_sampler.py), int64 lists",
                        "sharding": "by batch, one batch per rank, no data-path collective"},
             "pairs_per_s": world * B * P / (ms_per_step * 1e-3),
-            "loss_value_check": loss_value,
+            "loss_value_check": {"kernel": loss_value, "oracle_float64": loss_oracle,
+                                 "rel_err": abs(loss_value - loss_oracle) / abs(loss_oracle) if loss_oracle else None},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": TRAFFIC_NCU, "peak_source": peak_src,
+                         "traffic": ncu_traffic("oce_loss_fused_kernel<2,int64,f32,bwd,channels_last>"),
+                         "peak_source": peak_src,
                          "kernel": "oce_loss_fused_kernel<2,int64,f32,bwd,channels_last> (+ zero_fill_kernel)",
                          "kernel_ms": ms_per_step, "algorithmic_bytes_per_launch": ALGO_BYTES,
                          "note": "duration is the whole step: the 15.7 MB gradient zero-fill is included"},
@@ -543,8 +661,7 @@ def run_b200(args):
                                           "frac": algo_bf16 / (ms_bf16 * 1e-3) / 1e9 / peak,
                                           "algorithmic_bytes_per_launch": algo_bf16}},
             "i16_pairs": {"value": world * N_PX / (ms_i16 * 1e-3), "unit": "px/s", "ms_per_step": ms_i16,
-                          "note": "channels_last fp32 offsets, int16 coordinate lists as drawn by the device pair "
-                                  "sampler (the training loop's format; the reference's lists are int64)",
+                          "note": "channels_last fp32 offsets, int16 coordinate lists (the reference's lists are int64)",
                           "roofline": {"bound": "hbm", "achieved": algo_i16 / (ms_i16 * 1e-3) / 1e9, "peak": peak,
                                        "unit": "GB/s", "frac": algo_i16 / (ms_i16 * 1e-3) / 1e9 / peak,
                                        "algorithmic_bytes_per_launch": algo_i16}},
@@ -552,29 +669,180 @@ def run_b200(args):
                                "pairs_per_s": world * B * P / (ms_sampled * 1e-3),
                                "planar_ms_per_step": ms_sampled_planar,
                                "note": "cb200_oce_loss_sampled: pairs drawn inside the kernel (device pair stream), no "
-                                       "coordinate list in HBM; replaces sampler + list kernel of the training step",
+                                       "coordinate list in HBM; what train() runs per step",
                                "roofline": {"bound": "hbm", "achieved": algo_sampled / (ms_sampled * 1e-3) / 1e9,
                                             "peak": peak, "unit": "GB/s",
                                             "frac": algo_sampled / (ms_sampled * 1e-3) / 1e9 / peak,
                                             "algorithmic_bytes_per_launch": algo_sampled,
-                                            "note": "31.5 MB: at this size the kernel is issue / L2-latency bound "
-                                                    "(SURVEY 8d), the fraction is reported for completeness"}},
+                                            "note": "31.5 MB: at this size the kernel is bound by the L1 -> L2 request "
+                                                    "rate of its scattered 8-byte gathers (profiles/), not by HBM"}},
             "cpu_baseline": cpu_base,
-            "e2e": {"value": e2e_value, "unit": "px/s",
-                    "h2d_bytes_per_step": int(h_off.numel() * 4 + h_anc.numel() * 8 + h_ref.numel() * 8),
-                    "d2h_bytes_per_step": 4, "steps": e2e_steps, "ms_per_step": e2e_s.item() * 1e3,
-                    "with_device_pair_sampler": {
-                        "value": world * N_PX / e2e_sampled_s.item(), "unit": "px/s",
-                        "ms_per_step": e2e_sampled_s.item() * 1e3, "h2d_bytes_per_step": int(h_off.numel() * 4),
-                        "note": "int16 pair lists drawn on the device (same distribution as the reference "
-                                "sampler), sampling kernel inside the timed step"}},
+            "e2e": {"value": e2e_value, "unit": "px/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "steps": e2e_steps, "ms_per_step": e2e_s * 1e3,
+                    "h2d_GBps_per_rank": h2d_bytes / e2e_s / 1e9, "numa": numa,
+                    "note": "int64 lists as the reference's DataLoader delivers them; double-buffered uploads; the step "
+                            "is the host -> device copy (PCIe / host-memory bound), the kernels are 1-2 % of it",
+                    "int16_host_lists": {"value": world * N_PX / e2e_i16_s, "unit": "px/s", "ms_per_step": e2e_i16_s * 1e3,
+                                         "h2d_bytes_per_step": int(h_off.numel() * 4 + h_anc.numel() * 2 * 2)},
+                    "pairs_drawn_in_kernel": {"value": world * N_PX / e2e_sampled_s, "unit": "px/s",
+                                              "ms_per_step": e2e_sampled_s * 1e3,
+                                              "h2d_bytes_per_step": int(h_off.numel() * 4)}},
             "gpu_launches": int(launches * world),
             "clocks": clocks,
-            "detect": detect,
+            "multi_gpu": multi,
+            "detect": None,
         }
+        if detect is not None:
+            detect = dict(detect)
+            detect["tta_aggregate"] = tta
+            detect["post_processing"] = post
+            # the detect core numbers go LAST so that they are what a tail of this line shows
+            core = {k: detect.pop(k) for k in ["config", "labels_equal_reference_golden", "cpu_baseline", "e2e", "roofline",
+                                               "metric", "unit", "ms_per_volume", "value"]}
+            ordered = {k: detect[k] for k in ["tta_aggregate", "post_processing", "abi_calls_per_volume"]}
+            ordered.update(core)
+            line["detect"] = ordered
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Narrow this process to the CPUs of the NUMA node its GPU hangs off, so that pinned staging buffers are
+    first-touched there.  Returns a short description (or why it was not done)."""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank)
+        pci = f"{bus.pci_domain_id:04x}:{bus.pci_bus_id:02x}:{bus.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{pci}/numa_node").read())
+        if node < 0:
+            return f"gpu {pci}: no NUMA information"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return f"gpu {pci} on node {node}, {len(allowed)} cpus"
+    except Exception as e:  # noqa: BLE001
+        return f"not bound ({type(e).__name__})"
+
+
+# ------------------------------------------------------------------------------- B200 arm: multi-GPU inference
+SHARD_SHAPE, SHARD_OBJECTS, SHARD_BW = (272, 272, 272), 855, 10.0  # ~3.6 M foreground voxels, every one a seed
+
+
+def bench_multi_gpu(dev, rank, world, dist):
+    """Wall-clock jobs on the multi-GPU inference paths.
+
+    sharded_volume: ONE 272^3 volume whose foreground voxels are all seeds; every rank compacts its z-slab, the
+        point set is all-gathered, each rank climbs its slice of the seeds, (mode, count) are all-gathered,
+        suppression is replicated, labels are assigned per slab.  Job = max over ranks of the device time of
+        `sharded_mean_shift` (3 runs, last one reported, phases from CUDA events).  The N-rank centres and label
+        checksums are asserted equal to the 1-rank pipeline run on rank 0.
+    blockwise: BASELINE configs[4] -- a 16384^2 mosaic and a 1024^3 volume, scan blocks dealt round-robin; per
+        block the T = 32 TTA predictions are generated on the device, aggregated, detected and the uint16 labels are
+        copied to pinned host memory.  Job = ONE time.perf_counter around the whole loop per rank (generation,
+        launches, host syncs, copies all inside), max over ranks.
+    """
+    from cellulus_b200 import kernels as K
+    from cellulus_b200 import sharding, synthetic
+    from cellulus_b200.detect import detect_embeddings
+    from cellulus_b200.models import tta_aggregate
+    from cellulus_b200.utils.mean_shift import segment_embeddings_device
+
+    def allmax(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def allsum(x):
+        t = torch.tensor([x], device=dev, dtype=torch.int64)
+        if dist is not None:
+            dist.all_reduce(t)
+        return int(t.item())
+
+    out = {}
+    # ---- one volume, seeds sharded
+    emb, _, _ = synthetic.blob_scene(SHARD_SHAPE, SHARD_OBJECTS, radius=10.0, seed=0)
+    zs = sharding.shard_items(SHARD_SHAPE[0], rank, world)
+    slab = torch.from_numpy(np.ascontiguousarray(emb[:, zs.start:zs.stop])).to(dev)
+    pts, pix, n_local, _ = K.fg_compact(slab, 0.5)
+    pts[2, :n_local] += float(zs.start)  # z of the slab inside the volume (column 2 = z)
+    ops = sharding.cuda_ops("grid")
+    phases, ms = {}, 0.0
+    for _ in range(3):
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        phases = {}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        labels, centres = sharding.sharded_mean_shift(pts, n_local, SHARD_BW, ops, None, None, timings=phases)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = allmax(e0.elapsed_time(e1))
+    n_fg = allsum(n_local)
+    checksum = allsum(int((labels.to(torch.int64) * (torch.arange(n_local, device=dev) % 1009 + 1)).sum().item()))
+    equal = None
+    if rank == 0:  # the 1-rank pipeline on the whole volume: same centres, same labels
+        whole = torch.from_numpy(emb).to(dev)
+        ref_labels, info = segment_embeddings_device(whole, SHARD_BW, 0.5, 1.0, method="grid")
+        ref = ref_labels[whole[3] < 0.5].to(torch.int64)
+        bounds = [0]
+        for r in range(world):
+            z = sharding.shard_items(SHARD_SHAPE[0], r, world)
+            bounds.append(int((whole[3, :z.stop] < 0.5).sum().item()))
+        ref_sum = 0
+        for r in range(world):
+            seg = ref[bounds[r]:bounds[r + 1]]
+            ref_sum += int((seg * (torch.arange(seg.numel(), device=dev) % 1009 + 1)).sum().item())
+        same_centres = bool(torch.equal(info["centres"], centres))
+        equal = bool(same_centres and ref_sum == checksum)
+        assert equal, f"sharded mean-shift differs from the 1-rank pipeline (centres equal: {same_centres})"
+        del whole, ref_labels, ref
+    out["sharded_volume"] = {
+        "workload": f"one {SHARD_SHAPE[0]}^3 volume, {n_fg} foreground voxels, all of them seeds, bw {SHARD_BW}",
+        "n_gpus": world, "job_ms": ms, "fg_points_per_s": n_fg / ms * 1e3, "centres": int(centres.shape[1]),
+        "equals_one_rank_pipeline": equal, "collectives": "2 x all_gather (points; modes + counts), 1 x all_reduce (sizes)",
+        "phases_ms_rank0": {k: round(v, 3) for k, v in phases.items()}}
+    del slab, pts, pix, labels, emb
+    # ---- blockwise inference, BASELINE configs[4]
+    for kind, total, block in (("mosaic_16384x16384", (16384, 16384), (1024, 1024)),
+                               ("volume_1024x1024x1024", (1024, 1024, 1024), (128, 256, 256))):
+        nd = len(block)
+        blocks = sharding.scan_blocks(total, block)
+        mine = [blocks[i] for i in sharding.shard_round_robin(len(blocks), rank, world)]
+        host = torch.empty((1, *block), dtype=torch.uint16).pin_memory()
+        st = synthetic.block_stack(block, 10.0, 32, 10_000 + rank, dev)  # warm-up block
+        detect_embeddings(tta_aggregate(st), bandwidth=7.0, threshold=0.5 * nd, reduction_probability=0.1, rng="philox")
+        del st
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        labelled = 0
+        for b in mine:
+            seed = int(np.ravel_multi_index(tuple(o // s for o, s in zip(b, block)),
+                                            tuple(t // s + 1 for t, s in zip(total, block))))
+            st = synthetic.block_stack(block, 10.0, 32, seed, dev)
+            emb_b = tta_aggregate(st)
+            labels_b, _, _ = detect_embeddings(emb_b, bandwidth=7.0, threshold=0.5 * nd, reduction_probability=0.1,
+                                               rng="philox")
+            host.copy_(labels_b, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            labelled += int(np.count_nonzero(host.numpy()))
+            del st, emb_b, labels_b
+        job_s = allmax(time.perf_counter() - t0)
+        px = float(np.prod(block)) * len(blocks)
+        out[kind] = {"workload": f"configs[4]: {'x'.join(map(str, total))} in {len(blocks)} scan blocks of "
+                                 f"{'x'.join(map(str, block))}, T=32 predictions generated on the device + TTA aggregate + "
+                                 "detect (bw 7, rp 0.1) + labels to pinned host",
+                     "n_gpus": world, "job_s": job_s, "Mpx_per_s": px / job_s / 1e6, "foreground_px": allsum(labelled),
+                     "blocks_per_gpu_max": -(-len(blocks) // world),
+                     "timing": "one perf_counter around the whole job per rank, max over ranks"}
+    return out
 
 
 def main():

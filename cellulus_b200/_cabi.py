@@ -40,6 +40,8 @@ class DetectInfo(C.Structure):
         ("n_centres", C.c_int32),
         ("suppress_calls", C.c_int32),
         ("grid", Grid),
+        ("distance_tests", C.c_int64),
+        ("climb_steps", C.c_int64),
     ]
 
 
@@ -54,6 +56,7 @@ _pi64 = C.POINTER(C.c_int64)
 PROTOTYPES = {
     "cb200_version": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "cb200_error_string": (C.c_char_p, [_i]),
+    "cb200_fma_peak": (_i, [_i, _i, _i, _p, _pi64, _p]),
     "cb200_oce_loss_workspace_bytes": (_i64, []),
     "cb200_oce_loss_fwd_bwd": (_i, [_p, _i, _i, _p, _p, _i, _i, _i, _pi64, _i64, _f, _f, _p, _p, _p, _p]),
     "cb200_scale_inplace": (_i, [_p, _i64, _p, _p]),

@@ -194,7 +194,7 @@ extern "C" int cb200_detect_volume(const void* emb, int dtype, int num_dims, con
   CB200_CUDA_TRY(pool.get(&cell_start, (size_t)grid.n_cells + 1));
   CB200_CUDA_TRY(pool.get(&counts, (size_t)n_fit));
   CB200_CUDA_TRY(pool.get(&iters, (size_t)n_fit));
-  CB200_CUDA_TRY(pool.get(&work, 1));
+  CB200_CUDA_TRY(pool.get(&work, 8));
   CB200_CUDA_TRY(pool.get(&build_ws, (size_t)build_bytes));
   CB200_TRY_RC(cb200_grid_build(fit, n_fit, fit_stride, &grid, sorted, fit_cap, nullptr, cell_start, build_ws,
                                 build_bytes, st));
@@ -203,7 +203,7 @@ extern "C" int cb200_detect_volume(const void* emb, int dtype, int num_dims, con
                                    cudaMemcpyDeviceToDevice, st));
   CB200_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * n_fit, st));
   CB200_CUDA_TRY(cudaMemsetAsync(iters, 0, sizeof(int) * n_fit, st));
-  CB200_CUDA_TRY(cudaMemsetAsync(work, 0, sizeof(int), st));
+  CB200_CUDA_TRY(cudaMemsetAsync(work, 0, 8 * sizeof(int), st));
   CB200_TRY_RC(cb200_ms_grid_modes(sorted, n_fit, fit_cap, &grid, cell_start, modes, fit_cap, n_fit, bandwidth,
                                    max_iter > 0 ? max_iter : 300, counts, iters, work, st));
   info->n_seeds = n_fit;
@@ -218,6 +218,8 @@ extern "C" int cb200_detect_volume(const void* emb, int dtype, int num_dims, con
   CB200_CUDA_TRY(pool.get(&keep_dev, 2));
   CB200_CUDA_TRY(cudaMemsetAsync(keep_dev, 0, 2 * sizeof(int), st));
   int keep[2] = {0, 1};
+  long long stats[2] = {0, 0};  // the hill climb's work statistics ride on the first count read
+  CB200_CUDA_TRY(cudaMemcpyAsync(stats, work + 2, sizeof(stats), cudaMemcpyDeviceToHost, st));
   for (int call = 0; call < 64 && keep[1] != 0; ++call) {
     CB200_TRY_RC(cb200_nms_suppress(modes, fit_cap, D, counts, n_fit, bandwidth, &grid, 4, call > 0, keep_dev, nms_ws,
                                     nms_bytes, st));
@@ -226,6 +228,8 @@ extern "C" int cb200_detect_volume(const void* emb, int dtype, int num_dims, con
     ++info->suppress_calls;
   }
   lap("suppress");
+  info->distance_tests = stats[0];
+  info->climb_steps = stats[1];
   if (keep[1] != 0) return CB200_ENOCONVERGE;
   const int k_centres = keep[0];
   info->n_centres = k_centres;

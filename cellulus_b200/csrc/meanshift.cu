@@ -258,6 +258,8 @@ ms_grid_modes_kernel(const double* __restrict__ pts, int64_t pts_stride, GridDev
                      int64_t n_seeds, double r2, double stop, int max_iter, int* __restrict__ counts,
                      int* __restrict__ iters, int* __restrict__ work_counter) {
   const int lane = lane_id();
+  unsigned long long tests = 0;  // distance tests this lane made (statistics: the kernel's algorithmic work)
+  unsigned long long steps = 0;  // window evaluations (iterations + 1 per seed), counted by lane 0
   while (true) {
     int s = 0;
     if (lane == 0) s = atomicAdd(work_counter, 1);
@@ -301,6 +303,7 @@ ms_grid_modes_kernel(const double* __restrict__ pts, int64_t pts_stride, GridDev
                   ++cnt;
                 }
               }
+              tests += (unsigned)max(end - beg - lane + 31, 0) >> 5;
             }
           }
         }
@@ -326,7 +329,18 @@ ms_grid_modes_kernel(const double* __restrict__ pts, int64_t pts_stride, GridDev
       for (int k = 0; k < D; ++k) means[k * seed_stride + s] = m[k];
       counts[s] = n_within;
       iters[s] = it;
+      steps += (unsigned)it + 1u;
     }
+  }
+  // one statistics update per warp for the whole launch
+  tests += __shfl_xor_sync(FULL, tests, 16);
+  tests += __shfl_xor_sync(FULL, tests, 8);
+  tests += __shfl_xor_sync(FULL, tests, 4);
+  tests += __shfl_xor_sync(FULL, tests, 2);
+  tests += __shfl_xor_sync(FULL, tests, 1);
+  if (lane == 0 && tests) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(work_counter + 2), tests);
+    atomicAdd(reinterpret_cast<unsigned long long*>(work_counter + 4), steps);
   }
 }
 

@@ -50,6 +50,16 @@ def threshold_otsu(std: torch.Tensor, nbins: int = 256):
     return float(otsu_from_histogram(counts, edges))
 
 
+def _warn_if_labels_wrap(k: int, sample, bandwidth) -> None:
+    """the detection dataset is uint16 (`detect.py:30,161`); int32 labels above 65 535 are
+    silently narrowed there.  The dtype is kept (zarr layout contract) but the wrap is reported."""
+    if k > 65535:
+        import warnings
+
+        warnings.warn(f"sample {sample}, bandwidth {bandwidth}: {k} instances exceed the uint16 range of the "
+                      "`detection` dataset (cellulus/detect.py:30); labels above 65535 wrap around, as in the reference")
+
+
 def detect_embeddings(embeddings, bandwidth, threshold=None, num_bandwidths=1, reduction_probability=0.1,
                       seeds=None, rng="numpy", method="auto", label_dtype=torch.uint16, return_info=False,
                       one_call=None):
@@ -73,10 +83,67 @@ def detect_embeddings(embeddings, bandwidth, threshold=None, num_bandwidths=1, r
             label_dtype=label_dtype, want_mask=(k == 0), one_call=one_call)
         if k == 0:
             mask = info.pop("mask")
+        if label_dtype == torch.uint16:
+            _warn_if_labels_wrap(int(info.get("k", 0)), "?", bandwidth / (2**k))
         out.append(labels)
         infos.append(info)
     result = (torch.stack(out, 0), threshold, mask)
     return result + (infos,) if return_info else result
+
+
+def _detect_sample_sharded(cfg, ds, sample, nd, device, rank, world, ds_detection, ds_binary, ds_centred):
+    """One sample, all ranks: rank 0 does the O(N) preamble on the whole sample (threshold, mask, centring --
+    `detect.py:88-119`), every rank compacts its slab of the slowest axis and the mean-shift runs seed-sharded
+    (`sharding.sharded_mean_shift`: two all-gathers).  Results are identical to the single-GPU path."""
+    import torch.distributed as dist
+
+    spatial = tuple(ds.shape[2:])
+    thr_t = torch.zeros(1, dtype=torch.float64, device=device)
+    if rank == 0:
+        emb = torch.from_numpy(np.ascontiguousarray(ds[sample])).to(device)
+        threshold = cfg.threshold if cfg.threshold is not None else threshold_otsu(emb[nd])
+        print(f"For sample {sample}, binary threshold {threshold} was used.")
+        _, centred = K.centre_embeddings(emb, threshold)
+        ds_binary[sample, 0, ...] = (emb[nd] < threshold).cpu().numpy().astype(np.uint16)
+        ds_centred[sample] = centred.cpu().numpy()
+        thr_t[0] = threshold
+        del emb, centred
+    dist.broadcast(thr_t, 0)
+    threshold = float(thr_t.item())
+    rows = sharding.shard_items(spatial[0], rank, world)  # slab of the slowest spatial axis: rank order = raster order
+    slab_np = np.ascontiguousarray(ds[(sample, slice(None), slice(rows.start, rows.stop))])
+    slab = torch.from_numpy(slab_np).to(device)
+    pts, pix, n_local, _ = K.fg_compact(slab, threshold) if len(rows) else (torch.zeros((nd, 2), dtype=torch.float64,
+                                                                                          device=device), None, 0, None)
+    if n_local:
+        pts[nd - 1, :n_local] += float(rows.start)  # column nd-1 is the slowest axis (z in 3-D, y in 2-D)
+    counts = torch.zeros(world, dtype=torch.int64, device=device)
+    counts[rank] = n_local
+    dist.all_reduce(counts)
+    n_total, start = int(counts.sum()), int(counts[:rank].sum())
+    out = []
+    for k in range(cfg.num_bandwidths):
+        bandwidth = cfg.bandwidth / (2**k)
+        labels_slab = torch.zeros((len(rows), *spatial[1:]), dtype=torch.int32, device=device)
+        if n_total:
+            flags_local = None
+            if cfg.reduction_probability < 1.0:  # `np.random.rand(N) < p` over ALL points (utils/mean_shift.py:68-70)
+                flags = torch.zeros(n_total, dtype=torch.uint8, device=device)
+                if rank == 0:
+                    flags.copy_(torch.from_numpy((np.random.rand(n_total) < cfg.reduction_probability).astype(np.uint8)))
+                dist.broadcast(flags, 0)
+                flags_local = flags[start:start + n_local]
+            labels, centres = sharding.sharded_mean_shift(pts, n_local, bandwidth, sharding.cuda_ops("auto"), flags_local)
+            if n_local:
+                labels_slab.view(-1)[pix[:n_local].long()] = labels.to(torch.int32)
+            if rank == 0:
+                _warn_if_labels_wrap(int(centres.shape[1]), sample, bandwidth)
+        out.append(labels_slab.to(torch.uint16))
+    mine = torch.stack(out, 0).cpu().numpy()  # (num_bandwidths, rows, ...)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(mine, gathered, dst=0)
+    if rank == 0:
+        ds_detection[sample] = np.concatenate(gathered, axis=1)
 
 
 def detect(inference_config) -> None:
@@ -103,6 +170,15 @@ def detect(inference_config) -> None:
     if world > 1:
         torch.distributed.barrier()
     ds_detection, ds_binary, ds_centred = f[cfg.dataset_name], f["binary-segmentation"], f["centered-embeddings"]
+    if (world > 1 and meta.num_samples < world and inference_config.clustering == "meanshift"
+            and not inference_config.use_seeds):
+        # fewer samples than GPUs: every sample is split BY SEED over all ranks (north_star: "a single huge
+        # volume is split by seed with an NCCL all-gather of the point set") instead of leaving ranks idle
+        for sample in range(meta.num_samples):
+            _detect_sample_sharded(inference_config, ds, sample, nd, device, rank, world, ds_detection, ds_binary,
+                                   ds_centred)
+        torch.distributed.barrier()
+        return
     for sample in sharding.shard_round_robin(meta.num_samples, rank, world):
         emb = torch.from_numpy(np.ascontiguousarray(ds[sample])).to(device)  # float64, as stored
         threshold = inference_config.threshold

@@ -76,6 +76,25 @@ def _zero_workspace(kind: str, nbytes: int, device: torch.device) -> torch.Tenso
     return ws
 
 
+def fma_peak_tflops(dtype=torch.float64, device=None, iters: int = 4096, reps: int = 5) -> float:
+    """Measured FMA peak (TFLOP/s) of the FP32 / FP64 pipe of `device` (`cb200_fma_peak`, CUDA events, best of reps)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out = torch.zeros(2, dtype=torch.float64, device=device)
+    flop = C.c_int64(0)
+    code = _DTYPE_CODE[dtype]
+    best = 0.0
+    with torch.cuda.device(device):
+        st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        for _ in range(reps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            check(_lib().cb200_fma_peak(code, iters, 8, _ptr(out), C.byref(flop), st), "cb200_fma_peak")
+            e1.record()
+            e1.synchronize()
+            best = max(best, flop.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
 # --------------------------------------------------------------------------- loss slice
 _COORD_DTYPES = (torch.int64, torch.int32, torch.int16)
 _OFFSET_DTYPES = (torch.float32, torch.bfloat16)
@@ -475,18 +494,35 @@ def grid_build(points: torch.Tensor, n: int, grid: Grid, want_order: bool = Fals
     return sorted_pts, cell_start, order
 
 
+# the work buffer of the most recent `ms_grid_modes` call; `grid_modes_distance_tests()` reads its statistic
+last_grid_modes_work = [None]
+
+
+def grid_modes_distance_tests() -> int:
+    """Distance tests (seed x candidate point evaluations) made by the most recent `ms_grid_modes` call."""
+    w = last_grid_modes_work[0]
+    return 0 if w is None else int(w[2:4].view(torch.int64).item())
+
+
+def grid_modes_climb_steps() -> int:
+    """Sum over seeds of (iterations + 1) of the most recent `ms_grid_modes` call."""
+    w = last_grid_modes_work[0]
+    return 0 if w is None else int(w[4:6].view(torch.int64).item())
+
+
 def ms_grid_modes(sorted_pts, n, grid, cell_start, seeds_soa, n_seeds, bandwidth, max_iter=300):
     """Climb every seed to convergence (grid-hash form).  `seeds_soa` (D, cap) is updated IN PLACE to the modes.
     Returns `(counts, iters)` int32 device tensors."""
     dev = sorted_pts.device
     counts = torch.zeros(max(n_seeds, 1), dtype=torch.int32, device=dev)
     iters = torch.zeros(max(n_seeds, 1), dtype=torch.int32, device=dev)
-    work = torch.zeros(1, dtype=torch.int32, device=dev)
+    work = torch.zeros(8, dtype=torch.int32, device=dev)  # [0] claim counter, [2:4] / [4:6] uint64 statistics
     rc = _lib().cb200_ms_grid_modes(_ptr(sorted_pts), n, sorted_pts.stride(0), C.byref(grid), _ptr(cell_start),
                                     _ptr(seeds_soa), seeds_soa.stride(0), n_seeds, float(bandwidth), int(max_iter),
                                     _ptr(counts), _ptr(iters), _ptr(work), _stream(sorted_pts))
     check(rc, "cb200_ms_grid_modes")
     launch_counter["calls"] += 1
+    last_grid_modes_work[0] = work
     return counts, iters
 
 
@@ -797,7 +833,8 @@ def detect_volume(emb: torch.Tensor, bandwidth: float, threshold: float, reducti
     check(rc, "cb200_detect_volume")
     return labels, mask, centres, {"n_fg": int(info.n_foreground), "n_fit": int(info.n_fit),
                                    "n_seeds": int(info.n_seeds), "k": int(info.n_centres), "method": "grid",
-                                   "grid_cells": int(info.grid.n_cells), "suppress_calls": int(info.suppress_calls)}
+                                   "grid_cells": int(info.grid.n_cells), "suppress_calls": int(info.suppress_calls),
+                                   "distance_tests": int(info.distance_tests), "climb_steps": int(info.climb_steps)}
 
 
 def release_scratch(device=None) -> None:

@@ -94,18 +94,41 @@ class MeanShiftOps:
     assign: Callable
 
 
+class _PhaseTimer:
+    """CUDA-event stopwatch for the phases of `sharded_mean_shift` (device time, this rank)."""
+
+    def __init__(self, enabled, device):
+        self.on = enabled and device.type == "cuda"
+        self.marks = []
+        self.device = device
+
+    def mark(self, name):
+        if self.on:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.marks.append((name, e))
+
+    def result(self):
+        if not self.on or len(self.marks) < 2:
+            return {}
+        torch.cuda.synchronize(self.device)
+        return {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(self.marks[:-1], self.marks[1:])}
+
+
 def sharded_mean_shift(local_points: torch.Tensor, n_local: int, bandwidth: float, ops: MeanShiftOps,
-                       local_fit_flags: Optional[torch.Tensor] = None, group=None):
+                       local_fit_flags: Optional[torch.Tensor] = None, group=None, timings: Optional[dict] = None):
     """Mean-shift of one point set that is spread over the ranks (slab order = rank order).
 
     local_points (D, >= n_local) float64 SoA: this rank's foreground points in raster order.
     local_fit_flags (n_local,) uint8/bool or None: which of them take part in `fit` (the
     `reduction_probability` subset, `utils/mean_shift.py:68-70`).
     Returns `(labels_local (n_local,), centres (D, k))`; identical to running the single-GPU pipeline on
-    the concatenated point set.
+    the concatenated point set.  `timings` (optional dict) receives the device milliseconds per phase.
     """
     rank, world = _world(group)
     D = local_points.shape[0]
+    clock = _PhaseTimer(timings is not None, local_points.device)
+    clock.mark("start")
     if local_fit_flags is None:
         fit_local, n_fit_local = local_points[:, :n_local], n_local
     else:
@@ -114,6 +137,7 @@ def sharded_mean_shift(local_points: torch.Tensor, n_local: int, bandwidth: floa
         n_fit_local = int(keep.sum())
     # exchange 1: every rank needs the whole fit set (N x D doubles; O(ms) over NVSwitch)
     fit_all, _ = all_gather_columns(fit_local.contiguous(), n_fit_local, group)
+    clock.mark("gather_points")
     n_fit = fit_all.shape[1]
     if n_fit == 0:
         raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required by MeanShift.")
@@ -121,21 +145,31 @@ def sharded_mean_shift(local_points: torch.Tensor, n_local: int, bandwidth: floa
     mine = shard_items(n_fit, rank, world)
     seeds = fit_all[:, mine.start:mine.stop].contiguous()
     modes, counts, _ = ops.climb(fit_all, seeds, bandwidth)
+    clock.mark("climb")
     # exchange 2: converged (mode, count) of every seed, in global seed order
     packed = torch.cat([modes[:, :len(mine)], counts[:len(mine)].to(modes.dtype)[None]], dim=0)
     packed_all, _ = all_gather_columns(packed.contiguous(), len(mine), group)
     modes_all = packed_all[:D].contiguous()
     counts_all = packed_all[D].round().to(torch.int32).contiguous()
+    clock.mark("gather_modes")
     # centre suppression is deterministic: replicate it instead of broadcasting its result
     centres = ops.suppress(modes_all, counts_all, bandwidth, fit_all)
+    clock.mark("suppress")
     labels = ops.assign(local_points[:, :n_local].contiguous(), centres)
+    clock.mark("assign")
+    if timings is not None:
+        timings.update(clock.result())
     return labels, centres
 
 
 def cuda_ops(method: str = "auto") -> MeanShiftOps:
-    """`MeanShiftOps` on the B200 kernels."""
+    """`MeanShiftOps` on the B200 kernels.  The three steps share one cell grid (edge >= bandwidth over the
+    bounding box of the fit points): the hill climb hashes the points into it, the suppression derives its fine
+    grid from it, the label assignment hashes the centres into it (pruned nearest-centre search)."""
     from cellulus_b200 import kernels as K
     from cellulus_b200.utils import mean_shift as MS
+
+    ctx = {}
 
     def pad(t):  # kernels want an even stride (16-byte bulk copies)
         n = t.shape[1]
@@ -146,15 +180,21 @@ def cuda_ops(method: str = "auto") -> MeanShiftOps:
         out[:, :n] = t
         return out
 
+    def grid_of(points, bandwidth):
+        key = (points.data_ptr(), points.shape[1], float(bandwidth))
+        if ctx.get("key") != key:
+            lo, hi = K.bounding_box(pad(points), points.shape[1])
+            ctx["key"], ctx["grid"] = key, K.plan_grid(lo, hi, bandwidth)
+        return ctx["grid"]
+
     def climb(points, seeds, bandwidth):
         n, s = points.shape[1], seeds.shape[1]
         pts, sd = pad(points), pad(seeds)
+        grid = grid_of(points, bandwidth)
         use = method
         if use == "auto":
             use = "brute" if n * s <= MS._BRUTE_PAIR_LIMIT else "grid"
         if use == "grid":
-            lo, hi = K.bounding_box(pts, n)
-            grid = K.plan_grid(lo, hi, bandwidth)
             sorted_pts, cell_start, _ = K.grid_build(pts, n, grid)
             counts, iters = K.ms_grid_modes(sorted_pts, n, grid, cell_start, sd, s, bandwidth)
         else:
@@ -162,9 +202,7 @@ def cuda_ops(method: str = "auto") -> MeanShiftOps:
         return sd[:, :s], counts[:s], iters[:s]
 
     def suppress(modes, counts, bandwidth, points):
-        n = points.shape[1]
-        lo, hi = K.bounding_box(pad(points), n)
-        grid = K.plan_grid(lo, hi, bandwidth)
+        grid = grid_of(points, bandwidth)
         m = pad(modes)
         centres, k = K.nms_centres(m, counts.contiguous(), modes.shape[1], bandwidth, grid)
         if k == 0:
@@ -175,7 +213,7 @@ def cuda_ops(method: str = "auto") -> MeanShiftOps:
         n = points.shape[1]
         labels = torch.zeros(max(n, 1), dtype=torch.int32, device=points.device)
         if n:
-            K.assign_labels(pad(points), n, pad(centres), centres.shape[1], None, labels)
+            K.assign_labels(pad(points), n, pad(centres), centres.shape[1], None, labels, grid=ctx.get("grid"))
         return labels[:n]
 
     return MeanShiftOps(climb, suppress, assign)

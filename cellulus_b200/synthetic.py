@@ -93,3 +93,33 @@ def scene_for_points(num_points: int, num_dims: int, radius: float = 10.0, seed:
     side = int(np.ceil(total ** (1.0 / num_dims)))
     side = max(side, int(4 * radius))
     return (side,) * num_dims, num_objects
+
+
+def block_stack(shape, radius, T, seed, dev):
+    """T noisy predictions (T, D, *shape) of a jittered-lattice blob scene, built with torch ON THE DEVICE `dev`
+    (stands for the T test-time-augmentation passes of the U-Net over one scan block, BASELINE configs[4])."""
+    import torch
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    D = len(shape)
+    spacing = 2.6 * radius
+    cells = [int(np.ceil(s / spacing)) + 2 for s in shape]
+    centres = (torch.stack(torch.meshgrid(*[torch.arange(c, device=dev) for c in cells], indexing="ij"), -1).float()
+               - 0.5) * spacing + (torch.rand((*cells, D), generator=g, device=dev) - 0.5) * (spacing - 2 * radius)
+    coords = torch.stack(torch.meshgrid(*[torch.arange(s, device=dev) for s in shape], indexing="ij"), -1).float()
+    ci = torch.floor(coords / spacing + 1.0).long().clamp_(min=0)
+    best_d = torch.full(shape, 1e9, device=dev)
+    best_c = torch.zeros((*shape, D), device=dev)
+    for off in np.ndindex(*(3,) * D):
+        idx = [(ci[..., k] + off[k] - 1).clamp_(0, cells[k] - 1) for k in range(D)]
+        c = centres[tuple(idx)]
+        d = ((coords - c) ** 2).sum(-1)
+        closer = d < best_d
+        best_d = torch.where(closer, d, best_d)
+        best_c = torch.where(closer[..., None], c, best_c)
+    fg = best_d <= radius * radius
+    base = torch.where(fg[..., None], best_c - coords, torch.zeros_like(coords))
+    base = base.flip(-1).movedim(-1, 0)  # channel 0 = x (last axis)
+    sigma = torch.where(fg, 0.02, 1.0)[None, None]
+    return base[None] + sigma * torch.randn((T, D, *shape), generator=g, device=dev)

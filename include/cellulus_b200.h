@@ -60,6 +60,13 @@ CB200_API int cb200_version(int* major, int* minor, int* sm_arch);
 /* last CUDA error string for a positive return code */
 CB200_API const char* cb200_error_string(int code);
 
+/* Measurement aid (bench.py): runs blocks_per_sm * 148 blocks of 256 threads, 8 independent FMA chains per
+ * thread, `iters` rounds, in CB200_F32 or CB200_F64; *flop (host out) = the floating-point operations issued.
+ * Timed with CUDA events by the caller it gives the device's FMA peak, the roofline denominator of the
+ * mean-shift kernels.  `out`: 8 bytes of device scratch. */
+CB200_API int cb200_fma_peak(int dtype, int iters, int blocks_per_sm, void* out, int64_t* flop /* host out */,
+                   void* stream);
+
 /* ===================================================================== *
  *  Loss slice (training)                                                *
  * ===================================================================== */
@@ -297,7 +304,10 @@ CB200_API int cb200_ms_grid_modes(const double* points_sorted, int64_t n_points,
                         const cb200_grid* grid, const int* cell_start,
                         double* means, int64_t seed_stride, int64_t n_seeds,
                         double bandwidth, int max_iter, int* counts, int* iters,
-                        int* work_counter /* device int, zero */, void* stream);
+                        int* work_counter /* device, 32 bytes, zeroed by the caller: [0] seed claim
+                                             counter; bytes 8..15: uint64 statistic, distance tests made;
+                                             bytes 16..23: uint64 sum over seeds of (iterations + 1) */,
+                        void* stream);
 
 /*
  * Centre post-processing, sklearn:511-547: drop empty seeds, order by
@@ -358,6 +368,8 @@ typedef struct cb200_detect_info {
   int32_t n_centres;
   int32_t suppress_calls;
   cb200_grid grid;
+  int64_t distance_tests; /* seed x candidate evaluations of the hill climb (its algorithmic work) */
+  int64_t climb_steps;    /* sum over seeds of (iterations + 1): window evaluations */
 } cb200_detect_info;
 
 CB200_API int cb200_detect_volume(const void* emb, int dtype, int num_dims, const int64_t* spatial, double threshold,

@@ -725,6 +725,33 @@ def test_detect_full_pipeline_3d_properties():
 
 
 # ----------------------------------------------------------------------------- size filter
+def test_detect_full_size_config2_equals_reference_golden():
+    """BASELINE configs[2] at FULL size (128 x 256 x 256, 1.48 M foreground voxels, 148 k seeds): the drop-in
+    `mean_shift_segmentation` returns, label for label, what the REFERENCE returned on the same volume under the
+    same numpy seed (tests/golden/config2_labels.npz, written by tests/golden/make_golden_config2.py from
+    /root/reference: 220 s of scikit-learn on the authoring host)."""
+    import os
+
+    from cellulus_b200.utils.mean_shift import mean_shift_segmentation
+
+    path = os.path.join(os.path.dirname(__file__), "golden", "config2_labels.npz")
+    g = np.load(path)
+    bw, rp, thr, radius, objects = (float(v) for v in g["cfg"])
+    shape = tuple(int(v) for v in g["shape"])
+    emb, _, _ = synthetic.blob_scene(shape, int(objects), radius=radius, seed=0)
+    emb64 = emb.astype(np.float64)
+    mean_in = emb64[np.newaxis, :3].copy()
+    np.random.seed(0)
+    labels = mean_shift_segmentation(mean_in, emb64[3], bandwidth=bw, min_size=0, reduction_probability=rp,
+                                     threshold=thr, seeds=None)
+    gold = g["labels"].astype(np.int32)
+    assert labels.dtype == np.int32 and labels.shape == gold.shape
+    assert int((labels > 0).sum()) == int(g["foreground"])
+    assert np.array_equal(labels, gold)  # identical incl. numbering: ARI = 1 >= 0.999
+    # the reference's in-place side effect on its first argument (utils/mean_shift.py:15-32)
+    assert np.array_equal(mean_in[0, 0], emb64[0] + np.arange(shape[2])[None, None, :])
+
+
 @pytest.mark.parametrize("shape", [(64, 80), (10, 30, 34), (1, 9), (300, 300)])
 def test_size_filter_exact(shape):
     from cellulus_b200 import kernels as K

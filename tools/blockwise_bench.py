@@ -20,33 +20,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cellulus_b200 import sharding  # noqa: E402
 from cellulus_b200.detect import detect_embeddings  # noqa: E402
 from cellulus_b200.models import tta_aggregate  # noqa: E402
-
-
-def block_stack(shape, radius, T, seed, dev):
-    """T noisy predictions (T, D, *shape) of a jittered-lattice blob scene, built with torch on the device."""
-    g = torch.Generator(device=dev)
-    g.manual_seed(seed)
-    D = len(shape)
-    spacing = 2.6 * radius
-    cells = [int(np.ceil(s / spacing)) + 2 for s in shape]
-    centres = (torch.stack(torch.meshgrid(*[torch.arange(c, device=dev) for c in cells], indexing="ij"), -1).float()
-               - 0.5) * spacing + (torch.rand((*cells, D), generator=g, device=dev) - 0.5) * (spacing - 2 * radius)
-    coords = torch.stack(torch.meshgrid(*[torch.arange(s, device=dev) for s in shape], indexing="ij"), -1).float()
-    ci = torch.floor(coords / spacing + 1.0).long().clamp_(min=0)
-    best_d = torch.full(shape, 1e9, device=dev)
-    best_c = torch.zeros((*shape, D), device=dev)
-    for off in np.ndindex(*(3,) * D):
-        idx = [(ci[..., k] + off[k] - 1).clamp_(0, cells[k] - 1) for k in range(D)]
-        c = centres[tuple(idx)]
-        d = ((coords - c) ** 2).sum(-1)
-        closer = d < best_d
-        best_d = torch.where(closer, d, best_d)
-        best_c = torch.where(closer[..., None], c, best_c)
-    fg = best_d <= radius * radius
-    base = torch.where(fg[..., None], best_c - coords, torch.zeros_like(coords))
-    base = base.flip(-1).movedim(-1, 0)  # channel 0 = x (last axis)
-    sigma = torch.where(fg, 0.02, 1.0)[None, None]
-    return base[None] + sigma * torch.randn((T, D, *shape), generator=g, device=dev)
+from cellulus_b200.synthetic import block_stack  # noqa: E402
 
 
 def run(kind, scale, dev, rank, world):
