@@ -56,6 +56,19 @@ def scan_blocks(spatial: Sequence[int], block: Sequence[int]) -> List[Tuple[int,
     return out
 
 
+SEED_CHUNK = 2048
+
+
+def seed_indices(n_seeds: int, rank: int, world: int, device=None) -> torch.Tensor:
+    """Indices of the seeds `rank` climbs: chunks rank, rank + world, ... of SEED_CHUNK consecutive seeds."""
+    if world == 1:
+        return torch.arange(n_seeds, device=device)
+    n_chunks = -(-n_seeds // SEED_CHUNK)
+    starts = torch.arange(rank, n_chunks, world, device=device) * SEED_CHUNK
+    idx = (starts[:, None] + torch.arange(SEED_CHUNK, device=device)[None, :]).reshape(-1)
+    return idx[idx < n_seeds]
+
+
 def _world(group) -> Tuple[int, int]:
     if not dist.is_available() or not dist.is_initialized():
         return 0, 1
@@ -141,14 +154,21 @@ def sharded_mean_shift(local_points: torch.Tensor, n_local: int, bandwidth: floa
     n_fit = fit_all.shape[1]
     if n_fit == 0:
         raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required by MeanShift.")
-    # seeds = all fit points (sklearn:491-496), split evenly; raster order keeps neighbours together
-    mine = shard_items(n_fit, rank, world)
-    seeds = fit_all[:, mine.start:mine.stop].contiguous()
+    # seeds = all fit points (sklearn:491-496), dealt to the ranks in chunks of SEED_CHUNK consecutive seeds
+    # (block-cyclic: climbing cost varies over the volume, a contiguous split leaves ranks waiting for the slowest)
+    idx = [seed_indices(n_fit, r, world, fit_all.device) for r in range(world)]
+    mine = idx[rank]
+    seeds = fit_all[:, mine].contiguous() if world > 1 else fit_all.clone()
     modes, counts, _ = ops.climb(fit_all, seeds, bandwidth)
     clock.mark("climb")
-    # exchange 2: converged (mode, count) of every seed, in global seed order
-    packed = torch.cat([modes[:, :len(mine)], counts[:len(mine)].to(modes.dtype)[None]], dim=0)
-    packed_all, _ = all_gather_columns(packed.contiguous(), len(mine), group)
+    # exchange 2: converged (mode, count) of every seed; put back into global seed order
+    n_mine = int(mine.numel())
+    packed = torch.cat([modes[:, :n_mine], counts[:n_mine].to(modes.dtype)[None]], dim=0)
+    packed_all, _ = all_gather_columns(packed.contiguous(), n_mine, group)
+    if world > 1:
+        ordered = torch.empty_like(packed_all)
+        ordered[:, torch.cat(idx)] = packed_all
+        packed_all = ordered
     modes_all = packed_all[:D].contiguous()
     counts_all = packed_all[D].round().to(torch.int32).contiguous()
     clock.mark("gather_modes")

@@ -95,9 +95,9 @@ def scene_for_points(num_points: int, num_dims: int, radius: float = 10.0, seed:
     return (side,) * num_dims, num_objects
 
 
-def block_stack(shape, radius, T, seed, dev):
-    """T noisy predictions (T, D, *shape) of a jittered-lattice blob scene, built with torch ON THE DEVICE `dev`
-    (stands for the T test-time-augmentation passes of the U-Net over one scan block, BASELINE configs[4])."""
+def block_scene(shape, radius, seed, dev):
+    """Noise-free embeddings of a jittered-lattice blob scene, built with torch ON THE DEVICE `dev`:
+    `(base (D, *shape) float32, foreground (*shape) bool, generator)`; channel 0 = x (last axis)."""
     import torch
 
     g = torch.Generator(device=dev)
@@ -120,6 +120,17 @@ def block_stack(shape, radius, T, seed, dev):
         best_c = torch.where(closer[..., None], c, best_c)
     fg = best_d <= radius * radius
     base = torch.where(fg[..., None], best_c - coords, torch.zeros_like(coords))
-    base = base.flip(-1).movedim(-1, 0)  # channel 0 = x (last axis)
+    base = base.flip(-1).movedim(-1, 0).contiguous()  # channel 0 = x (last axis)
+    return base, fg, g
+
+
+def block_stack(shape, radius, T, seed, dev):
+    """T noisy predictions (T, D, *shape) of a jittered-lattice blob scene, built with torch ON THE DEVICE `dev`
+    (stands for the T test-time-augmentation passes of the U-Net over one scan block, BASELINE configs[4]):
+    tight noise inside the objects (per-pixel std 0.02 per channel), unit noise outside."""
+    import torch
+
+    base, fg, g = block_scene(shape, radius, seed, dev)
+    D = len(shape)
     sigma = torch.where(fg, 0.02, 1.0)[None, None]
     return base[None] + sigma * torch.randn((T, D, *shape), generator=g, device=dev)

@@ -64,3 +64,69 @@ def test_seed_sharded_mean_shift_two_gpus():
     assert np.array_equal(got, ref)
     for r in range(2):
         assert np.array_equal(results[r][1], info["centres"].cpu().numpy())
+
+
+def _detect_worker(rank, world, port, container, results):
+    """One rank of `detect(inference_config)` under a torchrun-like environment."""
+    import torch.distributed as dist
+
+    from cellulus_b200.configs import DatasetConfig, InferenceConfig
+    from cellulus_b200.detect import detect
+
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank),
+                       "LOCAL_RANK": str(rank), "WORLD_SIZE": str(world)})
+    torch.cuda.set_device(rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        np.random.seed(5)  # rank 0 draws the fit subset (np.random.rand over all foreground points)
+        cfg = InferenceConfig(
+            dataset_config=DatasetConfig(container_path=container, dataset_name="embeddings"),
+            prediction_dataset_config=DatasetConfig(container_path=container, dataset_name="embeddings"),
+            detection_dataset_config=DatasetConfig(container_path=container, dataset_name=f"detection_w{world}",
+                                                   secondary_dataset_name="embeddings"),
+            segmentation_dataset_config=DatasetConfig(container_path=container, dataset_name="segmentation"),
+            evaluation_dataset_config=DatasetConfig(container_path=container, dataset_name="gt"),
+            device=f"cuda:{rank}", threshold=0.5, bandwidth=5.0, num_bandwidths=2, reduction_probability=0.3,
+            crop_size=[40, 96, 96])
+        detect(cfg)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+            os.environ.pop(k, None)
+
+
+@pytest.mark.timeout(600)
+def test_detect_splits_one_sample_by_seed_over_two_gpus(tmp_path):
+    """`detect()` with ONE sample on TWO ranks takes the seed-sharded path (two all-gathers); the `detection`
+    dataset it writes equals the one a single rank writes (same numpy seed for the fit subset)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    from cellulus_b200 import synthetic, zarr_lite
+
+    emb_np, _, _ = synthetic.blob_scene((40, 96, 96), 30, radius=8.0, seed=2)
+    container = str(tmp_path / "one_sample.zarr")
+    g = zarr_lite.open(container)
+    a = g.create_dataset("embeddings", shape=(1, 4, 40, 96, 96), dtype=float)
+    a[0] = emb_np.astype(np.float64)
+    a.attrs["axis_names"] = ["s", "c", "z", "y", "x"]
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    results = mp.Manager().dict()
+    # binary-segmentation / centered-embeddings are created with fixed names (detect.py:40-80): one container each
+    import shutil
+
+    container2 = str(tmp_path / "one_sample_w2.zarr")
+    shutil.copytree(container, container2)
+    mp.spawn(_detect_worker, args=(1, port, container, results), nprocs=1, join=True)
+    mp.spawn(_detect_worker, args=(2, port + 1, container2, results), nprocs=2, join=True)
+    one = zarr_lite.open(container, "r")["detection_w1"][...]
+    two = zarr_lite.open(container2, "r")["detection_w2"][...]
+    assert one.shape == (1, 2, 40, 96, 96) and one.dtype == np.uint16 and one.max() > 5
+    assert np.array_equal(one, two)
+    for name in ("binary-segmentation", "centered-embeddings"):
+        assert np.array_equal(zarr_lite.open(container, "r")[name][...], zarr_lite.open(container2, "r")[name][...])

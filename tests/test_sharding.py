@@ -24,6 +24,15 @@ def test_shard_ranges_cover_everything():
             assert rr == list(range(n))
 
 
+def test_seed_chunks_are_dealt_block_cyclic():
+    for n in [0, 1, 2047, 2048, 2049, 10_000]:
+        for world in [1, 2, 3, 8]:
+            parts = [sharding.seed_indices(n, r, world) for r in range(world)]
+            assert sorted(torch.cat(parts).tolist()) == list(range(n))
+            if world > 1 and n > sharding.SEED_CHUNK:
+                assert parts[1][0].item() == sharding.SEED_CHUNK  # rank 1 starts with the second chunk
+
+
 def test_scan_blocks_shift_last_block_inward():
     # gunpowder Scan semantics (predict.py:129): stride = block, last block shifted inward, never shrunk
     assert sharding.scan_blocks((10,), (4,)) == [(0,), (4,), (6,)]
@@ -66,6 +75,7 @@ def _worker(rank, world, port, results):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    sharding.SEED_CHUNK = 16  # a few hundred seeds here: small chunks so that both ranks climb interleaved ranges
     try:
         X, fit = _scene()
         mine = sharding.shard_items(len(X), rank, world)  # slab = contiguous raster range
