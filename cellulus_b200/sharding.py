@@ -64,6 +64,8 @@ def seed_indices(n_seeds: int, rank: int, world: int, device=None) -> torch.Tens
     if world == 1:
         return torch.arange(n_seeds, device=device)
     n_chunks = -(-n_seeds // SEED_CHUNK)
+    if rank >= n_chunks:
+        return torch.zeros(0, dtype=torch.int64, device=device)
     starts = torch.arange(rank, n_chunks, world, device=device) * SEED_CHUNK
     idx = (starts[:, None] + torch.arange(SEED_CHUNK, device=device)[None, :]).reshape(-1)
     return idx[idx < n_seeds]
