@@ -193,6 +193,137 @@ label_otsu_kernel(const unsigned int* __restrict__ hist, const int64_t* __restri
   threshold[l] = centre(best_i);
 }
 
+// Integer images (one bin per value, integer bin centres, float64 arithmetic): every cumulative sum above is a sum of
+// INTEGERS -- exact in float32 while a label has fewer than 2^24 pixels, exact in float64 always -- so the order of
+// summation cannot change a bit and the sequential recurrences can be replaced by block-wide scans: one BLOCK per
+// label, each thread a contiguous strip of bins, weight2 / the reversed sums as (total - prefix).  Labels with
+// 2^24 pixels or more (float32 rounding would depend on the order) fall back to the sequential recurrence on
+// thread 0.  Same thresholds, bit for bit, as label_otsu_kernel<double>.
+constexpr int OTSU_BLOCK = 256;
+
+template <typename T>
+__device__ __forceinline__ T otsu_block_exclusive_scan(T v, T* s_warp, T& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const T u = __shfl_up_sync(FULL, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  T base = 0, tot = 0;
+#pragma unroll
+  for (int k = 0; k < OTSU_BLOCK / 32; ++k) {
+    const T t = s_warp[k];
+    if (k < warp) base += t;
+    tot += t;
+  }
+  __syncthreads();
+  total = tot;
+  return base + inc - v;
+}
+
+__global__ void __launch_bounds__(OTSU_BLOCK)
+label_otsu_block_kernel(const unsigned int* __restrict__ hist, const int64_t* __restrict__ offset,
+                        const int64_t* __restrict__ nbins, const double* __restrict__ centre0, int n_labels,
+                        float* __restrict__ scratch_w, double* __restrict__ scratch_c, double* __restrict__ threshold) {
+  __shared__ double s_d[OTSU_BLOCK / 32];
+  __shared__ unsigned long long s_u[OTSU_BLOCK / 32];
+  __shared__ double s_best[OTSU_BLOCK / 32];
+  __shared__ long long s_best_i[OTSU_BLOCK / 32];
+  const int l = blockIdx.x;
+  if (l >= n_labels) return;
+  const int64_t off = offset[l], nb = nbins[l];
+  if (nb <= 0) return;
+  const double c0 = centre0[l];
+  if (nb == 1) {
+    if (threadIdx.x == 0) threshold[l] = c0;
+    return;
+  }
+  const int64_t strip = (nb + OTSU_BLOCK - 1) / OTSU_BLOCK;
+  const int64_t i0 = min((int64_t)threadIdx.x * strip, nb), i1 = min(i0 + strip, nb);
+  unsigned long long w_loc = 0;
+  double cs_loc = 0.0;
+  for (int64_t i = i0; i < i1; ++i) {
+    const unsigned c = hist[off + i];
+    w_loc += c;
+    cs_loc += (double)c * (c0 + (double)i);  // integer-valued: exact
+  }
+  unsigned long long w_tot;
+  double cs_tot;
+  unsigned long long w = otsu_block_exclusive_scan<unsigned long long>(w_loc, s_u, w_tot);
+  double cs = otsu_block_exclusive_scan<double>(cs_loc, s_d, cs_tot);
+  if (w_tot >= (1ull << 24)) {  // float32 weights would round: the order matters, keep numpy's sequential order
+    if (threadIdx.x == 0) {
+      float fw = 0.f;
+      double fcs = 0.0;
+      for (int64_t i = nb - 1; i >= 0; --i) {
+        const float c = (float)hist[off + i];
+        fw = otsu_add(fw, c);
+        fcs = otsu_add(fcs, otsu_mul<double>(c, c0 + (double)i));
+        scratch_w[off + i] = fw;
+        scratch_c[off + i] = fcs;
+      }
+      fw = 0.f;
+      fcs = 0.0;
+      double best = 0.0;
+      int64_t best_i = 0;
+      for (int64_t i = 0; i + 1 < nb; ++i) {
+        const float c = (float)hist[off + i];
+        fw = otsu_add(fw, c);
+        fcs = otsu_add(fcs, otsu_mul<double>(c, c0 + (double)i));
+        const float w2 = scratch_w[off + i + 1];
+        const double v = otsu_var(fw, w2, otsu_div(fcs, fw), otsu_div(scratch_c[off + i + 1], w2));
+        if (i == 0 || v > best) {
+          best = v;
+          best_i = i;
+        }
+      }
+      threshold[l] = c0 + (double)best_i;
+    }
+    return;
+  }
+  // second pass over the strip: variance12[i] for i in [i0, min(i1, nb - 1)), first maximum
+  double best = -1.0;
+  long long best_i = 0x7fffffffffffffffll;
+  for (int64_t i = i0; i < i1 && i + 1 < nb; ++i) {
+    const unsigned c = hist[off + i];
+    w += c;
+    cs += (double)c * (c0 + (double)i);
+    const float w1 = (float)w, w2 = (float)(w_tot - w);  // exact: below 2^24
+    const double v = otsu_var(w1, w2, otsu_div(cs, w1), otsu_div(cs_tot - cs, w2));
+    if (v > best) {  // strict: the first maximum of the strip (variances are >= 0, NaN cannot occur)
+      best = v;
+      best_i = i;
+    }
+  }
+  // block argmax: larger value wins, equal values keep the smaller index (np.argmax: first maximum)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_down_sync(FULL, best, o);
+    const long long oi = __shfl_down_sync(FULL, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) {
+      best = ob;
+      best_i = oi;
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_best[threadIdx.x >> 5] = best;
+    s_best_i[threadIdx.x >> 5] = best_i;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < OTSU_BLOCK / 32; ++k) {
+      if (s_best[k] > best || (s_best[k] == best && s_best_i[k] < best_i)) {
+        best = s_best[k];
+        best_i = s_best_i[k];
+      }
+    }
+    threshold[l] = c0 + (double)best_i;
+  }
+}
+
 // ------------------------------------------------------------------ hole filling
 struct Boxes {
   int n;                      // instances
@@ -367,6 +498,9 @@ int cb200_label_otsu(const unsigned int* hist, const int64_t* hist_offset, const
   if (arithmetic_dtype == CB200_F32)
     label_otsu_kernel<float><<<blocks, 64, 0, st>>>(hist, hist_offset, num_bins, centre0, centres, n_labels, sw,
                                                     static_cast<float*>(sc), thresholds);
+  else if (arithmetic_dtype == CB200_F64 && !centres)  // integer image: exact sums, one block per label
+    label_otsu_block_kernel<<<n_labels, OTSU_BLOCK, 0, st>>>(hist, hist_offset, num_bins, centre0, n_labels, sw,
+                                                             static_cast<double*>(sc), thresholds);
   else if (arithmetic_dtype == CB200_F64)
     label_otsu_kernel<double><<<blocks, 64, 0, st>>>(hist, hist_offset, num_bins, centre0, centres, n_labels, sw,
                                                      static_cast<double*>(sc), thresholds);

@@ -448,10 +448,12 @@ CB200_API int cb200_label_stats(const int32_t* seg, const void* raw, int raw_dty
 CB200_API int cb200_label_histogram(const int32_t* seg, const void* raw, int raw_dtype, int64_t n_pix, int max_label,
                           const double* raw_min, const int64_t* hist_offset, const double* edges, int nbins,
                           unsigned int* hist, void* stream);
-/*   cb200_label_otsu      : the O(bins) tail of threshold_otsu for every label at once, one thread per label in
- *                           numpy's arithmetic (sequential float32 cumulative weights; products, means and
- *                           variance in `arithmetic_dtype` = CB200_F32 for float32 images, CB200_F64 for integer
- *                           and float64 images).  Label l owns hist[hist_offset[l] .. + num_bins[l]); bin centre
+/*   cb200_label_otsu      : the O(bins) tail of threshold_otsu for every label at once in numpy's arithmetic
+ *                           (float32 cumulative weights; products, means and variance in `arithmetic_dtype` =
+ *                           CB200_F32 for float32 images, CB200_F64 for integer and float64 images).  Integer
+ *                           images (`centres` == NULL): one BLOCK per label with block-wide scans -- all partial
+ *                           sums are integers, exact in any order; float images: one thread per label in
+ *                           numpy's sequential order.  Label l owns hist[hist_offset[l] .. + num_bins[l]); bin centre
  *                           i is centres[hist_offset[l] + i] when `centres` is given, else centre0[l] + i.
  *                           thresholds[l] = the centre at the first maximum; labels with num_bins <= 0 untouched. */
 CB200_API int64_t cb200_label_otsu_workspace_bytes(int64_t total_bins);
