@@ -12,7 +12,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CELLULUS_B200_LIB") or os.path.join(PKG, "libcellulus_b200.so")  # override: A/B builds
 
-OK, EINVAL, EUNSUPPORTED, ENOFIT, ENOCENTRE, ENOCONVERGE = 0, -1, -2, -3, -4, -5
+OK, EINVAL, EUNSUPPORTED, ENOFIT, ENOCENTRE, ENOCONVERGE, ENOSPACE = 0, -1, -2, -3, -4, -5, -6
 F32, BF16, F64, I64, I32, I16, U8, U16 = range(8)
 LAYOUT_PLANAR, LAYOUT_CHANNELS_LAST = 0, 1
 
@@ -42,6 +42,7 @@ class DetectInfo(C.Structure):
         ("grid", Grid),
         ("distance_tests", C.c_int64),
         ("climb_steps", C.c_int64),
+        ("workspace_needed", C.c_int64),
     ]
 
 
@@ -105,9 +106,9 @@ PROTOTYPES = {
     "cb200_edt_workspace_bytes": (_i64, [_i64]),
     "cb200_edt_within": (_i, [_p, _i, _pi64, _d, _p, _p, _p]),
     "cb200_grow_shrink": (_i, [_p, _i, _pi64, _d, _d, _p, _p]),
-    "cb200_detect_volume": (_i, [_p, _i, _i, _pi64, _d, _d, _d, _u64, _i, _p, _i, _p, _i, _p, _i64,
+    "cb200_detect_volume_workspace_bytes": (_i64, [_i, _pi64, _i64, _d]),
+    "cb200_detect_volume": (_i, [_p, _i, _i, _pi64, _d, _d, _d, _u64, _i, _p, _i, _p, _i, _p, _i64, _p, _i64, _i64,
                                  C.POINTER(DetectInfo), _p]),
-    "cb200_release_scratch": (_i, []),
     "cb200_label_presence": (_i, [_p, _i, _i64, _i, _p, _p]),
     "cb200_contingency": (_i, [_p, _p, _i, _i64, _p, _p, _i, _i, _i, _p, _p]),
     "cb200_label_stats_workspace_bytes": (_i64, [_i]),

@@ -17,6 +17,7 @@ const char* cb200_error_string(int code) {
   if (code == CB200_ENOFIT) return "the fit subset is empty";
   if (code == CB200_ENOCENTRE) return "no point was within the bandwidth of any seed";
   if (code == CB200_ENOCONVERGE) return "centre suppression did not reach its fix-point";
+  if (code == CB200_ENOSPACE) return "workspace too small for the counts found on the device (see info->workspace_needed)";
   if (code > 0) return cudaGetErrorString((cudaError_t)code);
   return "unknown error";
 }

@@ -9,80 +9,80 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
-#include <mutex>
-#include <vector>
 
 #include "common.cuh"
 
 namespace cb200 {
 
-// Library-owned scratch: a per-device list of cudaMalloc'ed chunks that is bump-allocated per call and kept
-// for the next one (cudaMalloc only while the working set is still growing -- the same idea as a caching
-// allocator; cudaMallocAsync was measured 2-4x slower here because blocks freed a few kernels ago are not yet
-// reusable and the pool keeps mapping new memory).  Calls are serialised per device; a call on another
-// stream first waits for the previous call's last kernel.
-struct Chunk {
+// Scratch of one call: bump-allocated from the CALLER's workspace (no cudaMalloc in here).  The sizes depend on
+// counts that are only known on the device, so a call that runs out of room stops, reports the bytes the counts it
+// has read so far call for (info->workspace_needed) and returns CB200_ENOSPACE; the caller grows its buffer and
+// calls again (the torch shim keeps one buffer per device and does this once per new high-water mark).
+struct Bump {
   char* base;
-  size_t size, used;
-};
-struct DeviceArena {
-  std::mutex lock;
-  std::vector<Chunk> chunks;
-  cudaEvent_t last_use = nullptr;
-  cudaStream_t last_stream = nullptr;
-  bool used_before = false;
-};
-static DeviceArena g_arena[64];
-
-struct ArenaScope {  // one call's view of the arena
-  DeviceArena& a;
-  cudaStream_t st;
-  std::unique_lock<std::mutex> guard;
-  ArenaScope(DeviceArena& arena, cudaStream_t s) : a(arena), st(s), guard(arena.lock) {
-    for (Chunk& c : a.chunks) c.used = 0;
-    if (a.used_before && a.last_stream != st) cudaStreamWaitEvent(st, a.last_use, 0);
-  }
-  ~ArenaScope() {
-    if (!a.last_use) cudaEventCreateWithFlags(&a.last_use, cudaEventDisableTiming);
-    cudaEventRecord(a.last_use, st);
-    a.last_stream = st;
-    a.used_before = true;
+  size_t size, used = 0, wanted = 0;
+  Bump(void* p, int64_t n) : base(static_cast<char*>(p)), size(n > 0 ? (size_t)n : 0) {
+    const size_t mis = reinterpret_cast<uintptr_t>(base) & 255;
+    if (mis) {
+      const size_t skip = 256 - mis;
+      base += skip;
+      size = size > skip ? size - skip : 0;
+    }
   }
   template <typename T>
-  cudaError_t get(T** out, size_t count) {
+  bool get(T** out, size_t count) {
     const size_t bytes = ((count ? count : 1) * sizeof(T) + 255) / 256 * 256;
-    for (Chunk& c : a.chunks) {
-      if (c.size - c.used >= bytes) {
-        *out = reinterpret_cast<T*>(c.base + c.used);
-        c.used += bytes;
-        return cudaSuccess;
-      }
+    wanted += bytes;
+    if (used + bytes > size) {
+      *out = nullptr;
+      return false;
     }
-    const size_t want = bytes > ((size_t)64 << 20) ? bytes : ((size_t)64 << 20);
-    void* p = nullptr;
-    const cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) return e;
-    a.chunks.push_back(Chunk{static_cast<char*>(p), want, bytes});
-    *out = static_cast<T*>(p);
-    return cudaSuccess;
+    *out = reinterpret_cast<T*>(base + used);
+    used += bytes;
+    return true;
   }
 };
+
+// bytes the sequence needs for n_pix pixels of which n_fg are foreground and n_fit take part in the fit
+static int64_t detect_bytes(int D, int64_t n_pix, int64_t n_fg, int64_t n_fit, int64_t n_cells, int64_t nms_bytes) {
+  auto al = [](int64_t b) { return (b + 255) / 256 * 256 + 256; };
+  int64_t t = 512;
+  t += al((int64_t)D * 8 * ((n_fg + 1) & ~(int64_t)1)) + al(4 * n_fg) + al(16) + al(cb200_compact_workspace_bytes(n_pix));
+  t += al(n_fg) + al((int64_t)D * 8 * ((n_fit + 1) & ~(int64_t)1));                       // flags, fit subset
+  t += al(48) + al(cb200_reduce_workspace_bytes());                                          // bounding box
+  t += 2 * al((int64_t)D * 8 * ((n_fit + 1) & ~(int64_t)1)) + al(4 * (n_cells + 1)) + 2 * al(4 * n_fit) + al(32);
+  t += al(cb200_grid_build_workspace_bytes(n_fit, n_cells));
+  t += al(nms_bytes) + al(8) + al((int64_t)D * 8 * ((n_fit + 1) & ~(int64_t)1));            // suppression, centres
+  t += al(cb200_assign_workspace_bytes(n_fg, (int)std::min<int64_t>(n_fit, INT32_MAX), n_cells));
+  return t;
+}
 
 }  // namespace cb200
 
 using namespace cb200;
 
-extern "C" int cb200_release_scratch(void) {
-  int device = 0;
-  CB200_CUDA_TRY(cudaGetDevice(&device));
-  if (device < 0 || device >= 64) return CB200_EUNSUPPORTED;
-  DeviceArena& a = g_arena[device];
-  std::lock_guard<std::mutex> guard(a.lock);
-  CB200_CUDA_TRY(cudaDeviceSynchronize());  // the last call's kernels may still be reading the arena
-  for (Chunk& c : a.chunks) cudaFree(c.base);
-  a.chunks.clear();
-  return CB200_OK;
+extern "C" int64_t cb200_detect_volume_workspace_bytes(int num_dims, const int64_t* spatial, int64_t expected_foreground,
+                                                       double reduction_probability) {
+  if (!spatial || (num_dims != 2 && num_dims != 3)) return -1;
+  int64_t n_pix = 1;
+  for (int k = 0; k < num_dims; ++k) n_pix *= spatial[k] > 0 ? spatial[k] : 1;
+  const int64_t n_fg = expected_foreground > 0 && expected_foreground < n_pix ? expected_foreground : n_pix;
+  const double p = reduction_probability < 1.0 ? reduction_probability : 1.0;
+  const int64_t n_fit = std::min<int64_t>(n_fg, (int64_t)(1.1 * p * (double)n_fg) + 4096);
+  const int64_t n_cells = std::min<int64_t>((int64_t)1 << 26, 4 * n_pix + 64);  // cells of edge >= bandwidth over the points
+  // suppression: a fine grid (8 cells per cell in 3-D) + a few arrays over the seeds; bounded as in cb200_nms_workspace_bytes
+  const int64_t nms = 64 * n_fit + 8 * 8 * std::min<int64_t>(n_cells, n_fit * 27 + 64) + 4096;
+  return detect_bytes(num_dims, n_pix, n_fg, n_fit, std::min<int64_t>(n_cells, n_fit * 27 + 64), nms);
 }
+
+// out of workspace: report what the counts known so far call for and stop
+#define POOL_GET(ptr, count)                                                                        \
+  do {                                                                                              \
+    if (!pool.get(ptr, count)) {                                                                    \
+      info->workspace_needed = detect_bytes(D, n_pix, known_fg, known_fit, known_cells, known_nms); \
+      return CB200_ENOSPACE;                                                                        \
+    }                                                                                               \
+  } while (0)
 
 #define CB200_TRY_RC(expr)        \
   do {                            \
@@ -93,9 +93,10 @@ extern "C" int cb200_release_scratch(void) {
 extern "C" int cb200_detect_volume(const void* emb, int dtype, int num_dims, const int64_t* spatial, double threshold,
                                    double bandwidth, double reduction_probability, uint64_t philox_seed, int max_iter,
                                    void* labels_out, int label_dtype, void* mask_out, int mask_dtype,
-                                   double* centres_out, int64_t centre_capacity, cb200_detect_info* info,
+                                   double* centres_out, int64_t centre_capacity, void* workspace,
+                                   int64_t workspace_bytes, int64_t foreground_capacity, cb200_detect_info* info,
                                    void* stream) {
-  if (!emb || !spatial || !labels_out || !info || !(bandwidth > 0.0)) return CB200_EINVAL;
+  if (!emb || !spatial || !labels_out || !info || !workspace || !(bandwidth > 0.0)) return CB200_EINVAL;
   if (num_dims != 2 && num_dims != 3) return CB200_EUNSUPPORTED;
   if (label_dtype != CB200_I32 && label_dtype != CB200_U16) return CB200_EUNSUPPORTED;
   const int D = num_dims;
@@ -115,22 +116,24 @@ extern "C" int cb200_detect_volume(const void* emb, int dtype, int num_dims, con
     fprintf(stderr, "[detect_volume] %-10s %8.1f us\n", what, std::chrono::duration<double, std::micro>(now - t_prev).count());
     t_prev = now;
   };
-  int device = 0;
-  CB200_CUDA_TRY(cudaGetDevice(&device));
-  if (device < 0 || device >= 64) return CB200_EUNSUPPORTED;
-  ArenaScope pool(g_arena[device], st);
+  Bump pool(workspace, workspace_bytes);
+  // what the workspace must hold, refined as the counts become known (for the CB200_ENOSPACE report)
+  int64_t known_fg = foreground_capacity > 0 ? foreground_capacity : n_pix;
+  int64_t known_fit = reduction_probability < 1.0 ? (int64_t)(1.1 * reduction_probability * (double)known_fg) + 4096 : known_fg;
+  int64_t known_cells = 1 << 16, known_nms = 64 * known_fit + (1 << 20);
   CB200_CUDA_TRY(cudaMemsetAsync(labels_out, 0, (size_t)n_pix * (label_dtype == CB200_I32 ? 4 : 2), st));
 
   // ---- foreground points (utils/mean_shift.py:15-36,85,94)
-  const int64_t cap = (n_pix + 1) & ~(int64_t)1;  // even stride (16-byte granules)
+  // room for `foreground_capacity` points (<= 0: every pixel); even stride (16-byte granules)
+  const int64_t cap = ((foreground_capacity > 0 && foreground_capacity < n_pix ? foreground_capacity : n_pix) + 1) & ~(int64_t)1;
   double* pts;
   int32_t* pix;
   long long* counts_dev;  // [0] foreground, [1] fit subset
   uint8_t* compact_ws;
-  CB200_CUDA_TRY(pool.get(&pts, (size_t)D * cap));
-  CB200_CUDA_TRY(pool.get(&pix, (size_t)cap));
-  CB200_CUDA_TRY(pool.get(&counts_dev, 2));
-  CB200_CUDA_TRY(pool.get(&compact_ws, (size_t)cb200_compact_workspace_bytes(n_pix)));
+  POOL_GET(&pts, (size_t)D * cap);
+  POOL_GET(&pix, (size_t)cap);
+  POOL_GET(&counts_dev, 2);
+  POOL_GET(&compact_ws, (size_t)cb200_compact_workspace_bytes(n_pix));
   CB200_CUDA_TRY(cudaMemsetAsync(counts_dev, 0, 2 * sizeof(long long), st));
   CB200_TRY_RC(cb200_fg_compact(emb, dtype, D, spatial, threshold, pts, pix, cap, counts_dev, mask_out, mask_dtype,
                                 compact_ws, st));
@@ -138,7 +141,14 @@ extern "C" int cb200_detect_volume(const void* emb, int dtype, int num_dims, con
   CB200_CUDA_TRY(cudaMemcpyAsync(&n, counts_dev, sizeof(long long), cudaMemcpyDeviceToHost, st));
   CB200_CUDA_TRY(cudaStreamSynchronize(st));
   info->n_foreground = n;
+  known_fg = n;
+  known_fit = reduction_probability < 1.0 ? (int64_t)(1.1 * reduction_probability * (double)n) + 4096 : n;
+  known_nms = 64 * known_fit + (1 << 20);
   lap("compact");
+  if (n > cap) {  // more foreground than the caller made room for: nothing beyond `cap` was written
+    info->workspace_needed = detect_bytes(D, n_pix, known_fg, known_fit, known_cells, known_nms);
+    return CB200_ENOSPACE;
+  }
   if (n == 0) return CB200_OK;  // all background (utils/mean_shift.py:83-84)
 
   // ---- fit subset (utils/mean_shift.py:67-70), Bernoulli flags from the device Philox stream
@@ -149,8 +159,8 @@ extern "C" int cb200_detect_volume(const void* emb, int dtype, int num_dims, con
     uint8_t* flags;
     double* subset;
     const int64_t sub_cap = (n + 1) & ~(int64_t)1;
-    CB200_CUDA_TRY(pool.get(&flags, (size_t)n));
-    CB200_CUDA_TRY(pool.get(&subset, (size_t)D * sub_cap));
+    POOL_GET(&flags, (size_t)n);
+    POOL_GET(&subset, (size_t)D * sub_cap);
     CB200_TRY_RC(cb200_bernoulli_flags(flags, n, reduction_probability, philox_seed, st));
     CB200_TRY_RC(cb200_select_points(pts, n, cap, D, flags, subset, sub_cap, counts_dev + 1, compact_ws, st));
     CB200_CUDA_TRY(cudaMemcpyAsync(&n_fit, counts_dev + 1, sizeof(long long), cudaMemcpyDeviceToHost, st));
@@ -159,14 +169,16 @@ extern "C" int cb200_detect_volume(const void* emb, int dtype, int num_dims, con
     fit_stride = sub_cap;
   }
   info->n_fit = n_fit;
+  known_fit = n_fit;
+  known_nms = 64 * known_fit + (1 << 20);
   lap("subset");
   if (n_fit == 0) return CB200_ENOFIT;  // sklearn: "Found array with 0 sample(s)"
 
   // ---- bounding box of the fit points -> cell grid
   double* box_dev;
   uint8_t* reduce_ws;
-  CB200_CUDA_TRY(pool.get(&box_dev, 6));
-  CB200_CUDA_TRY(pool.get(&reduce_ws, (size_t)cb200_reduce_workspace_bytes()));
+  POOL_GET(&box_dev, 6);
+  POOL_GET(&reduce_ws, (size_t)cb200_reduce_workspace_bytes());
   CB200_CUDA_TRY(cudaMemsetAsync(reduce_ws, 0, (size_t)cb200_reduce_workspace_bytes(), st));
   for (int k = 0; k < D; ++k)
     CB200_TRY_RC(cb200_minmax(fit + (size_t)k * fit_stride, CB200_F64, n_fit, box_dev + 2 * k, reduce_ws, st));
@@ -181,6 +193,7 @@ extern "C" int cb200_detect_volume(const void* emb, int dtype, int num_dims, con
   cb200_grid grid;
   CB200_TRY_RC(cb200_grid_plan(lo, hi, D, bandwidth, (int64_t)1 << 26, &grid));
   info->grid = grid;
+  known_cells = grid.n_cells;
   lap("bbox");
 
   // ---- grid hash of the fit points, every fit point climbs (sklearn:491-496, :108-128)
@@ -189,13 +202,13 @@ extern "C" int cb200_detect_volume(const void* emb, int dtype, int num_dims, con
   int *cell_start, *counts, *iters, *work;
   uint8_t* build_ws;
   const int64_t build_bytes = cb200_grid_build_workspace_bytes(n_fit, grid.n_cells);
-  CB200_CUDA_TRY(pool.get(&sorted, (size_t)D * fit_cap));
-  CB200_CUDA_TRY(pool.get(&modes, (size_t)D * fit_cap));
-  CB200_CUDA_TRY(pool.get(&cell_start, (size_t)grid.n_cells + 1));
-  CB200_CUDA_TRY(pool.get(&counts, (size_t)n_fit));
-  CB200_CUDA_TRY(pool.get(&iters, (size_t)n_fit));
-  CB200_CUDA_TRY(pool.get(&work, 8));
-  CB200_CUDA_TRY(pool.get(&build_ws, (size_t)build_bytes));
+  POOL_GET(&sorted, (size_t)D * fit_cap);
+  POOL_GET(&modes, (size_t)D * fit_cap);
+  POOL_GET(&cell_start, (size_t)grid.n_cells + 1);
+  POOL_GET(&counts, (size_t)n_fit);
+  POOL_GET(&iters, (size_t)n_fit);
+  POOL_GET(&work, 8);
+  POOL_GET(&build_ws, (size_t)build_bytes);
   CB200_TRY_RC(cb200_grid_build(fit, n_fit, fit_stride, &grid, sorted, fit_cap, nullptr, cell_start, build_ws,
                                 build_bytes, st));
   for (int k = 0; k < D; ++k)
@@ -212,10 +225,11 @@ extern "C" int cb200_detect_volume(const void* emb, int dtype, int num_dims, con
   // ---- centres: dedupe + greedy suppression (sklearn:511-547)
   const int64_t nms_bytes = cb200_nms_workspace_bytes(n_fit, &grid, bandwidth);
   if (nms_bytes < 0) return CB200_EUNSUPPORTED;
+  known_nms = nms_bytes;
   uint8_t* nms_ws;
   int* keep_dev;
-  CB200_CUDA_TRY(pool.get(&nms_ws, (size_t)nms_bytes));
-  CB200_CUDA_TRY(pool.get(&keep_dev, 2));
+  POOL_GET(&nms_ws, (size_t)nms_bytes);
+  POOL_GET(&keep_dev, 2);
   CB200_CUDA_TRY(cudaMemsetAsync(keep_dev, 0, 2 * sizeof(int), st));
   int keep[2] = {0, 1};
   long long stats[2] = {0, 0};  // the hill climb's work statistics ride on the first count read
@@ -241,14 +255,14 @@ extern "C" int cb200_detect_volume(const void* emb, int dtype, int num_dims, con
     centres = centres_out;
     c_stride = centre_capacity;
   } else {
-    CB200_CUDA_TRY(pool.get(&centres, (size_t)D * c_cap));
+    POOL_GET(&centres, (size_t)D * c_cap);
   }
   CB200_TRY_RC(cb200_nms_emit(modes, fit_cap, D, counts, n_fit, bandwidth, &grid, k_centres, centres, c_stride, nms_ws,
                               nms_bytes, st));
 
   // ---- predict on ALL foreground points, scatter, +1 (utils/mean_shift.py:74,101-104,57)
   uint8_t* assign_ws;
-  CB200_CUDA_TRY(pool.get(&assign_ws, (size_t)cb200_assign_workspace_bytes(n, k_centres, grid.n_cells)));
+  POOL_GET(&assign_ws, (size_t)cb200_assign_workspace_bytes(n, k_centres, grid.n_cells));
   CB200_TRY_RC(cb200_assign_labels(pts, n, cap, D, centres, c_stride, k_centres, &grid, pix, labels_out, label_dtype,
                                    assign_ws, st));
   lap("assign");

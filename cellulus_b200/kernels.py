@@ -801,11 +801,14 @@ def contingency(pred: torch.Tensor, gt: torch.Tensor, rank_pred: torch.Tensor, r
 
 
 # --------------------------------------------------------------------------- one call per volume
+_detect_workspaces = {}  # (device index, stream) -> (uint8 workspace tensor, foreground capacity it was sized for)
+
+
 def detect_volume(emb: torch.Tensor, bandwidth: float, threshold: float, reduction_probability: float = 1.0,
                   philox_seed: int = 0, max_iter: int = 300, label_dtype=torch.int32, want_mask: bool = False,
                   centre_capacity: int = 0):
-    """`cb200_detect_volume`: threshold -> labels in ONE C-ABI call (scratch and the count reads are handled
-    inside the library).  Returns `(labels (*S), mask | None, centres (D, centre_capacity) | None, info dict)`.
+    """`cb200_detect_volume`: threshold -> labels in ONE C-ABI call (the count reads are handled inside the
+    library, the scratch is a torch buffer kept per device and grown on demand).  Returns `(labels (*S), mask | None, centres (D, centre_capacity) | None, info dict)`.
     Raises ValueError with scikit-learn's messages where `MeanShift.fit` would."""
     _require_cuda(emb)
     emb = emb.contiguous()
@@ -818,11 +821,32 @@ def detect_volume(emb: torch.Tensor, bandwidth: float, threshold: float, reducti
     mask = torch.empty(spatial, dtype=torch.uint8, device=dev) if want_mask else None
     centres = torch.zeros((D, centre_capacity), dtype=torch.float64, device=dev) if centre_capacity > 0 else None
     info = _cabi.DetectInfo()
-    rc = _lib().cb200_detect_volume(
-        _ptr(emb), _code(emb, _FLOAT_DTYPES), D, spatial_array(spatial), float(threshold), float(bandwidth),
-        float(reduction_probability), int(philox_seed) & (2**64 - 1), int(max_iter), _ptr(labels),
-        _code(labels, (torch.int32, torch.uint16)), _ptr(mask), _DTYPE_CODE[torch.uint8] if want_mask else 0,
-        _ptr(centres), int(centre_capacity), C.byref(info), _stream(emb))
+    n_pix = int(np.prod(spatial))
+    # scratch is the caller's: one buffer per device and stream, sized for the largest foreground count seen so far
+    # (first guess: a quarter of the pixels); CB200_ENOSPACE reports what the counts found on the device call for
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws, capacity = _detect_workspaces.get(key, (None, 0))
+    if ws is None:
+        capacity = max(n_pix // 4, 1 << 16)
+        ws = torch.empty(_lib().cb200_detect_volume_workspace_bytes(D, spatial_array(spatial), capacity,
+                                                                    float(reduction_probability)),
+                         dtype=torch.uint8, device=dev)
+    for _ in range(6):
+        rc = _lib().cb200_detect_volume(
+            _ptr(emb), _code(emb, _FLOAT_DTYPES), D, spatial_array(spatial), float(threshold), float(bandwidth),
+            float(reduction_probability), int(philox_seed) & (2**64 - 1), int(max_iter), _ptr(labels),
+            _code(labels, (torch.int32, torch.uint16)), _ptr(mask), _DTYPE_CODE[torch.uint8] if want_mask else 0,
+            _ptr(centres), int(centre_capacity), _ptr(ws), ws.numel(), min(capacity, n_pix), C.byref(info),
+            _stream(emb))
+        if rc != _cabi.ENOSPACE:
+            break
+        capacity = max(capacity, int(info.n_foreground) + (int(info.n_foreground) >> 3))
+        need = max(int(info.workspace_needed) + (int(info.workspace_needed) >> 3),
+                   _lib().cb200_detect_volume_workspace_bytes(D, spatial_array(spatial), capacity,
+                                                              float(reduction_probability)))
+        ws = None  # release before growing
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    _detect_workspaces[key] = (ws, capacity)
     launch_counter["calls"] += 1
     if rc == _cabi.ENOFIT:
         raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required by MeanShift.")
@@ -838,6 +862,6 @@ def detect_volume(emb: torch.Tensor, bandwidth: float, threshold: float, reducti
 
 
 def release_scratch(device=None) -> None:
-    """`cb200_release_scratch`: give back the arena `detect_volume` keeps on `device` (default: current)."""
-    with torch.cuda.device(device if device is not None else torch.cuda.current_device()):
-        check(_lib().cb200_release_scratch(), "cb200_release_scratch")
+    """Drop the workspace buffers `detect_volume` keeps (all devices, or one)."""
+    for key in [k for k in _detect_workspaces if device is None or k[0] == torch.device(device).index]:
+        del _detect_workspaces[key]

@@ -40,6 +40,7 @@ extern "C" {
 #define CB200_ENOFIT (-3)      /* the fit subset is empty (sklearn: "Found array with 0 sample(s)") */
 #define CB200_ENOCENTRE (-4)   /* no seed had a neighbour (sklearn: "No point was within bandwidth ...") */
 #define CB200_ENOCONVERGE (-5) /* centre suppression did not reach its fix-point */
+#define CB200_ENOSPACE (-6)    /* the workspace is too small for the counts found on the device; see the call */
 
 /* element types */
 #define CB200_F32 0
@@ -355,9 +356,15 @@ CB200_API int cb200_assign_labels(const double* points, int64_t n_points, int64_
  * predict) behind one call, for callers that do not need the intermediate results:
  *   threshold -> foreground points -> fit subset (Bernoulli(reduction_probability) from the device Philox
  *   stream; 1.0 = all points) -> cell grid -> modes -> centres -> labels (+1, 0 = background).
- * Same kernels and results as the step-by-step entry points above.  Unlike them this one ALLOCATES its
- * scratch (a library-owned arena per device, kept for the next call) and SYNCHRONISES the stream up to four times to read the
- * data-dependent counts.  labels_out (n_pix, CB200_I32 / CB200_U16) is cleared by the call; mask_out optional
+ * Same kernels and results as the step-by-step entry points above.  It allocates nothing: all scratch comes from the
+ * caller's `workspace`.  Its sizes depend on counts that only exist on the device (foreground pixels, fit subset,
+ * cells, centres), so unlike the other entry points this one SYNCHRONISES the stream to read them (four small
+ * device -> host reads per volume) and is therefore not graph-capturable.  Protocol:
+ *   workspace_bytes = cb200_detect_volume_workspace_bytes(num_dims, spatial, expected_foreground, reduction_probability)
+ *   foreground_capacity = the expected_foreground the workspace was sized for (<= 0: every pixel)
+ *   return CB200_ENOSPACE: more foreground (or cells, or seeds) than there was room for; nothing useful was written,
+ *   info->n_foreground holds the count found and info->workspace_needed the bytes to call again with.
+ * labels_out (n_pix, CB200_I32 / CB200_U16) is cleared by the call; mask_out optional
  * (CB200_U8 / CB200_U16); centres_out optional device SoA (D x centre_capacity) receiving `cluster_centers_`.
  * Returns CB200_ENOFIT / CB200_ENOCENTRE where scikit-learn raises ValueError.
  */
@@ -370,15 +377,16 @@ typedef struct cb200_detect_info {
   cb200_grid grid;
   int64_t distance_tests; /* seed x candidate evaluations of the hill climb (its algorithmic work) */
   int64_t climb_steps;    /* sum over seeds of (iterations + 1): window evaluations */
+  int64_t workspace_needed; /* set with CB200_ENOSPACE */
 } cb200_detect_info;
 
+CB200_API int64_t cb200_detect_volume_workspace_bytes(int num_dims, const int64_t* spatial, int64_t expected_foreground,
+                                            double reduction_probability);
 CB200_API int cb200_detect_volume(const void* emb, int dtype, int num_dims, const int64_t* spatial, double threshold,
                         double bandwidth, double reduction_probability, uint64_t philox_seed, int max_iter,
                         void* labels_out, int label_dtype, void* mask_out, int mask_dtype, double* centres_out,
-                        int64_t centre_capacity, cb200_detect_info* info /* host out */, void* stream);
-
-/* Frees the scratch arena cb200_detect_volume keeps on the current device (synchronises the device first). */
-CB200_API int cb200_release_scratch(void);
+                        int64_t centre_capacity, void* workspace, int64_t workspace_bytes, int64_t foreground_capacity,
+                        cb200_detect_info* info /* host out */, void* stream);
 
 /*
  * Greedy seed-and-grow clustering, utils/greedy_cluster.py:46-120,176-253 (clustering = "greedy",

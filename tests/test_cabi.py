@@ -69,9 +69,12 @@ def test_arguments_are_validated_before_any_device_work(lib):
     assert lib.cb200_label_stats(p, p, _cabi.F32, 1, sp2, 5, p, p, p, p, None) == _cabi.EUNSUPPORTED
     assert lib.cb200_label_otsu(p, p, p, None, None, _cabi.F64, 3, 10, p, p, None) == _cabi.EINVAL
     assert lib.cb200_contingency(p, p, _cabi.U16, 10, p, p, -1, 2, 2, p, None) == _cabi.EINVAL
-    assert lib.cb200_detect_volume(p, _cabi.F32, 2, sp2, 0.5, 0.0, 1.0, 0, 300, p, _cabi.I32, None, 0, None, 0,
+    assert lib.cb200_detect_volume(p, _cabi.F32, 2, sp2, 0.5, 0.0, 1.0, 0, 300, p, _cabi.I32, None, 0, None, 0, p, 64, 0,
                                    ctypes.byref(info), None) == _cabi.EINVAL  # bandwidth must be positive
-    assert lib.cb200_detect_volume(p, _cabi.F32, 4, sp4, 0.5, 3.0, 1.0, 0, 300, p, _cabi.I32, None, 0, None, 0,
+    assert lib.cb200_detect_volume(p, _cabi.F32, 2, sp2, 0.5, 3.0, 1.0, 0, 300, p, _cabi.I32, None, 0, None, 0, None, 0, 0,
+                                   ctypes.byref(info), None) == _cabi.EINVAL  # the scratch is the caller's
+    assert lib.cb200_detect_volume_workspace_bytes(2, sp2, 0, 1.0) > lib.cb200_detect_volume_workspace_bytes(2, sp2, 16, 0.1) > 0
+    assert lib.cb200_detect_volume(p, _cabi.F32, 4, sp4, 0.5, 3.0, 1.0, 0, 300, p, _cabi.I32, None, 0, None, 0, p, 64, 0,
                                    ctypes.byref(info), None) == _cabi.EUNSUPPORTED
     assert lib.cb200_sample_pairs(p, p, _cabi.F32, 1, 2, sp2, 3.0, 4, 4, 0, 0, None) == _cabi.EUNSUPPORTED
     assert lib.cb200_error_string(_cabi.ENOFIT) == b"the fit subset is empty"

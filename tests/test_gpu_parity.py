@@ -945,9 +945,31 @@ def test_detect_volume_edge_cases():
         K.detect_volume(d, 3.0, 0.5, 0.0)
     d64 = d.double()
     a, _, _, _ = K.detect_volume(d64, 3.0, 0.5, 1.0)
-    K.release_scratch()  # the arena is rebuilt on demand
+    K.release_scratch()  # the workspace is rebuilt on demand
     b, _, _, _ = K.detect_volume(d, 3.0, 0.5, 1.0)
     assert torch.equal(a, b)  # float64 storage of float32 values: same result
-    free_before = torch.cuda.mem_get_info()[0]
+    # the workspace protocol: a buffer sized for too little foreground is refused with the size to come back
+    # with (CB200_ENOSPACE), nothing is allocated inside the library; the wrapper grows its buffer and retries
+    import ctypes as C
+
+    from cellulus_b200 import _cabi
+
+    lib = _cabi.load()
+    spatial = _cabi.spatial_array(d.shape[1:])
+    small = lib.cb200_detect_volume_workspace_bytes(2, spatial, 16, 1.0)
+    ws = torch.empty(small, dtype=torch.uint8, device=d.device)
+    labels = torch.empty(d.shape[1:], dtype=torch.int32, device=d.device)
+    info = _cabi.DetectInfo()
+    rc = lib.cb200_detect_volume(d.data_ptr(), _cabi.F32, 2, spatial, 0.5, 3.0, 1.0, 0, 300, labels.data_ptr(), _cabi.I32,
+                                 None, 0, None, 0, ws.data_ptr(), ws.numel(), 16, C.byref(info),
+                                 torch.cuda.current_stream().cuda_stream)
+    assert rc == _cabi.ENOSPACE and info.n_foreground == int((d[2] < 0.5).sum()) and info.workspace_needed > small
+    ws = torch.empty(info.workspace_needed, dtype=torch.uint8, device=d.device)
+    rc = lib.cb200_detect_volume(d.data_ptr(), _cabi.F32, 2, spatial, 0.5, 3.0, 1.0, 0, 300, labels.data_ptr(), _cabi.I32,
+                                 None, 0, None, 0, ws.data_ptr(), ws.numel(), info.n_foreground, C.byref(info),
+                                 torch.cuda.current_stream().cuda_stream)
+    assert rc == 0 and torch.equal(labels, a.to(torch.int32))
     K.release_scratch()
-    assert torch.cuda.mem_get_info()[0] >= free_before
+    big, _, _ = synthetic.blob_scene((300, 300), 120, radius=9.0, seed=3)  # 40 % foreground: beyond the first guess
+    c, _, _, info2 = K.detect_volume(torch.from_numpy(big).to(_dev()), 4.0, 0.5, 1.0)
+    assert info2["n_fg"] > 300 * 300 // 4 and int((c > 0).sum()) == info2["n_fg"]
