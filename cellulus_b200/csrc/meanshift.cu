@@ -247,12 +247,19 @@ grid_cell_start_kernel(const unsigned* __restrict__ sorted_keys, int64_t n, int6
   }
 }
 
+#ifndef CB200_MSG_UNROLL
+#define CB200_MSG_UNROLL 2
+#endif
+constexpr int MSG_UNROLL = CB200_MSG_UNROLL;  // trips of a row unrolled together (loads of later trips in flight)
 constexpr int MSG_THREADS = 256;
 
 // One warp per seed, climbing to convergence.  Seeds are claimed dynamically so that
 // slow climbers do not hold up a whole block.
+#ifndef CB200_MSG_MINBLOCKS
+#define CB200_MSG_MINBLOCKS 1
+#endif
 template <int D>
-__global__ void __launch_bounds__(MSG_THREADS)
+__global__ void __launch_bounds__(MSG_THREADS, CB200_MSG_MINBLOCKS)
 ms_grid_modes_kernel(const double* __restrict__ pts, int64_t pts_stride, GridDev g,
                      const int* __restrict__ cell_start, double* __restrict__ means, int64_t seed_stride,
                      int64_t n_seeds, double r2, double stop, int max_iter, int* __restrict__ counts,
@@ -302,6 +309,7 @@ ms_grid_modes_kernel(const double* __restrict__ pts, int64_t pts_stride, GridDev
           for (int r = 0; r < n_rows; ++r) {
             const int beg = __shfl_sync(FULL, my_beg, r);
             const int end = __shfl_sync(FULL, my_end, r);
+#pragma unroll MSG_UNROLL
             for (int i = beg + lane; i < end; i += 32) {
               double x[D];
 #pragma unroll
