@@ -62,7 +62,7 @@ def _warn_if_labels_wrap(k: int, sample, bandwidth) -> None:
 
 def detect_embeddings(embeddings, bandwidth, threshold=None, num_bandwidths=1, reduction_probability=0.1,
                       seeds=None, rng="numpy", method="auto", label_dtype=torch.uint16, return_info=False,
-                      one_call=None):
+                      one_call=None, bin_seeding=False):
     """Per-sample body of `detect.py:82-161` (`clustering="meanshift"`, `use_seeds=False`).
 
     embeddings : (D+1, *S) CUDA tensor, fp32 or fp64 (channel D = std), or a numpy array (uploaded)
@@ -80,7 +80,7 @@ def detect_embeddings(embeddings, bandwidth, threshold=None, num_bandwidths=1, r
     for k in range(num_bandwidths):
         labels, info = MS.segment_embeddings_device(
             embeddings, bandwidth / (2**k), threshold, reduction_probability, seeds=seeds, rng=rng, method=method,
-            label_dtype=label_dtype, want_mask=(k == 0), one_call=one_call)
+            label_dtype=label_dtype, want_mask=(k == 0), one_call=one_call, bin_seeding=bin_seeding)
         if k == 0:
             mask = info.pop("mask")
         if label_dtype == torch.uint16:

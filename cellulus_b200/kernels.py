@@ -559,6 +559,28 @@ def ms_brute_modes(points, n, seeds_soa, n_seeds, bandwidth, max_iter=300):
     return counts, iters
 
 
+def bin_seeds(points: torch.Tensor, n: int, bin_size: float):
+    """`cb200_bin_seeds`: sklearn `get_bin_seeds(points, bin_size)` on the device.  Returns `(seeds SoA (D, cap)
+    float64, n_seeds)`; one host sync (the count)."""
+    _require_cuda(points)
+    D = points.shape[0]
+    dev = points.device
+    cap = max(2, (n + 1) & ~1)
+    seeds = torch.zeros((D, cap), dtype=torch.float64, device=dev)
+    n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+    overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    nbytes = _lib().cb200_bin_seeds_workspace_bytes(n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    rc = _lib().cb200_bin_seeds(_ptr(points), n, points.stride(0), D, float(bin_size), _ptr(seeds), cap, _ptr(n_out),
+                                _ptr(overflow), _ptr(ws), nbytes, _stream(points))
+    check(rc, "cb200_bin_seeds")
+    launch_counter["calls"] += 1
+    k, bad = int(n_out.item()), int(overflow.item())
+    if bad:
+        raise _cabi.CellulusB200Error("bin_seeds: a bin index exceeds 2^20 (coordinates / bin_size too large)")
+    return seeds, k
+
+
 def nms_centres(modes_soa, counts, n_seeds, bandwidth, grid: Grid, rounds_per_call: int = 4):
     """sklearn:511-547 on the device.  Returns `(centres (D, cap) SoA in `cluster_centers_` order, K)`.
     One host sync per call of `rounds_per_call` rounds (the fix-point takes 2-3 rounds in practice)."""

@@ -30,7 +30,8 @@ def _seeds_to_soa(seeds, D, device):
     return soa, n
 
 
-def cluster_points_device(points, n, fit_points, n_fit, bandwidth, seeds=None, method="auto", max_iter=300):
+def cluster_points_device(points, n, fit_points, n_fit, bandwidth, seeds=None, method="auto", max_iter=300,
+                          bin_seeding=False):
     """sklearn `MeanShift(bandwidth, seeds).fit(fit_points)` centre finding on the device.
 
     points / fit_points: SoA (D, cap) float64.  Returns `(centres SoA (D, >=K), K, info)`.
@@ -39,7 +40,10 @@ def cluster_points_device(points, n, fit_points, n_fit, bandwidth, seeds=None, m
     dev = points.device
     if n_fit == 0:
         raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required by MeanShift.")
-    if seeds is None:
+    if seeds is None and bin_seeding:
+        # sklearn MeanShift(bin_seeding=True): seeds = get_bin_seeds(X, bandwidth) (sklearn:493-494)
+        seeds_soa, n_seeds = K.bin_seeds(fit_points, n_fit, bandwidth)
+    elif seeds is None:
         seeds_soa, n_seeds = fit_points.clone(), n_fit  # every fit point is a seed (sklearn:491-496)
     else:
         seeds_soa, n_seeds = _seeds_to_soa(seeds, D, dev)
@@ -66,18 +70,20 @@ def cluster_points_device(points, n, fit_points, n_fit, bandwidth, seeds=None, m
 
 def segment_embeddings_device(emb, bandwidth, threshold, reduction_probability=1.0, seeds=None, rng="numpy",
                               fit_flags=None, method="auto", label_dtype=torch.int32, want_mask=False,
-                              philox_seed=0, assign="grid", one_call=False):
+                              philox_seed=0, assign="grid", one_call=False, bin_seeding=False):
     """threshold -> foreground points -> fit subset -> modes -> centres -> labels, all on the device.
 
     emb: (D+1, *S) CUDA tensor (fp32/fp64), channel D = std.  Returns `(labels (*S), info)`;
     labels are 0 for background and 1..K otherwise (`utils/mean_shift.py:57,101-104`).
     `rng`: "numpy" draws the fit subset exactly like the reference (`np.random.rand(N) < p`,
     :68-70, global RNG) and uploads the flags; "philox" draws it on the device.
+    `bin_seeding`: seed with scikit-learn's grid-binned seeds (`MeanShift(bin_seeding=True)`) instead of every fit
+    point -- BASELINE configs[3]'s second seeding mode; the reference itself never enables it.
     `one_call`: run the identical sequence inside the library (`cb200_detect_volume`: one C-ABI call, no
     interpreter between the kernels); needs the device RNG (or no subsampling) and the grid kernels, and
     reports counts only (no per-seed modes / iterations in `info`).
     """
-    if one_call and seeds is None and fit_flags is None and method in ("auto", "grid") and assign == "grid" and (
+    if one_call and seeds is None and not bin_seeding and fit_flags is None and method in ("auto", "grid") and assign == "grid" and (
             rng == "philox" or reduction_probability >= 1.0):
         labels, mask, _, info = K.detect_volume(emb, bandwidth, threshold, reduction_probability, philox_seed,
                                                label_dtype=label_dtype, want_mask=want_mask)
@@ -106,7 +112,8 @@ def segment_embeddings_device(emb, bandwidth, threshold, reduction_probability=1
         fit_pts, n_fit = K.select_points(pts, n, fit_flags)
     else:
         fit_pts, n_fit = pts, n
-    centres, k, cinfo = cluster_points_device(pts, n, fit_pts, n_fit, bandwidth, seeds=seeds, method=method)
+    centres, k, cinfo = cluster_points_device(pts, n, fit_pts, n_fit, bandwidth, seeds=seeds, method=method,
+                                              bin_seeding=bin_seeding)
     # predict on ALL foreground (:74), scatter, +1; pruned nearest-centre search over the same cell grid
     K.assign_labels(pts, n, centres, k, pix, labels, grid=cinfo["grid"] if assign == "grid" else None)
     info.update(cinfo)

@@ -311,6 +311,20 @@ CB200_API int cb200_ms_grid_modes(const double* points_sorted, int64_t n_points,
                         void* stream);
 
 /*
+ * Grid-binned seeds: scikit-learn's get_bin_seeds (sklearn:254-297; MeanShift(bin_seeding=True), min_bin_freq = 1),
+ * the "grid-binned" seeding of BASELINE configs[3] (the reference itself always seeds with every fit point):
+ *   bins = unique np.round(point / bin_size) (float64 division, round half to even), seeds = float32(bin) *
+ *   float32(bin_size) widened to float64, written as an SoA (D x seed_stride, seed_stride >= n_points) in key
+ *   order (the order of seeds does not influence the fitted centres); if every point has its own bin the points
+ *   themselves are the seeds, as in scikit-learn.  *n_out (device int64) = number of seeds; *overflow (device
+ *   int) is set when a bin index does not fit 21 bits (|point / bin_size| >= 2^20): the result is then invalid.
+ */
+CB200_API int64_t cb200_bin_seeds_workspace_bytes(int64_t n_points);
+CB200_API int cb200_bin_seeds(const double* points, int64_t n_points, int64_t pts_stride, int num_dims, double bin_size,
+                    double* seeds, int64_t seed_stride, long long* n_out, int* overflow, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+
+/*
  * Centre post-processing, sklearn:511-547: drop empty seeds, order by
  * (count, coords) descending, merge exact duplicates, greedy suppression of
  * every centre within `bandwidth` (inclusive) of an earlier survivor --

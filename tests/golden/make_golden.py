@@ -256,6 +256,34 @@ def golden_mean_shift(ms):
     np.savez_compressed(os.path.join(HERE, "mean_shift.npz"), **out)
 
 
+def golden_bin_seeding():
+    """BASELINE configs[3] "grid-binned" seeds: scikit-learn's own `get_bin_seeds` and
+    `MeanShift(bandwidth, bin_seeding=True)` (what `AnchorMeanshift` would run with that option) on the
+    foreground points of a blob scene: seeds, centres, labels of all points."""
+    import sklearn
+    from sklearn.cluster import MeanShift, get_bin_seeds
+
+    out = {"sklearn_version": np.array(sklearn.__version__)}
+    for name, shape, K, radius, bw in [("2d", (90, 110), 12, 8.0, 5.0), ("3d", (14, 34, 36), 5, 5.0, 3.5),
+                                       ("2d_fine", (40, 44), 3, 6.0, 0.4), ("2d_fail", (30, 32), 2, 5.0, 0.01)]:
+        emb, _, _ = synthetic.blob_scene(shape, K, radius=radius, seed=len(name) + K)
+        D = len(shape)
+        emb64 = emb.astype(np.float64)
+        grids = np.meshgrid(*[np.arange(s) for s in shape], indexing="ij")
+        mask = emb64[D] < 0.5
+        X = np.stack([(emb64[ch] + grids[D - 1 - ch])[mask] for ch in range(D)], axis=1)
+        import warnings
+
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")  # "Binning data failed": the 2d_fine case returns the points themselves
+            seeds = get_bin_seeds(X, bw, 1)
+            ms = MeanShift(bandwidth=bw, bin_seeding=True).fit(X)
+        out.update({f"{name}_emb": emb, f"{name}_bw": np.array(bw), f"{name}_seeds": np.asarray(seeds, dtype=np.float64),
+                    f"{name}_centres": ms.cluster_centers_, f"{name}_labels": ms.predict(X).astype(np.int32)})
+        print("bin seeding", name, "N", len(X), "seeds", len(seeds), "K", len(ms.cluster_centers_))
+    np.savez_compressed(os.path.join(HERE, "bin_seeding.npz"), **out)
+
+
 def golden_greedy(gc):
     """`Cluster2d/3d.cluster` of the reference (utils/greedy_cluster.py, loaded by path) on small scenes."""
     out = {}
@@ -420,6 +448,7 @@ def main():
     golden_sampler(ZarrDataset)
     golden_tta(UNetModel)
     golden_mean_shift(ms)
+    golden_bin_seeding()
     golden_greedy(load_by_path("ref_greedy_cluster", os.path.join(REF, "cellulus/utils/greedy_cluster.py")))
     golden_post_process()
     golden_evaluate()

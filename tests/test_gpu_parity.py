@@ -442,6 +442,50 @@ def test_loss_full_size_config1_against_oracle():
             assert _rel(g.cpu().numpy(), exact[3].numpy()) <= LOSS_RTOL
 
 
+def test_torch_library_ops_opcheck_and_values():
+    """The dispatcher registration (`torch.ops.cellulus_b200.*`): `torch.library.opcheck` (schema, fake tensor,
+    autograd registration, AOT dispatch) and the same numbers as the eager entry points / the oracle."""
+    import cellulus_b200.ops  # noqa: F401
+    from cellulus_b200.criterions import oce_loss_fused
+    from oracle import device_sampler as ods
+
+    dev = _dev()
+    ns = torch.ops.cellulus_b200
+    S = (44, 44)  # square: the reference sampler draws column d from output_shape[d] (quirk Q4)
+    np.random.seed(2)
+    a, r = osampler.sample_coordinates(S, 6.0, 0.2, 2)
+    anchors, refs = torch.from_numpy(a)[None].to(dev), torch.from_numpy(r)[None].to(dev)
+    offsets = torch.from_numpy(synthetic.loss_offsets(1, 2, S, seed=9)).to(dev)
+    o = offsets.clone().requires_grad_(True)
+    torch.library.opcheck(ns.oce_loss_fused.default, (o, anchors, refs, 10.0, 1e-2))
+    torch.library.opcheck(ns.oce_loss_sampled.default, (o, 6.0, 200, 11, 3, 1, 10.0, 1e-2))
+    stack = torch.from_numpy(synthetic.tta_stack(8, 2, (20, 24), seed=0)).to(dev)
+    torch.library.opcheck(ns.tta_aggregate.default, (stack,))
+    emb, _, _ = synthetic.blob_scene((48, 56), 5, radius=6.0, seed=2)
+    emb_d = torch.from_numpy(emb).to(dev)
+    torch.library.opcheck(ns.detect_volume.default, (emb_d, 3.0, 0.5, 1.0, 0))
+    # values and gradients: a weighted mix of all three results, against the oracle
+    res, _ = ns.oce_loss_fused(o, anchors, refs, 10.0, 1e-2)
+    (0.5 * res[0] + 2.0 * res[1] - res[2]).backward()
+    oo = offsets.cpu().clone().requires_grad_(True)
+    ea = oloss.select_and_add_coordinates(oo, anchors.cpu())
+    er = oloss.select_and_add_coordinates(oo, refs.cpu())
+    loss, oce, reg = oloss.oce_loss(ea, er, 10.0, 1e-2)
+    (0.5 * loss + 2.0 * oce - reg).backward()
+    assert abs(res[0].item() - loss.item()) <= LOSS_RTOL * abs(loss.item())
+    assert _rel(o.grad.cpu().numpy(), oo.grad.numpy()) <= 2e-5
+    # the dispatcher op and the eager entry point launch the same kernel
+    l2, _, _ = oce_loss_fused(offsets, anchors, refs, 10.0, 1e-2)
+    assert abs(l2.item() - res[0].item()) <= 1e-6 * abs(l2.item())
+    res_s, g_s = ns.oce_loss_sampled(offsets, 6.0, 200, 11, 3, 1, 10.0, 1e-2)
+    a_s, r_s = ods.sample_pairs(1, S[::-1], 6.0, 200, 11, 3, 1)
+    l_s, _, _, g_ref = oloss.loss_step(offsets.cpu(), torch.from_numpy(a_s), torch.from_numpy(r_s), 10.0, 1e-2)
+    assert abs(res_s[0].item() - l_s.item()) <= LOSS_RTOL * abs(l_s.item())
+    assert _rel(g_s.cpu().numpy(), g_ref.numpy()) <= LOSS_RTOL
+    assert torch.equal(ns.tta_aggregate(stack), K.tta_aggregate(stack))
+    assert torch.equal(ns.detect_volume(emb_d, 3.0, 0.5, 1.0, 0), K.detect_volume(emb_d, 3.0, 0.5, 1.0, 0)[0])
+
+
 # ----------------------------------------------------------------------------- TTA
 @pytest.mark.parametrize("case", ["2d", "3d"])
 def test_tta_matches_reference_golden(golden, case):
@@ -659,6 +703,32 @@ def test_mean_shift_kats_and_edges():
     with pytest.raises(ValueError, match="No point was within bandwidth"):
         pts = _soa(X, dev)
         cluster_points_device(pts, 3, pts, 3, 5.0, seeds=np.array([[50.0, 50.0]]), method="grid")
+
+
+@pytest.mark.parametrize("case", ["2d", "3d", "2d_fine", "2d_fail"])
+def test_bin_seeding_matches_sklearn_golden(golden, case):
+    """Grid-binned seeding (BASELINE configs[3]): `cb200_bin_seeds` yields scikit-learn's `get_bin_seeds` set
+    (bit-identical float32 products; sklearn's order is first-seen, ours key order) and clustering with
+    `bin_seeding=True` reproduces `MeanShift(bandwidth, bin_seeding=True)`: same centres in the same order, same
+    labels for every foreground pixel."""
+    from cellulus_b200.utils.mean_shift import segment_embeddings_device
+
+    g = golden("bin_seeding")
+    emb, bw = g[f"{case}_emb"], float(g[f"{case}_bw"])
+    D = emb.shape[0] - 1
+    X = oms.points_from_embedding(emb[:D].astype(np.float64), emb[D].astype(np.float64) < 0.5)
+    seeds, k = K.bin_seeds(_soa(X, _dev()), len(X), bw)
+    got = seeds[:, :k].cpu().numpy().T
+    ref = g[f"{case}_seeds"]
+    assert got.shape == ref.shape
+    order = lambda a: a[np.lexsort(a.T[::-1])]  # noqa: E731
+    assert np.array_equal(order(got), order(ref))
+    labels, info = segment_embeddings_device(torch.from_numpy(emb).to(_dev()), bw, 0.5, 1.0, bin_seeding=True)
+    centres = info["centres"].cpu().numpy().T
+    assert centres.shape == g[f"{case}_centres"].shape
+    assert np.abs(centres - g[f"{case}_centres"]).max() <= 1e-9 * bw
+    fg = labels[torch.from_numpy(emb[D] < 0.5).to(_dev())].cpu().numpy()
+    assert np.array_equal(fg - 1, g[f"{case}_labels"])
 
 
 @pytest.mark.parametrize("nd", [2, 3])

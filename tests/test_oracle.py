@@ -325,3 +325,17 @@ def test_device_stream_has_the_reference_samplers_distribution(nd, out_shape, ka
     chi2 = (((k1 * x - k2 * y) ** 2) / np.maximum(x + y, 1)).sum()
     dof = len(sup) - 1
     assert chi2 < dof + 6 * np.sqrt(2 * dof)
+
+
+@pytest.mark.parametrize("case", ["2d", "3d", "2d_fine", "2d_fail"])
+def test_bin_seeding_oracle_matches_sklearn_golden(golden, case):
+    """`oracle.mean_shift.get_bin_seeds` + the restated fit/predict against scikit-learn's own
+    `get_bin_seeds` / `MeanShift(bin_seeding=True)` outputs (tests/golden/bin_seeding.npz)."""
+    g = golden("bin_seeding")
+    emb, bw = g[f"{case}_emb"].astype(np.float64), float(g[f"{case}_bw"])
+    D = emb.shape[0] - 1
+    X = oms.points_from_embedding(emb[:D], emb[D] < 0.5)
+    seeds = np.asarray(oms.get_bin_seeds(X, bw), dtype=np.float64)
+    assert np.array_equal(seeds, g[f"{case}_seeds"])  # same bins, same first-seen order, same float32 products
+    labels, centres = oms.segment_points(X, None, bw, seeds=seeds)
+    assert np.array_equal(centres, g[f"{case}_centres"]) and np.array_equal(labels, g[f"{case}_labels"])

@@ -176,6 +176,27 @@ def test_zarr_lite_compressor_roundtrip(tmp_path, codec):
         assert raw == x[0].tobytes()
 
 
+def test_torch_library_ops_are_registered_with_fake_impls():
+    """`torch.ops.cellulus_b200.*`: schema + fake (meta) implementations, checked without a GPU by shape propagation."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    import cellulus_b200.ops  # noqa: F401
+
+    ns = torch.ops.cellulus_b200
+    assert "Tensor offsets, Tensor anchor_coordinates" in str(ns.oce_loss_fused.default._schema)
+    with FakeTensorMode():
+        o = torch.empty(2, 2, 16, 20, device="cuda").contiguous(memory_format=torch.channels_last)
+        a = torch.empty(2, 50, 2, dtype=torch.int64, device="cuda")
+        res, grad = ns.oce_loss_fused(o, a, a, 10.0, 1e-5)
+        assert res.shape == (4,) and grad.shape == o.shape and grad.dtype == torch.float32
+        assert grad.is_contiguous(memory_format=torch.channels_last)
+        res, grad = ns.oce_loss_sampled(torch.empty(1, 3, 8, 9, 10, device="cuda"), 3.0, 40, 5, 1, 0, 10.0, 1e-5)
+        assert res.shape == (4,) and grad.shape == (1, 3, 8, 9, 10)
+        assert ns.tta_aggregate(torch.empty(8, 2, 5, 6, device="cuda")).shape == (3, 5, 6)
+        lab = ns.detect_volume(torch.empty(4, 5, 6, 7, device="cuda"), 3.0, 0.5, 1.0, 0)
+        assert lab.shape == (5, 6, 7) and lab.dtype == torch.int32
+
+
 def test_unet_stand_in_geometry_and_checkpoint_keys():
     m = get_model(in_channels=1, out_channels=2, num_fmaps=12, fmap_inc_factor=2, features_in_last_layer=64,
                   downsampling_factors=[(2, 2)], num_spatial_dims=2)
