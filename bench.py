@@ -871,6 +871,84 @@ def bench_multi_gpu(dev, rank, world, dist):
     return out
 
 
+# ------------------------------------------------------------------------------- BASELINE configs[3] sweep
+def run_sweep(args):
+    """`--sweep`: mean-shift on synthetic embeddings of 1M - 64M foreground points, D in {2, 3}, bandwidth in
+    {0.5, 1, 2} x object radius, seeds = every foreground point vs scikit-learn's grid-binned seeds
+    (SURVEY 8d D2).  One JSON line {"sweep": [...]}; per row: device time threshold -> labels (CUDA events),
+    foreground points labelled per second.  CPU legs (the reference's engine, scikit-learn, hill climb on one core)
+    at 1 M points: binned seeding in full, all-point seeding on a 200-seed subset with the extrapolation stated."""
+    from cellulus_b200 import kernels as K
+    from cellulus_b200 import synthetic
+    from cellulus_b200.utils.mean_shift import segment_embeddings_device
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    radius = 10.0
+    rows = []
+    for D in (2, 3):
+        fg_frac = (np.pi * radius**2) / (2.6 * radius) ** 2 if D == 2 else (4.0 / 3.0 * np.pi * radius**3) / (2.6 * radius) ** 3
+        for n_m in (1, 4, 16, 64):
+            if n_m > args.sweep_max:
+                continue
+            side = int(round((n_m * 1e6 / fg_frac) ** (1.0 / D)))
+            shape = (side,) * D
+            base, fg, gen = synthetic.block_scene(shape, radius, 7 * D + n_m, dev)
+            emb = torch.empty((D + 1, *shape), device=dev)
+            emb[:D] = base + torch.where(fg, 0.5, 1.0)[None] * torch.randn(base.shape, generator=gen, device=dev)
+            emb[D] = torch.where(fg, 0.0, 1.0) + 0.1 * torch.rand(shape, generator=gen, device=dev)
+            n_fg = int(fg.sum().item())
+            del base, fg
+            for bw_factor in (0.5, 1.0, 2.0):
+                bw = bw_factor * radius
+                for seeding in ("all_foreground", "grid_binned"):
+                    kw = dict(reduction_probability=1.0, bin_seeding=(seeding == "grid_binned"), method="grid",
+                              label_dtype=torch.int32)
+                    try:
+                        segment_embeddings_device(emb, bw, 0.5, **kw)  # warm-up (allocator, first launches)
+                        torch.cuda.synchronize(dev)
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        labels, info = segment_embeddings_device(emb, bw, 0.5, **kw)
+                        e1.record()
+                        torch.cuda.synchronize(dev)
+                        ms = e0.elapsed_time(e1)
+                        row = {"D": D, "shape": list(shape), "fg_points": n_fg, "bandwidth": bw, "seeds": seeding,
+                               "n_seeds": int(info["n_seeds"]), "centres": int(info["k"]), "ms": round(ms, 3),
+                               "fg_points_per_s": round(n_fg / ms * 1e3), "Mpx_per_s": round(float(np.prod(shape)) / ms / 1e3, 1),
+                               "distance_tests": K.grid_modes_distance_tests(), "climb_steps": K.grid_modes_climb_steps()}
+                        del labels, info
+                    except Exception as e:  # noqa: BLE001  (e.g. out of memory at the largest sizes)
+                        row = {"D": D, "fg_points": n_fg, "bandwidth": bw, "seeds": seeding, "error": str(e)[:160]}
+                        torch.cuda.empty_cache()
+                    if n_m == 1 and bw_factor == 1.0 and not args.skip_cpu:
+                        row["cpu_baseline"] = sweep_cpu_leg(emb, D, bw, seeding)
+                    rows.append(row)
+                    print(json.dumps(row), file=sys.stderr, flush=True)
+            del emb
+            torch.cuda.empty_cache()
+    print(json.dumps({"metric": "mean-shift sweep (BASELINE configs[3])", "unit": "ms per point set (threshold -> labels, device)",
+                      "sweep": rows}), flush=True)
+
+
+def sweep_cpu_leg(emb, D, bw, seeding):
+    from oracle import mean_shift as oms
+
+    e = emb.cpu().numpy().astype(np.float64)
+    X = oms.points_from_embedding(e[:D], e[D] < 0.5)
+    if seeding == "grid_binned":
+        fit_s, pred_s, n_seeds, k = oms.sklearn_cluster_seconds(X, bw, bin_seeding=True)
+        return {"seconds": fit_s + pred_s, "fit_seconds": fit_s, "predict_seconds": pred_s, "n_seeds": n_seeds, "centres": k,
+                "kind": "port", "cores": 1, "sample": f"full point set ({len(X)} points), scikit-learn MeanShift(bin_seeding=True)"}
+    rng = np.random.default_rng(0)
+    subset = X[rng.choice(len(X), 200, replace=False)]
+    fit_s, pred_s, _, _ = oms.sklearn_cluster_seconds(X, bw, seeds=subset)
+    per_seed = fit_s / 200  # includes the one-off KD-tree build: an upper bound per seed
+    return {"seconds_extrapolated": per_seed * len(X) + pred_s, "per_seed_ms": per_seed * 1e3, "kind": "port", "cores": 1,
+            "sample": f"200 of {len(X)} seeds climbed by scikit-learn on the full point set, x {len(X)} / 200 (the "
+                      "reference seeds with every fit point; a full run would take hours)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -879,8 +957,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--skip-detect", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="BASELINE configs[3]: mean-shift sweep instead of the headline")
+    ap.add_argument("--sweep-max", type=float, default=16, help="largest point set of the sweep, millions (64 = all)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.sweep:
+        run_sweep(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

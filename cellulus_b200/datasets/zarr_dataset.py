@@ -36,6 +36,7 @@ class ZarrDataset(IterableDataset):  # type: ignore
         kappa: float,
         normalization_factor: float,
         sample_pairs: bool = True,
+        coordinate_dtype=np.int64,
     ):
         self.dataset_config = dataset_config
         self.crop_size = tuple(crop_size)
@@ -44,6 +45,10 @@ class ZarrDataset(IterableDataset):  # type: ignore
         self.control_point_jitter = control_point_jitter
         self.normalization_factor = normalization_factor
         self.sample_pairs = sample_pairs
+        # host pair lists are int64 in the reference (numpy's default); a narrower type (np.int16 / np.int32) is
+        # converted HERE, in the DataLoader workers, so that the training step ships a quarter / half of the bytes
+        # over PCIe -- the loss kernels read int16 / int32 / int64 lists alike
+        self.coordinate_dtype = np.dtype(coordinate_dtype)
         meta = DatasetMetaData.from_dataset_config(dataset_config)
         self.num_dims = meta.num_dims
         self.num_spatial_dims = meta.num_spatial_dims
@@ -91,6 +96,10 @@ class ZarrDataset(IterableDataset):  # type: ignore
                     break
             if self.sample_pairs:
                 anchors, refs = self.sample_coordinates()
+                if self.coordinate_dtype != anchors.dtype:
+                    if max(self.output_shape) > np.iinfo(self.coordinate_dtype).max:
+                        raise ValueError(f"coordinate_dtype {self.coordinate_dtype} cannot hold the output extent {self.output_shape}")
+                    anchors, refs = anchors.astype(self.coordinate_dtype), refs.astype(self.coordinate_dtype)
                 yield crop, anchors, refs
             else:
                 yield crop

@@ -207,3 +207,22 @@ def segment_points(X, fit_mask, bandwidth, seeds=None):
     modes, counts, _ = mean_shift_modes(Xr, s, bandwidth)
     centres = nms_centres(modes, counts, bandwidth)
     return predict_labels(X, centres), centres
+
+
+def sklearn_cluster_seconds(X, bandwidth, seeds=None, bin_seeding=False):
+    """Wall time of the reference's engine on a point set: `MeanShift(bandwidth, seeds=, bin_seeding=,
+    cluster_all=False).fit(X)` followed by `.predict(X)` (what `AnchorMeanshift.compute_mean_shift` runs,
+    `cellulus/utils/mean_shift.py:60-76`; `n_jobs=None`: the hill climb is single-core).  For the CPU legs of the
+    benchmark sweep.  Returns `(fit_seconds, predict_seconds, n_seeds_climbed, n_centres)`."""
+    import time
+
+    from sklearn.cluster import MeanShift
+
+    ms = MeanShift(bandwidth=bandwidth, seeds=seeds, bin_seeding=bin_seeding, cluster_all=False)
+    t0 = time.perf_counter()
+    ms.fit(X)
+    t1 = time.perf_counter()
+    ms.predict(X)
+    t2 = time.perf_counter()
+    n_seeds = len(seeds) if seeds is not None else (len(get_bin_seeds(X, bandwidth)) if bin_seeding else len(X))
+    return t1 - t0, t2 - t1, n_seeds, len(ms.cluster_centers_)

@@ -106,6 +106,11 @@ def test_dataset_crops_and_host_sampler_match_reference_order(tmp_path):
     np.random.seed(3)
     a_ref, r_ref = osampler.sample_coordinates((44, 44), 10.0, 0.1, 2)
     assert np.array_equal(anchors, a_ref) and np.array_equal(refs, r_ref)
+    assert anchors.dtype == np.int64  # the reference's list format
+    ds.coordinate_dtype = np.dtype(np.int16)  # narrowed in the DataLoader worker: a quarter of the PCIe bytes
+    np.random.seed(3)
+    _, a16, r16 = next(iter(ds))
+    assert a16.dtype == np.int16 and np.array_equal(a16, a_ref) and np.array_equal(r16, r_ref)
 
 
 def test_elastic_augmentation(tmp_path):

@@ -13,6 +13,10 @@ from cellulus_b200.detect import detect_embeddings  # noqa: E402
 from cellulus_b200.models import tta_aggregate  # noqa: E402
 
 what = sys.argv[1] if len(sys.argv) > 1 else "all"
+if os.environ.get("CB200_PROFILE_SMALL"):  # compute-sanitizer runs: same code paths, sizes it finishes in seconds
+    bench.B, bench.OUT = 2, (124, 124)
+    bench.N_ANCHORS, bench.N_REFS = int(0.1 * 104 * 104), 31
+    bench.DET_SHAPE, bench.DET_OBJECTS = (32, 64, 64), 25
 dev = torch.device("cuda:0")
 torch.cuda.set_device(dev)
 if what in ("all", "loss"):
