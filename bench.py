@@ -904,6 +904,11 @@ def run_sweep(args):
                 for seeding in ("all_foreground", "grid_binned"):
                     kw = dict(reduction_probability=1.0, bin_seeding=(seeding == "grid_binned"), method="grid",
                               label_dtype=torch.int32)
+                    if seeding == "all_foreground" and n_m * bw_factor**D > 64:
+                        # every point a seed with a wide window: > 1e12 distance tests -- tens of seconds here, weeks on
+                        # the CPU reference; left out of the sweep
+                        rows.append({"D": D, "fg_points": n_fg, "bandwidth": bw, "seeds": seeding, "skipped": "work > 64 M x r^D"})
+                        continue
                     try:
                         segment_embeddings_device(emb, bw, 0.5, **kw)  # warm-up (allocator, first launches)
                         torch.cuda.synchronize(dev)
