@@ -59,7 +59,9 @@ PROTOTYPES = {
     "cb200_error_string": (C.c_char_p, [_i]),
     "cb200_fma_peak": (_i, [_i, _i, _i, _p, _pi64, _p]),
     "cb200_oce_loss_workspace_bytes": (_i64, []),
+    "cb200_oce_loss_staging_bytes": (_i64, [_i, _i, _i, _i, _pi64]),
     "cb200_oce_loss_fwd_bwd": (_i, [_p, _i, _i, _p, _p, _i, _i, _i, _pi64, _i64, _f, _f, _p, _p, _p, _p]),
+    "cb200_oce_loss_fwd_bwd_staged": (_i, [_p, _i, _i, _p, _p, _i, _i, _i, _pi64, _i64, _f, _f, _p, _p, _p, _p, _i64, _p]),
     "cb200_scale_inplace": (_i, [_p, _i64, _p, _p]),
     "cb200_gather_add_coords": (_i, [_p, _i, _p, _i, _i, _i, _pi64, _i64, _p, _p]),
     "cb200_scatter_add_coords": (_i, [_p, _p, _i, _i, _i, _pi64, _i64, _p, _p]),

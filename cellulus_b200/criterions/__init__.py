@@ -1,6 +1,7 @@
 """Loss factory with the reference's call signature (`cellulus/criterions/__init__.py:4-17`)."""
 
 from cellulus_b200.criterions.oce_loss import (  # noqa: F401
+    GraphedLossCycle,
     GraphedLossStep,
     OCELoss,
     oce_loss_fused,

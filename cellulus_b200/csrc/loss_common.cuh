@@ -12,7 +12,11 @@ struct LossWorkspace {
   unsigned long long bad;   // pairs skipped: coordinate out of range
   unsigned int ticket;      // blocks finished
   unsigned int pad;
+  // in-kernel operand preparation (oce_loss.cu): CTAs that have finished their slice, per sample slot (b % 32);
+  // one counter per 128-byte line so that the pollers of different samples hit different L2 slices
+  unsigned int arrived[32 * 32];
 };
+constexpr unsigned LOSS_ZERO_SLOTS = 32, LOSS_ZERO_PITCH = 32;
 
 template <int D>
 struct Shape {
@@ -109,6 +113,8 @@ __device__ __forceinline__ void block_reduce_to_workspace(float oce, float nrm, 
     ws->acc[1] = 0.0;
     ws->bad = 0ull;
     ws->ticket = 0u;
+#pragma unroll
+    for (unsigned i = 0; i < LOSS_ZERO_SLOTS; ++i) ws->arrived[i * LOSS_ZERO_PITCH] = 0u;
   }
 }
 

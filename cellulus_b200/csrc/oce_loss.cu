@@ -218,6 +218,170 @@ oce_loss_fused_kernel(const OT* __restrict__ offsets, const CT* __restrict__ anc
   block_reduce_to_workspace(acc_oce, acc_nrm, bad, ws, w, out);
 }
 
+// ---- the fused kernel for PLANAR 2-D tensors with staging scratch -------------------------------------
+// The reference's model emits planar NCHW offsets (models/unet.py:69-71); gathered in place, a scattered reference
+// pixel costs one L1 wavefront per lane PER CHANNEL (57 us per configs[1] step against 47 us channels-last).  This
+// form prepares its own operands inside the launch: the CTAs of a sample write a channels-last copy of that
+// sample's offsets into caller scratch (`staged`; prep & 4: two pixels per thread, 8-byte loads, 16-byte stores)
+// and clear the sample's gradient (prep & 3: 1 = scalar stores, 2 = 16-byte stores) between them; each CTA then
+// counts itself in and, with its first list loads in flight, waits until every CTA of its sample slot has
+// arrived.  All CTAs of the grid are co-resident by construction (one wave, checked by the launcher), so the wait
+// cannot starve.  From there on it is the kernel above with 8-byte gathers from the copy; the gradient -- one
+// reduction per run of equal anchors -- stays planar.  ONE launch per step.
+// (The same in-kernel clearing for the other layouts was built and measured: 49.5 us against 49.4 us behind the
+// zero-fill grid with an identical body -- programmatic dependent launch already hides the zero-fill.)
+template <int D, typename OT>
+__device__ __forceinline__ void gather_staged(const OT* base, unsigned first, unsigned pix, float (&o)[D]) {
+  static_assert(D == 2, "staged gathers are built for 2-D embeddings");
+  // the copy was written by other CTAs of THIS launch: plain (coherent) loads, not ld.global.nc
+  if constexpr (sizeof(OT) == 4) {
+    asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(o[0]), "=f"(o[1]) : "l"(reinterpret_cast<const float2*>(base) + (first + pix)));
+  } else {
+    unsigned v;
+    asm volatile("ld.global.b32 %0, [%1];" : "=r"(v) : "l"(reinterpret_cast<const unsigned*>(base) + (first + pix)));
+    o[0] = __uint_as_float(v << 16);
+    o[1] = __uint_as_float(v & 0xffff0000u);
+  }
+}
+
+template <typename OT>
+__device__ __forceinline__ void chunk_gather_staged(Chunk<2>& c, const OT* staged, unsigned first, const Shape<2>& shape,
+                                                    int& bad) {
+  constexpr int D = 2;
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < D; ++k)
+    ok = ok && ((unsigned)c.ca[k] < (unsigned)shape.ext[k]) && ((unsigned)c.cr[k] < (unsigned)shape.ext[k]);
+  int pa, pr;
+  if (__builtin_expect(__any_sync(FULL, c.live && !ok), 0)) {
+    int wa[D], wr[D];
+    ok = wrap_and_check<D>(c.ca, wa, shape) & wrap_and_check<D>(c.cr, wr, shape);
+    pa = pixel_of<D>(wa, shape);
+    pr = pixel_of<D>(wr, shape);
+    if (c.live && !ok) ++bad;
+  } else {
+    pa = pixel_of<D>(c.ca, shape);
+    pr = pixel_of<D>(c.cr, shape);
+  }
+  c.live = c.live && ok;
+  c.pix_a = c.live ? pa : -1;
+  if (c.live) {
+    gather_staged<D, OT>(staged, first, (unsigned)pa, c.oa);
+    gather_staged<D, OT>(staged, first, (unsigned)pr, c.orf);
+  } else {
+#pragma unroll
+    for (int k = 0; k < D; ++k) c.oa[k] = c.orf[k] = 0.f;
+  }
+}
+
+template <typename CT, typename OT, bool BWD>
+__global__ void __launch_bounds__(LOSS_THREADS, LOSS_MIN_BLOCKS)
+oce_loss_staged_kernel(const OT* __restrict__ offsets, const CT* __restrict__ anchors, const CT* __restrict__ refs,
+                       unsigned P, unsigned chunks_per_sample, Shape<2> shape, float neg_log2e_over_t, float two_over_t,
+                       float w, float* __restrict__ grad, LossWorkspace* ws, float* out, unsigned prep, OT* staged) {
+  constexpr int D = 2;
+  const unsigned lane = lane_id();
+  const unsigned b = blockIdx.y;
+  const unsigned stride = gridDim.x * (LOSS_THREADS / 32);
+  const unsigned npix = (unsigned)shape.npix;
+  if constexpr (BWD) {
+    const unsigned n = npix * D;  // floats per sample (< 2^31: make_shape)
+    float* __restrict__ g = grad + (size_t)b * n;
+    const unsigned per = ((n + gridDim.x - 1) / gridDim.x + 3u) & ~3u;
+    const unsigned lo = min(n, blockIdx.x * per), hi = min(n, lo + per);
+    if ((prep & 3u) == 2u) {
+      float4* __restrict__ g4 = reinterpret_cast<float4*>(g + lo);
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (unsigned i = threadIdx.x; i < ((hi - lo) >> 2); i += LOSS_THREADS) g4[i] = z;
+    } else {
+      for (unsigned i = lo + threadIdx.x; i < hi; i += LOSS_THREADS) g[i] = 0.f;
+    }
+  }
+  {
+    // planar (2, npix) -> interleaved (npix, 2) for this CTA's slice of the sample's pixels
+    const OT* __restrict__ src = offsets + (size_t)b * npix * 2;
+    OT* __restrict__ dst = staged + (size_t)b * npix * 2;
+    const unsigned per = ((npix + gridDim.x - 1) / gridDim.x + 1u) & ~1u;
+    const unsigned lo = min(npix, blockIdx.x * per), hi = min(npix, lo + per);
+    bool done = false;
+    if constexpr (sizeof(OT) == 4) {
+      if ((prep & 4u) != 0) {  // even npix, aligned bases
+        for (unsigned i = lo + 2 * threadIdx.x; i + 1 < hi; i += 2 * LOSS_THREADS) {
+          const float2 x = __ldg(reinterpret_cast<const float2*>(src + i));
+          const float2 y = __ldg(reinterpret_cast<const float2*>(src + npix + i));
+          *reinterpret_cast<float4*>(dst + 2 * (size_t)i) = make_float4(x.x, y.x, x.y, y.y);
+        }
+        done = true;
+      }
+    }
+    if (!done) {
+      for (unsigned i = lo + threadIdx.x; i < hi; i += LOSS_THREADS) {
+        dst[2 * (size_t)i] = src[i];
+        dst[2 * (size_t)i + 1] = src[npix + i];
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&ws->arrived[(b % LOSS_ZERO_SLOTS) * LOSS_ZERO_PITCH]) : "memory");
+
+  const CT* __restrict__ a_base = anchors + (size_t)b * P * D;
+  const CT* __restrict__ r_base = refs + (size_t)b * P * D;
+  const unsigned first = b * npix;
+  float acc_oce = 0.f, acc_nrm = 0.f;
+  int bad = 0;
+  RawCoord<D, CT> na, nr;
+  auto fetch = [&](unsigned c) {
+    const unsigned p = (c << 5) + lane;
+    if (c < chunks_per_sample && p < P) {
+      na.load(a_base, p);
+      nr.load(r_base, p);
+    }
+  };
+  auto take = [&](Chunk<D>& ch, unsigned c) {
+    ch.live = c < chunks_per_sample && ((c << 5) + lane) < P;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      ch.ca[k] = na.get(k);
+      ch.cr[k] = nr.get(k);
+    }
+  };
+  unsigned c0 = blockIdx.x * (LOSS_THREADS / 32) + (threadIdx.x >> 5);
+  const bool has_work = c0 < chunks_per_sample;
+  Chunk<D> cur, nxt;
+  na.zero();
+  nr.zero();
+  if (has_work) {
+    fetch(c0);
+    take(cur, c0);
+    fetch(c0 + stride);
+  }
+  // every CTA of the sample slot has written its slice: one poller per CTA, the other warps park on the barrier
+  if (threadIdx.x == 0) {
+    const unsigned slot = b % LOSS_ZERO_SLOTS;
+    const unsigned target = gridDim.x * ((gridDim.y - slot + LOSS_ZERO_SLOTS - 1) / LOSS_ZERO_SLOTS);
+    const unsigned* flag = &ws->arrived[slot * LOSS_ZERO_PITCH];
+    unsigned seen;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+      if (seen >= target) break;
+      __nanosleep(40);
+    }
+  }
+  __syncthreads();
+  if (has_work) {
+    chunk_gather_staged<OT>(cur, staged, first, shape, bad);
+    for (; c0 < chunks_per_sample; c0 += stride) {
+      chunk_finish<D, BWD, false>(cur, grad, first, shape, neg_log2e_over_t, two_over_t, w, lane, acc_oce, acc_nrm);
+      take(nxt, c0 + stride);
+      fetch(c0 + 2 * stride);
+      if (c0 + stride < chunks_per_sample) chunk_gather_staged<OT>(nxt, staged, first, shape, bad);
+      cur = nxt;
+    }
+  }
+  block_reduce_to_workspace(acc_oce, acc_nrm, bad, ws, w, out);
+}
+
 // zero-fill of the gradient tensor: 4 independent 16-byte stores per thread per trip, one wave
 __global__ void __launch_bounds__(256) zero_fill_kernel(float4* __restrict__ p, int64_t n4, float* __restrict__ tail,
                                                         int n_tail) {
@@ -405,15 +569,72 @@ static int launch_fused_variant(const void* offsets, const void* anchors, const 
   return CB200_OK;
 }
 
+// CB200_LOSS_STAGED=0: planar tensors are gathered in place even when the caller passes staging scratch;
+// CB200_LOSS_COOP=1: cooperative instead of plain launch of the staged form (+3 us per launch, measured).  A/B switches.
+static const bool g_staged = [] { const char* e = getenv("CB200_LOSS_STAGED"); return !(e && e[0] == '0'); }();
+static const bool g_coop = [] { const char* e = getenv("CB200_LOSS_COOP"); return e && e[0] == '1'; }();
+
+// returns CB200_OK with *launched = false when the staged form does not apply (grid larger than one resident wave)
+template <typename CT, typename OT, bool BWD>
+static int launch_staged_variant(const void* offsets, const void* anchors, const void* refs, int batch, const Shape<2>& shape,
+                                 int64_t P, float T, float w, float* grad, float* out, LossWorkspace* ws, void* staged,
+                                 cudaStream_t st, bool* launched) {
+  auto kernel = oce_loss_staged_kernel<CT, OT, BWD>;
+  static int occupancy = 0;  // per template instantiation
+  if (occupancy == 0) {
+    int occ = 0;
+    CB200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, LOSS_THREADS, 0));
+    occupancy = occ > 0 ? occ : 1;
+  }
+  const unsigned cps = (unsigned)((P + 31) >> 5);
+  unsigned blocks_x = (unsigned)((CB200_SM_COUNT * occupancy) / batch);
+  const unsigned needed = (cps + (LOSS_THREADS / 32) - 1) / (LOSS_THREADS / 32);
+  if (blocks_x > needed) blocks_x = needed;
+  if (blocks_x < 1) blocks_x = 1;
+  *launched = false;
+  // the CTAs wait for each other: every one of them must be resident at once
+  if ((uint64_t)blocks_x * batch > (uint64_t)CB200_SM_COUNT * occupancy) return CB200_OK;
+  unsigned prep = ((shape.npix % 2 == 0) && reinterpret_cast<uintptr_t>(offsets) % 8 == 0 &&
+                   reinterpret_cast<uintptr_t>(staged) % 16 == 0) ? 4u : 8u;
+  if (BWD) prep |= ((reinterpret_cast<uintptr_t>(grad) % 16 == 0) && ((shape.npix * 2) % 4 == 0)) ? 2u : 1u;
+  const float log2e = 1.4426950408889634f;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks_x, (unsigned)batch);
+  cfg.blockDim = dim3(LOSS_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.numAttrs = g_coop ? 1 : 0;
+  CB200_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, (const OT*)offsets, (const CT*)anchors, (const CT*)refs, (unsigned)P,
+                                    cps, shape, -log2e / T, 2.0f / T, w, grad, ws, out, prep, (OT*)staged));
+  *launched = true;
+  return CB200_OK;
+}
+
 template <int D, typename CT, typename OT>
 static int launch_fused(const void* offsets, int layout, const void* anchors, const void* refs, int batch,
                         const int64_t* spatial, int64_t P, float T, float w, float* grad, float* out, void* workspace,
-                        cudaStream_t st) {
+                        void* staging, int64_t staging_bytes, cudaStream_t st) {
   Shape<D> shape;
   if (!make_shape<D>(spatial, shape)) return CB200_EINVAL;
   if (P >= ((int64_t)1 << 31) - 64 || batch > 65535) return CB200_EUNSUPPORTED;
   if ((int64_t)batch * D * shape.npix > INT32_MAX) return CB200_EUNSUPPORTED;  // 32-bit element indices
   auto* ws = static_cast<LossWorkspace*>(workspace);
+  if constexpr (D == 2) {
+    // planar tensors + caller scratch: gather from a channels-last copy made inside the kernel (one-wave grids)
+    if (layout == CB200_LAYOUT_PLANAR && g_staged && staging &&
+        staging_bytes >= (int64_t)sizeof(OT) * batch * D * shape.npix && reinterpret_cast<uintptr_t>(staging) % (2 * sizeof(OT)) == 0) {
+      bool launched = false;
+      const int rc = grad ? launch_staged_variant<CT, OT, true>(offsets, anchors, refs, batch, shape, P, T, w, grad, out, ws,
+                                                               staging, st, &launched)
+                          : launch_staged_variant<CT, OT, false>(offsets, anchors, refs, batch, shape, P, T, w, grad, out, ws,
+                                                                staging, st, &launched);
+      if (rc != CB200_OK || launched) return rc;
+    }
+  }
   if (grad) {
     const int rc = zero_fill(grad, (int64_t)batch * D * shape.npix, st);
     if (rc != CB200_OK) return rc;
@@ -431,22 +652,24 @@ static int launch_fused(const void* offsets, int layout, const void* anchors, co
 template <int D, typename CT>
 static int dispatch_offsets(const void* offsets, int odt, int layout, const void* a, const void* r, int batch,
                             const int64_t* spatial, int64_t P, float T, float w, float* grad, float* out, void* ws,
-                            cudaStream_t st) {
+                            void* staging, int64_t staging_bytes, cudaStream_t st) {
   if (odt == CB200_F32)
-    return launch_fused<D, CT, float>(offsets, layout, a, r, batch, spatial, P, T, w, grad, out, ws, st);
+    return launch_fused<D, CT, float>(offsets, layout, a, r, batch, spatial, P, T, w, grad, out, ws, staging,
+                                      staging_bytes, st);
   if (odt == CB200_BF16)
-    return launch_fused<D, CT, __nv_bfloat16>(offsets, layout, a, r, batch, spatial, P, T, w, grad, out, ws, st);
+    return launch_fused<D, CT, __nv_bfloat16>(offsets, layout, a, r, batch, spatial, P, T, w, grad, out, ws, staging,
+                                              staging_bytes, st);
   return CB200_EUNSUPPORTED;
 }
 
 template <int D>
 static int dispatch_coords(const void* offsets, int odt, int layout, const void* a, const void* r, int cdt, int batch,
                            const int64_t* spatial, int64_t P, float T, float w, float* grad, float* out, void* ws,
-                           cudaStream_t st) {
+                           void* sg, int64_t sgb, cudaStream_t st) {
   switch (cdt) {
-    case CB200_I64: return dispatch_offsets<D, long long>(offsets, odt, layout, a, r, batch, spatial, P, T, w, grad, out, ws, st);
-    case CB200_I32: return dispatch_offsets<D, int>(offsets, odt, layout, a, r, batch, spatial, P, T, w, grad, out, ws, st);
-    case CB200_I16: return dispatch_offsets<D, short>(offsets, odt, layout, a, r, batch, spatial, P, T, w, grad, out, ws, st);
+    case CB200_I64: return dispatch_offsets<D, long long>(offsets, odt, layout, a, r, batch, spatial, P, T, w, grad, out, ws, sg, sgb, st);
+    case CB200_I32: return dispatch_offsets<D, int>(offsets, odt, layout, a, r, batch, spatial, P, T, w, grad, out, ws, sg, sgb, st);
+    case CB200_I16: return dispatch_offsets<D, short>(offsets, odt, layout, a, r, batch, spatial, P, T, w, grad, out, ws, sg, sgb, st);
   }
   return CB200_EUNSUPPORTED;
 }
@@ -496,10 +719,30 @@ extern "C" {
 int64_t cb200_oce_loss_workspace_bytes(void) { return (int64_t)sizeof(LossWorkspace); }
 
 
+int64_t cb200_oce_loss_staging_bytes(int offsets_dtype, int offsets_layout, int batch, int num_dims, const int64_t* spatial) {
+  if (!spatial || batch <= 0 || num_dims != 2 || offsets_layout != CB200_LAYOUT_PLANAR) return 0;
+  const int64_t esize = offsets_dtype == CB200_F32 ? 4 : offsets_dtype == CB200_BF16 ? 2 : 0;
+  int64_t n = (int64_t)batch * num_dims * esize;
+  for (int k = 0; k < num_dims; ++k) {
+    if (spatial[k] <= 0) return 0;
+    n *= spatial[k];
+  }
+  return n;
+}
+
 int cb200_oce_loss_fwd_bwd(const void* offsets, int offsets_dtype, int offsets_layout, const void* anchors,
                            const void* refs, int coord_dtype, int batch, int num_dims, const int64_t* spatial, int64_t pairs_per_sample,
                            float temperature, float regularization_weight, float* grad, float* out, void* workspace,
                            void* stream) {
+  return cb200_oce_loss_fwd_bwd_staged(offsets, offsets_dtype, offsets_layout, anchors, refs, coord_dtype, batch, num_dims,
+                                       spatial, pairs_per_sample, temperature, regularization_weight, grad, out,
+                                       workspace, nullptr, 0, stream);
+}
+
+int cb200_oce_loss_fwd_bwd_staged(const void* offsets, int offsets_dtype, int offsets_layout, const void* anchors,
+                                  const void* refs, int coord_dtype, int batch, int num_dims, const int64_t* spatial,
+                                  int64_t pairs_per_sample, float temperature, float regularization_weight, float* grad,
+                                  float* out, void* workspace, void* staging, int64_t staging_bytes, void* stream) {
   if (!offsets || !spatial || !out || !workspace) return CB200_EINVAL;
   if (batch <= 0 || pairs_per_sample < 0 || !(temperature != 0.f)) return CB200_EINVAL;
   if (pairs_per_sample > 0 && (!anchors || !refs)) return CB200_EINVAL;  // an empty list may be a null pointer
@@ -507,10 +750,10 @@ int cb200_oce_loss_fwd_bwd(const void* offsets, int offsets_dtype, int offsets_l
   cudaStream_t st = (cudaStream_t)stream;
   if (num_dims == 2)
     return dispatch_coords<2>(offsets, offsets_dtype, offsets_layout, anchors, refs, coord_dtype, batch, spatial, pairs_per_sample,
-                              temperature, regularization_weight, grad, out, workspace, st);
+                              temperature, regularization_weight, grad, out, workspace, staging, staging_bytes, st);
   if (num_dims == 3)
     return dispatch_coords<3>(offsets, offsets_dtype, offsets_layout, anchors, refs, coord_dtype, batch, spatial, pairs_per_sample,
-                              temperature, regularization_weight, grad, out, workspace, st);
+                              temperature, regularization_weight, grad, out, workspace, nullptr, 0, st);
   return CB200_EUNSUPPORTED;
 }
 

@@ -126,8 +126,9 @@ def _offsets_layout(offsets):
     return offsets.contiguous(), _cabi.LAYOUT_PLANAR
 
 
-def oce_loss_fwd_bwd(offsets, anchors, refs, temperature, regularization_weight, want_grad=True):
-    """`cb200_oce_loss_fwd_bwd`: returns `(out4, grad)`; out4 = [loss, oce, reg, n_bad] (fp32, device)."""
+def oce_loss_fwd_bwd(offsets, anchors, refs, temperature, regularization_weight, want_grad=True, staged=True):
+    """`cb200_oce_loss_fwd_bwd_staged`: returns `(out4, grad)`; out4 = [loss, oce, reg, n_bad] (fp32, device).
+    `staged=False` calls `cb200_oce_loss_fwd_bwd` (no staging scratch: planar offsets are gathered in place)."""
     B, D = _check_loss_inputs(offsets, [anchors, refs])
     offsets, layout = _offsets_layout(offsets)
     anchors = anchors.contiguous()
@@ -138,11 +139,15 @@ def oce_loss_fwd_bwd(offsets, anchors, refs, temperature, regularization_weight,
     # the gradient is produced in the memory layout of `offsets` (empty_like preserves channels_last)
     grad = torch.empty_like(offsets, dtype=torch.float32) if want_grad else None
     ws = _zero_workspace("loss", _lib().cb200_oce_loss_workspace_bytes(), offsets.device)
-    rc = _lib().cb200_oce_loss_fwd_bwd(
-        _ptr(offsets), odt, layout, _ptr(anchors), _ptr(refs), cdt, B, D, spatial_array(offsets.shape[2:]),
+    spatial = spatial_array(offsets.shape[2:])
+    # planar 2-D offsets (the reference's NCHW output): scratch for the kernel's own channels-last copy
+    staging_bytes = _lib().cb200_oce_loss_staging_bytes(odt, layout, B, D, spatial) if staged else 0
+    staging = torch.empty(staging_bytes, dtype=torch.uint8, device=offsets.device) if staging_bytes > 0 else None
+    rc = _lib().cb200_oce_loss_fwd_bwd_staged(
+        _ptr(offsets), odt, layout, _ptr(anchors), _ptr(refs), cdt, B, D, spatial,
         anchors.shape[1], float(temperature), float(regularization_weight), _ptr(grad), _ptr(out), _ptr(ws),
-        _stream(offsets))
-    check(rc, "cb200_oce_loss_fwd_bwd")
+        _ptr(staging), staging_bytes, _stream(offsets))
+    check(rc, "cb200_oce_loss_fwd_bwd_staged")
     launch_counter["calls"] += 1
     return out, grad
 

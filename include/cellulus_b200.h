@@ -72,8 +72,12 @@ CB200_API int cb200_fma_peak(int dtype, int iters, int blocks_per_sm, void* out,
  *  Loss slice (training)                                                *
  * ===================================================================== */
 
-/* bytes of scratch needed by cb200_oce_loss_fwd_bwd (accumulators + ticket) */
+/* bytes of scratch needed by cb200_oce_loss_fwd_bwd (accumulators, ticket, arrival counters) */
 CB200_API int64_t cb200_oce_loss_workspace_bytes(void);
+/* bytes of OPTIONAL staging scratch for cb200_oce_loss_fwd_bwd_staged: non-zero for 2-D CB200_LAYOUT_PLANAR
+ * offsets (one copy of the offsets tensor), 0 where staging is not used (channels-last, 3-D) */
+CB200_API int64_t cb200_oce_loss_staging_bytes(int offsets_dtype, int offsets_layout, int batch, int num_dims,
+                                     const int64_t* spatial /* host, num_dims */);
 
 /*
  * Fused neighbour gather + OCE loss forward + backward in ONE pass.
@@ -103,6 +107,22 @@ CB200_API int cb200_oce_loss_fwd_bwd(const void* offsets, int offsets_dtype, int
                            int64_t pairs_per_sample,
                            float temperature, float regularization_weight,
                            float* grad, float* out, void* workspace, void* stream);
+/*
+ * Same call with caller-provided staging scratch (`staging_bytes` >= cb200_oce_loss_staging_bytes(...), 16-byte
+ * aligned; contents undefined before and after).  For planar 2-D offsets -- what the reference's model emits,
+ * models/unet.py:69-71 -- the kernel first writes a channels-last copy of the offsets into the scratch (its
+ * thread blocks transpose their sample between them) and gathers from the copy, so that a scattered reference
+ * pixel costs one memory transaction instead of one per channel; gradient and results are identical in layout
+ * and value to cb200_oce_loss_fwd_bwd.  staging == NULL (or too small) behaves exactly like cb200_oce_loss_fwd_bwd.
+ * The gradient is cleared inside the same launch: ONE kernel per call.
+ */
+CB200_API int cb200_oce_loss_fwd_bwd_staged(const void* offsets, int offsets_dtype, int offsets_layout,
+                           const void* anchors, const void* refs, int coord_dtype,
+                           int batch, int num_dims, const int64_t* spatial /* host, num_dims */,
+                           int64_t pairs_per_sample,
+                           float temperature, float regularization_weight,
+                           float* grad, float* out, void* workspace,
+                           void* staging, int64_t staging_bytes, void* stream);
 
 /* grad *= *scale (device scalar); returns immediately on the device when *scale == 1.
  * Used by the autograd shim to apply the upstream gradient of `loss`. */

@@ -99,6 +99,37 @@ def test_fused_loss_matches_oracle_seeded(nd, coord_dtype):
     assert _rel(off_d.grad.cpu().numpy(), 2.0 * g_ref.numpy()) <= LOSS_RTOL
 
 
+@pytest.mark.parametrize("odt", [torch.float32, torch.bfloat16])
+def test_fused_loss_planar_staged_and_in_place_agree(odt):
+    """Planar 2-D offsets take one of three routes through the same entry: gathered from the kernel's own
+    channels-last copy (staging scratch passed, the default), gathered in place (no scratch), and -- when the grid
+    does not fit one resident wave (here: more samples than resident thread blocks) -- in place behind a separate
+    zero-fill grid.  All three against the oracle; odd extents exercise the scalar transposition / zero-fill."""
+    for B, out_shape, P in ((3, (61, 75), 3000), (2, (64, 96), 5000), (900, (12, 14), 64)):
+        rng = np.random.default_rng(B)
+        ext_xyz = np.array(out_shape[::-1])
+        anchors = np.stack([rng.integers(0, ext_xyz[k], size=(B, P)) for k in range(2)], -1)
+        anchors = np.repeat(anchors[:, ::16], 16, axis=1)[:, :P]
+        refs = np.clip(anchors + rng.integers(-5, 6, size=anchors.shape), 0, ext_xyz - 1)
+        anchors, refs = torch.from_numpy(anchors).long(), torch.from_numpy(refs).long()
+        offsets = torch.from_numpy(synthetic.loss_offsets(B, 2, out_shape, seed=3)).to(odt)
+        l_ref, o_ref, r_ref, g_ref = oloss.loss_step(offsets.float(), anchors, refs, 10.0, 1e-3)
+        off_d, a_d, r_d = offsets.to(_dev()), anchors.to(_dev()), refs.to(_dev())
+        for staged in (True, False):
+            for want_grad in (True, False):
+                out, grad = K.oce_loss_fwd_bwd(off_d, a_d, r_d, 10.0, 1e-3, want_grad=want_grad, staged=staged)
+                out = out.cpu().numpy()
+                assert abs(out[0] - l_ref.item()) <= LOSS_RTOL * abs(l_ref.item()), (B, staged, want_grad)
+                assert abs(out[2] - r_ref.item()) <= LOSS_RTOL * abs(r_ref.item())
+                assert out[3] == 0
+                if want_grad:
+                    assert grad.is_contiguous()
+                    assert _rel(grad.cpu().numpy(), g_ref.numpy()) <= LOSS_RTOL, (B, staged)
+        # the step is repeatable on the same workspace (arrival counters are left zeroed)
+        out2, grad2 = K.oce_loss_fwd_bwd(off_d, a_d, r_d, 10.0, 1e-3)
+        assert _rel(grad2.cpu().numpy(), g_ref.numpy()) <= LOSS_RTOL
+
+
 @pytest.mark.parametrize("nd", [2, 3])
 def test_fused_loss_channels_last_layout(nd):
     """The same op on a channels-last offsets tensor (zero-copy, vector gathers): identical results, and the
