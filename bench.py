@@ -668,7 +668,10 @@ def run_b200(args):
                                          "the gradient and gathers from its own channels-last copy of the offsets "
                                          "(15.7 MB staging scratch written inside the same launch)",
                        "roofline": {"bound": "hbm", "achieved": achieved_planar, "peak": peak, "unit": "GB/s",
-                                    "frac": achieved_planar / peak}},
+                                    "frac": achieved_planar / peak,
+                                    "traffic": ncu_traffic("oce_loss_staged_kernel<int64,f32,bwd>"),
+                                    "kernel": "oce_loss_staged_kernel<int64,f32,bwd> (one launch per step)",
+                                    "algorithmic_bytes_per_launch": ALGO_BYTES}},
             "bf16_offsets": {"value": world * N_PX / (ms_bf16 * 1e-3), "unit": "px/s", "ms_per_step": ms_bf16,
                              "offsets_layout": "channels_last, bf16 storage, fp32 arithmetic, fp32 gradient",
                              "roofline": {"bound": "hbm", "achieved": algo_bf16 / (ms_bf16 * 1e-3) / 1e9,

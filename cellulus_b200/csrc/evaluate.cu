@@ -23,17 +23,32 @@ __device__ __forceinline__ LabelVec<T> load_labels(const T* p, int64_t vec_index
   return r;
 }
 
+// Label images are mostly one value (background) and a few thousand objects: marking `present[v]` straight in
+// global memory makes every warp store to the same few bytes (measured 230 us for an 8 MB image: 36 GB/s).  Each
+// block therefore collects the values it sees in a shared-memory bitmap -- a broadcast read per label, an atomicOr
+// only the first time a bit is seen -- and writes the set bits out once at the end.  Values beyond the bitmap
+// (int32 labels >= PRESENCE_BITS) take the direct path.
+constexpr int PRESENCE_BITS = 1 << 16;  // covers every uint16 label
 template <typename T>
 __global__ void __launch_bounds__(256)
 label_presence_kernel(const T* __restrict__ labels, int64_t n, int64_t nvec, int max_value, uint8_t* __restrict__ present) {
   constexpr int N = LabelVec<T>::N;
+  __shared__ unsigned bits[PRESENCE_BITS / 32];
+  const int n_words = (min(max_value, PRESENCE_BITS - 1) >> 5) + 1;
+  for (int w = threadIdx.x; w < n_words; w += blockDim.x) bits[w] = 0u;
+  __syncthreads();
   const int64_t gs = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int last = -1;
   auto mark = [&](int v) {
     if (v == last || v < 0 || v > max_value) return;
     last = v;
-    if (!present[v]) present[v] = 1;
+    if (v < PRESENCE_BITS) {
+      const unsigned bit = 1u << (v & 31);
+      if (!(bits[v >> 5] & bit)) atomicOr(&bits[v >> 5], bit);
+    } else if (!present[v]) {
+      present[v] = 1;
+    }
   };
   for (int64_t i = tid; i < nvec; i += gs) {
     const LabelVec<T> x = load_labels<T>(labels, i);
@@ -41,6 +56,15 @@ label_presence_kernel(const T* __restrict__ labels, int64_t n, int64_t nvec, int
     for (int k = 0; k < N; ++k) mark((int)x.v[k]);
   }
   for (int64_t i = nvec * N + tid; i < n; i += gs) mark((int)labels[i]);  // tail
+  __syncthreads();
+  for (int w = threadIdx.x; w < n_words; w += blockDim.x) {
+    unsigned m = bits[w];
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      present[w * 32 + b] = 1;
+    }
+  }
 }
 
 template <typename T>
@@ -108,10 +132,10 @@ int cb200_label_presence(const void* labels, int dtype, int64_t n, int max_value
   const bool aligned = reinterpret_cast<uintptr_t>(labels) % 16 == 0;
   if (dtype == CB200_U16) {
     const int64_t nvec = aligned ? n / 8 : 0;
-    label_presence_kernel<uint16_t><<<grid_for(nvec + 256, 256, 2, 8), 256, 0, st>>>((const uint16_t*)labels, n, nvec, max_value, present);
+    label_presence_kernel<uint16_t><<<grid_for(nvec + 256, 256, 4, 4), 256, 0, st>>>((const uint16_t*)labels, n, nvec, max_value, present);
   } else if (dtype == CB200_I32) {
     const int64_t nvec = aligned ? n / 4 : 0;
-    label_presence_kernel<int32_t><<<grid_for(nvec + 256, 256, 2, 8), 256, 0, st>>>((const int32_t*)labels, n, nvec, max_value, present);
+    label_presence_kernel<int32_t><<<grid_for(nvec + 256, 256, 4, 4), 256, 0, st>>>((const int32_t*)labels, n, nvec, max_value, present);
   } else {
     return CB200_EUNSUPPORTED;
   }
