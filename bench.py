@@ -458,12 +458,27 @@ def run_b200(args):
     N_SETS = 3
     torch.manual_seed(rank)
 
-    def make_steps(memory_format, dtype=torch.float32, coord_dtype=torch.int64):
+    # Headline pair lists: the reference's own sampler (zarr_dataset.py:177-251, restated in the dataset module of this
+    # package on numpy's global generator) under np.random.seed, samples drawn b = 0..7 in order -- SURVEY 8d.
+    from cellulus_b200.datasets.zarr_dataset import sample_coordinates
+
+    host_lists = []
+    for i in range(N_SETS):
+        np.random.seed(N_SETS * rank + i)
+        pairs = [sample_coordinates(OUT, KAPPA, N_ANCHORS, N_REFS, D) for _ in range(B)]
+        host_lists.append((torch.from_numpy(np.stack([p[0] for p in pairs])).to(dev),
+                           torch.from_numpy(np.stack([p[1] for p in pairs])).to(dev)))
+    assert tuple(host_lists[0][0].shape) == (B, P, D) and host_lists[0][0].dtype == torch.int64
+
+    def make_steps(memory_format, dtype=torch.float32, coord_dtype=torch.int64, reference_lists=False):
         steps = []
         for i in range(N_SETS):
             off = torch.randn(B, D, *OUT, device=dev).to(dtype).contiguous(memory_format=memory_format)
-            anc, ref = K.sample_pairs(B, (OUT[1], OUT[0]), KAPPA, N_ANCHORS, N_REFS, seed=1234 + 17 * rank + i,
-                                      device=dev, dtype=coord_dtype)
+            if reference_lists:
+                anc, ref = host_lists[i]
+            else:
+                anc, ref = K.sample_pairs(B, (OUT[1], OUT[0]), KAPPA, N_ANCHORS, N_REFS, seed=1234 + 17 * rank + i,
+                                          device=dev, dtype=coord_dtype)
             steps.append(GraphedLossStep(off, anc, ref, TEMP, REGW))
         return steps
 
@@ -504,7 +519,7 @@ def run_b200(args):
 
     warm = max(args.warmup, 3)
     # (1) headline: channels-last offsets (the layout this framework keeps the U-Net output in)
-    steps_cl = make_steps(torch.channels_last)
+    steps_cl = make_steps(torch.channels_last, reference_lists=True)
     ms_per_step = timed(steps_cl, args.steps, warm)
     launches = timed.calls * 2  # zero-fill + fused kernel per step
     value = world * N_PX / (ms_per_step * 1e-3)
@@ -516,7 +531,7 @@ def run_b200(args):
         loss_oracle = oloss.loss_step_float64(steps_cl[0].offsets.cpu().contiguous(), steps_cl[0].anchors.cpu(),
                                               steps_cl[0].refs.cpu(), TEMP, REGW)[0].item()
     # (2) same op on the planar NCHW tensor the reference's model emits
-    steps_pl = make_steps(torch.contiguous_format)
+    steps_pl = make_steps(torch.contiguous_format, reference_lists=True)
     ms_planar = timed(steps_pl, args.steps, warm)
     # (2b) bf16 offsets (BASELINE configs[1] trains the U-Net in bf16): bf16 storage, fp32 arithmetic and gradient
     steps_bf = make_steps(torch.channels_last, torch.bfloat16)
@@ -651,8 +666,8 @@ def run_b200(args):
                              "(126 MB L2), no explicit flush",
                        "step": "zero-fill + fused gather/loss/backward kernel (programmatic dependent launch); replayed from CUDA "
                                "graphs of 3 steps (one per input set), the remainder of K as single-step graphs",
-                       "pairs": "device pair stream (cb200_sample_pairs: the reference sampler's distribution, "
-                                "oracle/device_sampler.py), int64 lists",
+                       "pairs": "int64 lists from the reference's sampler (zarr_dataset.py:177-251 restated on numpy's global "
+                                "generator, np.random.seed(3 * rank + set)); the bf16 / int16 variants use the device pair stream",
                        "sharding": "by batch, one batch per rank, no data-path collective"},
             "pairs_per_s": world * B * P / (ms_per_step * 1e-3),
             "loss_value_check": {"kernel": loss_value, "oracle_float64": loss_oracle,

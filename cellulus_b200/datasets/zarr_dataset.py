@@ -24,6 +24,28 @@ from .augment import elastic_crop
 from .meta_data import DatasetMetaData
 
 
+def sample_offsets_within_radius(radius, number_offsets, num_spatial_dims):
+    """`zarr_dataset.py:177-196` on numpy's global generator: `num_spatial_dims * number_offsets` candidates per
+    axis, keep the open ball minus the origin, take the first `number_offsets`, draw again when short."""
+    n = num_spatial_dims * number_offsets
+    cols = [np.random.randint(-radius, radius + 1, size=n) for _ in range(num_spatial_dims)]
+    offsets = np.stack(cols, axis=1)
+    offsets = offsets[(offsets**2).sum(axis=1) < radius**2]
+    offsets = offsets[np.absolute(offsets).sum(axis=1) > 0]
+    if len(offsets) < number_offsets:
+        return sample_offsets_within_radius(radius, number_offsets, num_spatial_dims)
+    return offsets[:number_offsets]
+
+
+def sample_coordinates(output_shape, kappa, num_anchors, num_references, num_spatial_dims):
+    """`zarr_dataset.py:198-242`, same RNG call order (per-dim anchors, then per-dim offsets): int64 `(P, D)` anchor
+    and reference lists of one sample, every anchor repeated `num_references` times (`np.repeat`, `:236`)."""
+    cols = [np.random.randint(kappa, output_shape[d] - kappa + 1, size=num_anchors) for d in range(num_spatial_dims)]
+    anchor_samples = np.repeat(np.stack(cols, axis=1), num_references, axis=0)
+    reference_samples = anchor_samples + sample_offsets_within_radius(kappa, len(anchor_samples), num_spatial_dims)
+    return anchor_samples, reference_samples
+
+
 class ZarrDataset(IterableDataset):  # type: ignore
     def __init__(
         self,
@@ -107,23 +129,12 @@ class ZarrDataset(IterableDataset):  # type: ignore
     # ---- the pair sampler (hot path)
     def sample_offsets_within_radius(self, radius, number_offsets):
         """`:177-196`: rejection-sample integer offsets in the open ball minus the origin."""
-        n = self.num_spatial_dims * number_offsets
-        cols = [np.random.randint(-radius, radius + 1, size=n) for _ in range(self.num_spatial_dims)]
-        offsets = np.stack(cols, axis=1)
-        offsets = offsets[(offsets**2).sum(axis=1) < radius**2]
-        offsets = offsets[np.absolute(offsets).sum(axis=1) > 0]
-        if len(offsets) < number_offsets:
-            return self.sample_offsets_within_radius(radius, number_offsets)
-        return offsets[:number_offsets]
+        return sample_offsets_within_radius(radius, number_offsets, self.num_spatial_dims)
 
     def sample_coordinates(self):
         """`:198-242`, same RNG call order: per-dim anchors, then per-dim offsets."""
-        num_anchors, num_references = self.get_num_anchors(), self.get_num_references()
-        cols = [np.random.randint(self.kappa, self.output_shape[d] - self.kappa + 1, size=num_anchors)
-                for d in range(self.num_spatial_dims)]
-        anchor_samples = np.repeat(np.stack(cols, axis=1), num_references, axis=0)
-        reference_samples = anchor_samples + self.sample_offsets_within_radius(self.kappa, len(anchor_samples))
-        return anchor_samples, reference_samples
+        return sample_coordinates(self.output_shape, self.kappa, self.get_num_anchors(), self.get_num_references(),
+                                  self.num_spatial_dims)
 
     def pair_stream(self):
         """Parameters of the device pair stream for this dataset's crops: what `criterion.fused_sampled` needs to
