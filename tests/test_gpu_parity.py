@@ -259,6 +259,54 @@ def test_fused_loss_autograd_generality():
     assert _rel(o.grad.cpu().numpy(), oracle_grad(0.5, 2.0, -1.0)) <= 2e-5
 
 
+def test_graphed_loss_steps_and_cycle_match_oracle():
+    """`GraphedLossStep` (one step per CUDA graph) and `GraphedLossCycle` (several steps, each with its own static
+    buffers, in ONE graph -- how bench.py replays the loss step) against the oracle, for explicit lists in both
+    layouts and for the sampled kernel; replays are repeatable and see new data written into the static buffers."""
+    from cellulus_b200.criterions import GraphedLossCycle, GraphedLossStep
+
+    dev = _dev()
+    out_shape = (60, 76)
+    steps, expected = [], []
+    for i, fmt in enumerate((torch.contiguous_format, torch.channels_last, torch.channels_last)):
+        np.random.seed(20 + i)
+        pairs = [osampler.sample_coordinates((60, 60), 10.0, 0.1, 2) for _ in range(2)]
+        anchors = torch.from_numpy(np.stack([p[0] for p in pairs])).long()
+        refs = torch.from_numpy(np.stack([p[1] for p in pairs])).long()
+        offsets = torch.from_numpy(synthetic.loss_offsets(2, 2, out_shape, seed=30 + i))
+        expected.append(oloss.loss_step(offsets, anchors, refs, 10.0, 1e-4))
+        steps.append(GraphedLossStep(offsets.to(dev).contiguous(memory_format=fmt), anchors.to(dev), refs.to(dev), 10.0, 1e-4))
+    cycle = GraphedLossCycle(steps)
+    assert len(cycle) == 3
+    for _ in range(2):
+        cycle.replay()
+    for (raw, grad), (l_ref, _, r_ref, g_ref) in zip(cycle.results, expected):
+        assert abs(raw[0].item() - l_ref.item()) <= LOSS_RTOL * abs(l_ref.item())
+        assert abs(raw[2].item() - r_ref.item()) <= LOSS_RTOL * abs(r_ref.item())
+        assert raw[3].item() == 0
+        assert _rel(grad.cpu().numpy(), g_ref.numpy()) <= LOSS_RTOL
+    for s, (l_ref, _, _, g_ref) in zip(steps, expected):
+        s.replay()
+        assert abs(s.loss.item() - l_ref.item()) <= LOSS_RTOL * abs(l_ref.item())
+        assert _rel(s.grad.cpu().numpy(), g_ref.numpy()) <= LOSS_RTOL
+    # new data in a static buffer is what the next replay computes on
+    new_off = torch.from_numpy(synthetic.loss_offsets(2, 2, out_shape, seed=99))
+    steps[1].offsets.copy_(new_off.to(dev))
+    l_new, _, _, g_new = oloss.loss_step(new_off, steps[1].anchors.cpu(), steps[1].refs.cpu(), 10.0, 1e-4)
+    cycle.replay()
+    assert abs(cycle.results[1][0][0].item() - l_new.item()) <= LOSS_RTOL * abs(l_new.item())
+    assert _rel(cycle.results[1][1].cpu().numpy(), g_new.numpy()) <= LOSS_RTOL
+    # the sampled kernel in a graph: equal to the explicit-list kernel on the lists of the same stream
+    sp = dict(kappa=10.0, num_anchors=160, num_references=31, seed=7, sequence=3, extent_xyz=(60, 60))
+    off = torch.from_numpy(synthetic.loss_offsets(2, 2, out_shape, seed=5)).to(dev).contiguous(memory_format=torch.channels_last)
+    g = GraphedLossStep(off, None, None, 10.0, 1e-4, sampled=sp)
+    g.replay()
+    a, r = K.sample_pairs(2, (60, 60), 10.0, 160, 31, seed=7, sequence=3, device=dev)
+    l_ref, _, _, g_ref = oloss.loss_step(off.cpu().contiguous(), a.cpu(), r.cpu(), 10.0, 1e-4)
+    assert abs(g.loss.item() - l_ref.item()) <= LOSS_RTOL * abs(l_ref.item())
+    assert _rel(g.grad.cpu().numpy(), g_ref.numpy()) <= LOSS_RTOL
+
+
 def test_fused_loss_bf16_offsets():
     from cellulus_b200.criterions import oce_loss_fused
 
