@@ -91,6 +91,42 @@ def detect_embeddings(embeddings, bandwidth, threshold=None, num_bandwidths=1, r
     return result + (infos,) if return_info else result
 
 
+def add_coordinates(embeddings: torch.Tensor) -> torch.Tensor:
+    """Copy of a (D+1, *S) embedding tensor with the pixel coordinates added to its first D channels: channel 0 += x
+    (last axis), channel 1 += y, channel 2 += z -- what `mean_shift_segmentation` does to its argument in place
+    (`utils/mean_shift.py:15-32`)."""
+    D = embeddings.shape[0] - 1
+    out = embeddings.clone()
+    for c in range(D):
+        axis = D - 1 - c  # spatial axis of column c
+        shape = [1] * D
+        shape[axis] = embeddings.shape[1 + axis]
+        out[c] += torch.arange(embeddings.shape[1 + axis], device=embeddings.device, dtype=embeddings.dtype).view(shape)
+    return out
+
+
+def detect_with_seeds(centred, bandwidth, threshold, num_bandwidths, reduction_probability,
+                      label_dtype=torch.uint16):
+    """The `use_seeds=True` bandwidth loop of `detect.py:121-144`, WITH its side effect: the first
+    `mean_shift_segmentation` call adds the coordinate grids to `embeddings_centered` through a view, so from the
+    second bandwidth on the reference finds its seeds on the shifted channels and clusters a copy of them to which
+    the coordinates are added once more.  Reproduced as is (drop-in: same detections for every bandwidth index --
+    including the reference's failure mode: with ordinary bandwidths the displaced seeds of index >= 1 reach no
+    point and scikit-learn's "No point was within bandwidth" ValueError comes up, here as there).
+    Returns `((num_bandwidths, *S) labels, (*S) uint8 mask)`."""
+    labels, mask, shifted = [], None, None
+    for k in range(num_bandwidths):
+        source = centred if k == 0 else shifted
+        lab, _, m = detect_embeddings(source, bandwidth / (2**k), threshold, 1, reduction_probability,
+                                      seeds=K.find_seeds(source), rng="numpy", label_dtype=label_dtype)
+        labels.append(lab[0])
+        if k == 0:
+            mask = m
+            if num_bandwidths > 1:
+                shifted = add_coordinates(centred)
+    return torch.stack(labels, 0), mask
+
+
 def _detect_sample_sharded(cfg, ds, sample, nd, device, rank, world, ds_detection, ds_binary, ds_centred):
     """One sample, all ranks: rank 0 does the O(N) preamble on the whole sample (threshold, mask, centring --
     `detect.py:88-119`), every rank compacts its slab of the slowest axis and the mean-shift runs seed-sharded
@@ -192,13 +228,8 @@ def detect(inference_config) -> None:
                 K.greedy_cluster(emb, mask, inference_config.bandwidth / (2**k), inference_config.min_size)[0]
                 .to(torch.int32).to(torch.uint16) for k in range(inference_config.num_bandwidths)])
         elif inference_config.use_seeds:
-            # detect.py:128-144: seeds from the centred embeddings, clustering on the centred embeddings.
-            # (The reference adds the coordinates to `embeddings_centered` in place on every pass, so its
-            # bandwidth index >= 1 runs on doubly-shifted data -- SURVEY quirk Q9; index 0 is reproduced.)
-            seeds = K.find_seeds(centred)
-            labels, _, mask = detect_embeddings(
-                centred, inference_config.bandwidth, threshold, inference_config.num_bandwidths,
-                inference_config.reduction_probability, seeds=seeds, rng="numpy", label_dtype=torch.uint16)
+            labels, mask = detect_with_seeds(centred, inference_config.bandwidth, threshold,
+                                             inference_config.num_bandwidths, inference_config.reduction_probability)
         else:
             labels, _, mask = detect_embeddings(
                 emb, inference_config.bandwidth, threshold, inference_config.num_bandwidths,

@@ -69,3 +69,26 @@ def find_seeds(embeddings_centered: np.ndarray, sigma: float = 2.0) -> np.ndarra
     magnitude = np.linalg.norm(embeddings_centered[:-1], axis=0)
     smooth = ndimage.gaussian_filter(magnitude, sigma=sigma)
     return np.flip(peak_local_max(-smooth), 1)
+
+
+def use_seeds_detections(embeddings_centered: np.ndarray, threshold: float, bandwidth: float, num_bandwidths: int,
+                         reduction_probability: float) -> np.ndarray:
+    """The `use_seeds=True` bandwidth loop of `detect.py:121-144,160`, side effects included.
+
+    `embeddings_centered_mean` starts as a VIEW of `embeddings_centered` (`:121-123`), so the first
+    `mean_shift_segmentation` call adds the coordinate grids to `embeddings_centered` itself
+    (`utils/mean_shift.py:15-32`); from the second bandwidth on the seeds are found on those shifted channels
+    (`:129-132`) and the clustering runs on a COPY of them (`:142-144`) to which the coordinates are added once
+    more.  Returns the `(num_bandwidths, *S)` int32 detections.  Mutates `embeddings_centered` like the reference.
+    """
+    from oracle import mean_shift as oms
+
+    nd = embeddings_centered.shape[0] - 1
+    mean = embeddings_centered[np.newaxis, :nd]  # a view
+    std = embeddings_centered[-1]
+    out = []
+    for k in range(num_bandwidths):
+        seeds = find_seeds(embeddings_centered)
+        out.append(oms.mean_shift_segmentation(mean, std, bandwidth / (2**k), 0, reduction_probability, threshold, seeds))
+        mean = embeddings_centered[np.newaxis, :nd, ...].copy()
+    return np.stack(out)

@@ -80,6 +80,45 @@ def test_mean_shift_with_integer_seeds_matches_oracle():
     assert np.array_equal(labels[0].cpu().numpy(), ref)
 
 
+def test_use_seeds_bandwidth_loop_reproduces_reference_side_effect():
+    """`detect.py:121-144` with `use_seeds=True` and several bandwidths: the first clustering call shifts
+    `embeddings_centered` in place, later bandwidths find their seeds on, and cluster, the shifted data (SURVEY
+    quirk Q9).  The device loop against the oracle restatement of those lines, detection for detection -- and,
+    where the reference's second bandwidth finds no point near its (displaced) seeds, the same ValueError."""
+    from cellulus_b200.detect import add_coordinates, detect_with_seeds
+    from oracle import seeds as oseeds
+
+    emb, _, _ = synthetic.blob_scene((90, 110), 12, radius=8.0, seed=21, dtype=np.float64)
+    thr, rp = 0.5, 0.5
+    centred = ootsu.centre_embeddings(emb, emb[2] < thr)
+    d = torch.from_numpy(centred).cuda()
+    # (a) a bandwidth wide enough that the displaced seeds of index >= 1 still reach points
+    ref_in = centred.copy()
+    np.random.seed(9)
+    ref = oseeds.use_seeds_detections(ref_in, thr, 160.0, 3, rp)
+    # the in-place side effect itself: one coordinate grid added to the first D channels
+    assert np.array_equal(add_coordinates(d).cpu().numpy(), ref_in) and not np.array_equal(ref_in, centred)
+    np.random.seed(9)
+    labels, mask = detect_with_seeds(d, 160.0, thr, 3, rp, label_dtype=torch.int32)
+    assert np.array_equal(labels.cpu().numpy(), ref)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), emb[2] < thr)
+    assert torch.equal(d, torch.from_numpy(centred).cuda())  # the device loop leaves its input alone
+    # (b) index 0 alone is the ordinary seeded detection
+    np.random.seed(9)
+    ref0 = oseeds.use_seeds_detections(centred.copy(), thr, 6.0, 1, rp)
+    np.random.seed(9)
+    labels0, _ = detect_with_seeds(d, 6.0, thr, 1, rp, label_dtype=torch.int32)
+    assert np.array_equal(labels0.cpu().numpy(), ref0) and ref0.max() > 1
+    # (c) an ordinary bandwidth: the reference's second pass fails (scikit-learn: no point within bandwidth of any
+    # seed) -- so does the drop-in
+    with pytest.raises(ValueError, match="No point was within bandwidth"):
+        np.random.seed(9)
+        oseeds.use_seeds_detections(centred.copy(), thr, 6.0, 2, rp)
+    with pytest.raises(ValueError, match="No point was within bandwidth"):
+        np.random.seed(9)
+        detect_with_seeds(d, 6.0, thr, 2, rp, label_dtype=torch.int32)
+
+
 def test_salt_pepper_statistics():
     from cellulus_b200 import kernels as K
 

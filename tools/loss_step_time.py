@@ -1,8 +1,11 @@
 """Time the explicit-list loss step at configs[1] the way bench.py does (CUDA-graph replay, 3 input sets of 211 MB
 visited round-robin) for one library variant / one set of CB200_LOSS_* switches; one line per run.
 
-    CB200_LOSS_ZERO=kernel python tools/loss_step_time.py     # separate zero-fill grid (round-1 form)
-    python tools/loss_step_time.py                            # gradient cleared inside the fused kernel
+    python tools/loss_step_time.py [cl cl_multi planar planar_multi cl_i16]
+    CB200_LOSS_STAGED=0 python tools/loss_step_time.py planar            # planar offsets gathered in place
+    CELLULUS_B200_LIB=variants/x.so python tools/loss_step_time.py       # a library built with other -D switches
+
+`*_multi`: the three steps captured in ONE graph (what bench.py replays); otherwise one graph per step.
 """
 import os
 import sys
