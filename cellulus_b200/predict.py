@@ -4,8 +4,11 @@ context, last block shifted inward -- `cellulus_b200.sharding.scan_blocks`), eac
 model's infer-mode forward (TTA loop + aggregate resident on the device) and lands in the `embeddings`
 dataset `(s, D+1, *spatial)` float64 with the reference's attributes.
 
-Multi-GPU (torchrun): samples are dealt to ranks round-robin; scan blocks of one sample stay on one rank so
-that no two ranks ever write the same chunk.
+Multi-GPU (torchrun): samples are dealt to ranks round-robin and the scan blocks of one sample stay on one rank
+(no two ranks ever write the same chunk) -- unless there are fewer samples than ranks (one mosaic, one volume:
+BASELINE configs[4]): then the scan blocks of EVERY sample are dealt to the ranks round-robin, each rank fills the
+part of its blocks that no later block of the scan overwrites (`sharding.owned_extents`), the partial volumes are
+summed onto rank 0 over NCCL and rank 0 writes the dataset.
 """
 
 from __future__ import annotations
@@ -51,20 +54,27 @@ def predict(model: torch.nn.Module, inference_config, normalization_factor) -> N
         torch.distributed.barrier()
     ds = f[name]
 
-    blocks = sharding.scan_blocks(meta.spatial_array, out_shape)
+    blocks = sharding.owned_extents(meta.spatial_array, out_shape)
+    share_samples = world > 1 and meta.num_samples < world  # fewer samples than ranks: deal the scan blocks instead
+    samples = range(meta.num_samples) if share_samples else sharding.shard_round_robin(meta.num_samples, rank, world)
     with torch.no_grad():
-        for sample in sharding.shard_round_robin(meta.num_samples, rank, world):
+        for sample in samples:
             raw = _normalize(np.asarray(raw_ds[sample]), normalization_factor)  # (c, *spatial)
             # a volume smaller than one output block is padded up to it (the reference's Scan would fail)
             pad = [(0, 0)] + [(ctx, ctx + max(0, o - s)) for ctx, o, s in zip(context, out_shape, meta.spatial_array)]
             raw = torch.from_numpy(np.pad(raw, pad, mode="reflect")).to(device)
-            result = torch.empty((nd + 1, *meta.spatial_array), dtype=torch.float32, device=device)
-            for off in blocks:
+            alloc = torch.zeros if share_samples else torch.empty
+            result = alloc((nd + 1, *meta.spatial_array), dtype=torch.float32, device=device)
+            mine = blocks[rank::world] if share_samples else blocks
+            for off, owned in mine:
                 src = (slice(None),) + tuple(slice(o, o + c) for o, c in zip(off, crop))
                 emb = model(raw[src][None])[0]  # (D+1, *out_shape), on the device
-                dst = (slice(None),) + tuple(slice(o, min(o + b, s)) for o, b, s in zip(off, out_shape, meta.spatial_array))
-                cut = (slice(None),) + tuple(slice(0, d.stop - d.start) for d in dst[1:])
+                dst = (slice(None),) + tuple(slice(o, o + e) for o, e in zip(off, owned))
+                cut = (slice(None),) + tuple(slice(0, e) for e in owned)
                 result[dst] = emb[cut]
-            ds[sample] = result.double().cpu().numpy()
+            if share_samples:
+                torch.distributed.reduce(result, dst=0)
+            if not share_samples or rank == 0:
+                ds[sample] = result.double().cpu().numpy()
     if world > 1:
         torch.distributed.barrier()

@@ -56,6 +56,21 @@ def scan_blocks(spatial: Sequence[int], block: Sequence[int]) -> List[Tuple[int,
     return out
 
 
+def owned_extents(spatial: Sequence[int], block: Sequence[int]) -> List[Tuple[Tuple[int, ...], Tuple[int, ...]]]:
+    """For every block of `scan_blocks(spatial, block)`, in the same order: `(offset, extent)` of the part of the
+    block that no LATER block of the scan overwrites.  Walking the blocks in scan order and writing each one whole
+    (what a single process does, `predict.py:129`) leaves every output pixel with the value of the last block that
+    covers it; blocks only overlap where the last block of an axis is shifted inward, and there the later block is
+    the one with the larger offset.  Writing only the owned part of every block therefore gives the same volume in
+    ANY order -- which is what lets the blocks of one sample be dealt to different ranks and summed."""
+    axes = []
+    for s, b in zip(spatial, block):
+        offs = sorted({o[len(axes)] for o in scan_blocks(spatial, block)})
+        ends = {o: min(o + b, s, offs[i + 1] if i + 1 < len(offs) else s) for i, o in enumerate(offs)}
+        axes.append(ends)
+    return [(off, tuple(axes[a][o] - o for a, o in enumerate(off))) for off in scan_blocks(spatial, block)]
+
+
 SEED_CHUNK = 2048
 
 

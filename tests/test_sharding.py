@@ -119,3 +119,29 @@ def test_single_process_path_needs_no_process_group():
     ref_labels, ref_centres = oms.segment_points(X, fit, 4.0)
     assert np.array_equal(labels.numpy(), ref_labels + 1)
     assert np.array_equal(centres.numpy().T, ref_centres)
+
+
+@pytest.mark.parametrize("spatial,block", [((10,), (4,)), ((50, 70), (16, 32)), ((9, 20, 33), (4, 8, 16)), ((5, 5), (8, 8)),
+                                           ((32, 32), (16, 16)), ((33, 17), (16, 16))])
+def test_owned_extents_partition_the_volume_like_a_sequential_scan(spatial, block):
+    """Writing only the owned part of every scan block (in any order, by any rank) leaves the volume exactly as a
+    sequential scan that writes every block whole (`predict.py:129`): each pixel belongs to the LAST block covering it."""
+    from cellulus_b200 import sharding
+
+    blocks = sharding.scan_blocks(spatial, block)
+    owned = sharding.owned_extents(spatial, block)
+    assert [o for o, _ in owned] == blocks
+    sequential = np.zeros(spatial, np.int64)
+    for i, off in enumerate(blocks):
+        sequential[tuple(slice(o, min(o + b, s)) for o, b, s in zip(off, block, spatial))] = i + 1
+    summed, cover = np.zeros(spatial, np.int64), np.zeros(spatial, np.int64)
+    for rank in range(3):  # three "ranks", blocks dealt round-robin, partial volumes summed
+        part = np.zeros(spatial, np.int64)
+        for i in range(rank, len(owned), 3):
+            off, ext = owned[i]
+            sl = tuple(slice(o, o + e) for o, e in zip(off, ext))
+            part[sl] = i + 1
+            cover[sl] += 1
+        summed += part
+    assert (cover == 1).all()
+    assert np.array_equal(summed, sequential)
