@@ -73,6 +73,7 @@ PROTOTYPES = {
     "cb200_tta_accumulate": (_i, [_p, _p, _i, _i, _i64, _p]),
     "cb200_tta_finalize": (_i, [_p, _i, _i, _i64, _p, _p]),
     "cb200_salt_pepper": (_i, [_p, _i64, _f, _f, _u64, _u64, _p, _p]),
+    "cb200_salt_pepper_device_seed": (_i, [_p, _i64, _f, _f, _p, _u64, _p, _p]),
     "cb200_centre_workspace_bytes": (_i64, []),
     "cb200_centre_embeddings": (_i, [_p, _i, _i, _i64, _d, _p, _p, _p, _p]),
     "cb200_channel_norm": (_i, [_p, _i, _i, _i64, _p, _p]),

@@ -217,10 +217,12 @@ tta_finalize_kernel(const float* __restrict__ state, int T, int C, int64_t n, fl
 
 // Salt / pepper noise of the infer-mode forward (models/unet.py:80-82): out = (u <= p) ? value : raw,
 // u ~ U[0,1) from Philox (the reference draws u on the CPU and copies it over for every pass).
+// `seed_dev` (optional): the seed is read from device memory, so that a CUDA graph of the whole test-time-augmentation
+// loop draws fresh noise on every replay (the graph bumps the seed itself).
 __global__ void __launch_bounds__(256)
-salt_pepper_kernel(const float* __restrict__ raw, int64_t n, float p, float value, uint64_t seed, uint64_t sequence,
-                   float* __restrict__ out) {
-  const Philox rng(seed);
+salt_pepper_kernel(const float* __restrict__ raw, int64_t n, float p, float value, uint64_t seed,
+                   const uint64_t* __restrict__ seed_dev, uint64_t sequence, float* __restrict__ out) {
+  const Philox rng(seed_dev ? __ldg(seed_dev) : seed);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = (n + 3) / 4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -248,6 +250,16 @@ int cb200_salt_pepper(const float* raw, int64_t n, float p, float value, uint64_
   if (!raw || !out || n < 0) return CB200_EINVAL;
   if (n == 0) return CB200_OK;
   salt_pepper_kernel<<<grid_for((n + 3) / 4, 256, 2, 16), 256, 0, (cudaStream_t)stream>>>(raw, n, p, value, seed,
+                                                                                          nullptr, sequence, out);
+  CB200_LAUNCH_CHECK();
+  return CB200_OK;
+}
+
+int cb200_salt_pepper_device_seed(const float* raw, int64_t n, float p, float value, const uint64_t* seed, uint64_t sequence,
+                                  float* out, void* stream) {
+  if (!raw || !out || !seed || n < 0) return CB200_EINVAL;
+  if (n == 0) return CB200_OK;
+  salt_pepper_kernel<<<grid_for((n + 3) / 4, 256, 2, 16), 256, 0, (cudaStream_t)stream>>>(raw, n, p, value, 0, seed,
                                                                                           sequence, out);
   CB200_LAUNCH_CHECK();
   return CB200_OK;

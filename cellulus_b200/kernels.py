@@ -298,14 +298,21 @@ def tta_finalize(state, num_passes, channels, spatial):
 _FLOAT_DTYPES = (torch.float32, torch.float64)
 
 
-def salt_pepper(raw: torch.Tensor, p: float, value: float, seed: int, sequence: int) -> torch.Tensor:
-    """`noisy[rnd <= p] = value` of `models/unet.py:80-82` with the uniform draw on the device."""
+def salt_pepper(raw: torch.Tensor, p: float, value: float, seed, sequence: int) -> torch.Tensor:
+    """`noisy[rnd <= p] = value` of `models/unet.py:80-82` with the uniform draw on the device.
+    `seed`: an int, or a one-element int64 CUDA tensor that the kernel reads when it runs (CUDA-graph replays)."""
     _require_cuda(raw)
     raw = raw.contiguous()
     assert raw.dtype == torch.float32
     out = torch.empty_like(raw)
-    check(_lib().cb200_salt_pepper(_ptr(raw), raw.numel(), float(p), float(value), int(seed) & (2**64 - 1),
-                                   int(sequence), _ptr(out), _stream(raw)), "cb200_salt_pepper")
+    if isinstance(seed, torch.Tensor):
+        _require_cuda(seed)
+        assert seed.dtype == torch.int64 and seed.numel() == 1 and seed.device == raw.device
+        check(_lib().cb200_salt_pepper_device_seed(_ptr(raw), raw.numel(), float(p), float(value), _ptr(seed),
+                                                   int(sequence), _ptr(out), _stream(raw)), "cb200_salt_pepper_device_seed")
+    else:
+        check(_lib().cb200_salt_pepper(_ptr(raw), raw.numel(), float(p), float(value), int(seed) & (2**64 - 1),
+                                       int(sequence), _ptr(out), _stream(raw)), "cb200_salt_pepper")
     launch_counter["calls"] += 1
     return out
 

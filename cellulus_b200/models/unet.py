@@ -87,6 +87,8 @@ class UNetModel(nn.Module):  # type: ignore
             conv(features_in_last_layer, features_in_last_layer, 1), nn.ReLU(),
             conv(features_in_last_layer, out_channels, 1))
         self.tta_seed = 0
+        self.tta_cuda_graph = True
+        self._tta_graphs = {}
 
     def head_forward(self, backbone_output):
         return self.head(backbone_output)
@@ -98,24 +100,63 @@ class UNetModel(nn.Module):  # type: ignore
         embeddings = []
         for sample in range(raw.shape[0]):
             raw_sample = raw[sample: sample + 1].detach().float().contiguous()
-            acc, pass_index = None, 0
-            for val in [0.5, 1.0]:
-                for _ in range(self.num_infer_iterations):
-                    noisy = K.salt_pepper(raw_sample, self.p_salt_pepper, val, self.tta_seed, pass_index)
-                    prediction = self.head_forward(self.backbone(noisy))[0].detach().float().contiguous()
-                    if acc is None:
-                        acc = TTAAccumulator(prediction.shape[0], prediction.shape[1:], prediction.device)
-                    acc.add(prediction)
-                    pass_index += 1
-            self.tta_seed += 1
-            embeddings.append(acc.result())
+            if self.tta_cuda_graph and raw_sample.is_cuda and not torch.is_grad_enabled():
+                embeddings.append(self._tta_replay(raw_sample))
+            else:
+                embeddings.append(self._tta_loop(raw_sample, self.tta_seed))
+                self.tta_seed += 1
         return torch.stack(embeddings, dim=0)
 
-    def set_infer(self, p_salt_pepper, num_infer_iterations, device):
+    def _tta_loop(self, raw_sample, seed):
+        """The 2 x `num_infer_iterations` noisy passes of one sample (`models/unet.py:76-89`) folded into the
+        running mean / M2 as they are produced; `seed`: int, or a device tensor read by the noise kernel."""
+        acc, pass_index = None, 0
+        for val in [0.5, 1.0]:
+            for _ in range(self.num_infer_iterations):
+                noisy = K.salt_pepper(raw_sample, self.p_salt_pepper, val, seed, pass_index)
+                prediction = self.head_forward(self.backbone(noisy))[0].detach().float().contiguous()
+                if acc is None:
+                    acc = TTAAccumulator(prediction.shape[0], prediction.shape[1:], prediction.device)
+                acc.add(prediction)
+                pass_index += 1
+        return acc.result()
+
+    def _tta_replay(self, raw_sample):
+        """The whole loop of one sample as ONE CUDA graph per input shape: ~30 small kernels per pass
+        x 32 passes are launch-bound when driven from the interpreter.  The noise seed lives in device memory and is
+        set before every replay, so each call draws fresh noise -- the same streams, in the same order, as the
+        eager loop.  Weights are read through their storage: loading a checkpoint in place is seen by the graph."""
+        key = (tuple(raw_sample.shape), raw_sample.device.index, float(self.p_salt_pepper), int(self.num_infer_iterations))
+        entry = self._tta_graphs.get(key)
+        if entry is None:
+            device = raw_sample.device
+            static_in = raw_sample.clone()
+            seed = torch.tensor([self.tta_seed], dtype=torch.int64, device=device)
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):  # warm-up outside the capture (cuDNN plans, allocator); noise seed untouched
+                self._tta_loop(static_in, seed)
+            torch.cuda.current_stream(device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self._tta_loop(static_in, seed)
+            entry = (graph, static_in, static_out, seed)
+            self._tta_graphs[key] = entry
+        graph, static_in, static_out, seed = entry
+        static_in.copy_(raw_sample)
+        seed.fill_(self.tta_seed)
+        graph.replay()
+        self.tta_seed += 1
+        return static_out.clone()
+
+    def set_infer(self, p_salt_pepper, num_infer_iterations, device, cuda_graph: bool = True):
+        """`models/unet.py:102-106`; `cuda_graph=False` drives the test-time-augmentation loop eagerly."""
         self.mode = "infer"
         self.p_salt_pepper = p_salt_pepper
         self.num_infer_iterations = num_infer_iterations
         self.device: torch.device = device
+        self.tta_cuda_graph = bool(cuda_graph)
+        self._tta_graphs = {}
 
     @staticmethod
     def select_and_add_coordinates(outputs, coordinates):

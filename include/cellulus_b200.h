@@ -211,6 +211,10 @@ CB200_API int cb200_tta_finalize(const float* state, int num_passes, int channel
  * u ~ U[0,1) drawn on the device (Philox; `sequence` distinguishes the passes). */
 CB200_API int cb200_salt_pepper(const float* raw, int64_t n, float p, float value, uint64_t seed, uint64_t sequence,
                       float* out, void* stream);
+/* Same draw with the seed read from DEVICE memory (one uint64) when the kernel runs: a CUDA graph of the whole
+ * test-time-augmentation loop of models/unet.py:73-89 then draws fresh noise on every replay. */
+CB200_API int cb200_salt_pepper_device_seed(const float* raw, int64_t n, float p, float value, const uint64_t* seed,
+                      uint64_t sequence, float* out, void* stream);
 
 /*
  * Foreground threshold, detect.py:88-94 (+ skimage threshold_otsu, np.histogram).

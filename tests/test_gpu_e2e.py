@@ -153,6 +153,35 @@ def test_infer_mode_forward_matches_reference_formula():
     assert (out[0].cpu() - ref).abs().max().item() <= 1e-5 * max(ref.abs().max().item(), 1.0)
 
 
+def test_infer_mode_cuda_graph_equals_eager_loop():
+    """The test-time-augmentation loop replayed from a CUDA graph (the default) against the same loop driven
+    eagerly: same noise streams in the same order, call after call, for two input shapes used alternately."""
+    from cellulus_b200.models import get_model
+
+    torch.manual_seed(1)
+    model = get_model(1, 2, 4, 2, 8, [(2, 2)], 2).cuda().eval()
+    eager = get_model(1, 2, 4, 2, 8, [(2, 2)], 2).cuda().eval()
+    eager.load_state_dict(model.state_dict())
+    model.set_infer(p_salt_pepper=0.05, num_infer_iterations=2, device=torch.device("cuda"))
+    eager.set_infer(p_salt_pepper=0.05, num_infer_iterations=2, device=torch.device("cuda"), cuda_graph=False)
+    inputs = [torch.rand(1, 1, 60, 60, device="cuda"), torch.rand(2, 1, 52, 68, device="cuda"),
+              torch.rand(1, 1, 60, 60, device="cuda"), torch.rand(2, 1, 52, 68, device="cuda")]
+    outs = []
+    with torch.no_grad():
+        for raw in inputs:
+            a, b = model(raw), eager(raw)
+            # same kernels on the same data; a convolution algorithm may differ under capture: last-bit tolerance
+            assert a.shape == b.shape and torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+            outs.append(a)
+        assert len(model._tta_graphs) == 2 and len(eager._tta_graphs) == 0
+        again = model(inputs[0])  # a later call on the same data draws other noise
+    assert not torch.equal(again, outs[0]) and (again[:, 2] > 0).any()
+    # with gradients enabled the loop is driven eagerly (nothing is captured under autograd)
+    n_graphs = len(model._tta_graphs)
+    model(torch.rand(1, 1, 44, 44, device="cuda"))
+    assert len(model._tta_graphs) == n_graphs
+
+
 def _toml(tmp, crop):
     return f"""
 experiment_name = "e2e"
