@@ -69,6 +69,8 @@ PROTOTYPES = {
     "cb200_sample_pairs": (_i, [_p, _p, _i, _i, _i, _pi64, _d, _i64, _i, _u64, _u64, _p]),
     "cb200_oce_loss_sampled": (_i, [_p, _i, _i, _i, _i, _pi64, _pi64, _d, _i64, _i, _u64, _u64, _f, _f, _p, _p, _p, _p, _p,
                                     _i, _p]),
+    "cb200_oce_loss_sampled_staged": (_i, [_p, _i, _i, _i, _i, _pi64, _pi64, _d, _i64, _i, _u64, _u64, _f, _f, _p, _p, _p,
+                                           _p, _p, _i, _p, _i64, _p]),
     "cb200_tta_aggregate": (_i, [_p, _i, _i, _i64, _p, _p]),
     "cb200_tta_accumulate": (_i, [_p, _p, _i, _i, _i64, _p]),
     "cb200_tta_finalize": (_i, [_p, _i, _i, _i64, _p, _p]),

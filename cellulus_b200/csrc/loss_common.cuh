@@ -173,6 +173,53 @@ __device__ __forceinline__ void scatter_pixel(float* __restrict__ gbase, unsigne
   }
 }
 
+// Gather from the channels-last STAGED copy of planar 2-D offsets that a loss kernel writes at the start of its own
+// launch (oce_loss.cu: oce_loss_staged_kernel; oce_sampled.cu: LY_STAGED).
+template <int D, typename OT>
+__device__ __forceinline__ void gather_staged(const OT* base, unsigned first, unsigned pix, float (&o)[D]) {
+  static_assert(D == 2, "staged gathers are built for 2-D embeddings");
+  // the copy was written by other CTAs of THIS launch: plain (coherent) loads, not ld.global.nc
+  if constexpr (sizeof(OT) == 4) {
+    asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(o[0]), "=f"(o[1]) : "l"(reinterpret_cast<const float2*>(base) + (first + pix)));
+  } else {
+    unsigned v;
+    asm volatile("ld.global.b32 %0, [%1];" : "=r"(v) : "l"(reinterpret_cast<const unsigned*>(base) + (first + pix)));
+    o[0] = __uint_as_float(v << 16);
+    o[1] = __uint_as_float(v & 0xffff0000u);
+  }
+}
+
+// how a loss kernel sees the (B, D, *S) offsets / gradient tensors
+constexpr int LY_PLANAR = 0, LY_CL = 1, LY_STAGED = 2;  // staged: gathers from the copy, gradient stays planar
+
+// planar (2, npix) per sample -> interleaved (npix, 2): this CTA's share of ALL batch * npix pixels.
+// vec: npix even and both bases aligned (8-byte loads, 16-byte stores, two pixels per thread).
+template <typename OT>
+__device__ __forceinline__ void stage_interleaved_slice(const OT* __restrict__ offsets, OT* __restrict__ staged, unsigned batch,
+                                                        unsigned npix, bool vec) {
+  const unsigned total = batch * npix;  // < 2^31 (launcher)
+  const unsigned per = ((total + gridDim.x - 1) / gridDim.x + 1u) & ~1u;
+  const unsigned lo = min(total, blockIdx.x * per), hi = min(total, lo + per);
+  if constexpr (sizeof(OT) == 4) {
+    if (vec) {
+      for (unsigned g = lo + 2 * threadIdx.x; g + 1 < hi; g += 2 * blockDim.x) {
+        const unsigned b = g / npix, i = g - b * npix;
+        const OT* src = offsets + (size_t)b * npix * 2 + i;
+        const float2 x = __ldg(reinterpret_cast<const float2*>(src));
+        const float2 y = __ldg(reinterpret_cast<const float2*>(src + npix));
+        *reinterpret_cast<float4*>(staged + 2 * (size_t)g) = make_float4(x.x, y.x, x.y, y.y);
+      }
+      return;
+    }
+  }
+  for (unsigned g = lo + threadIdx.x; g < hi; g += blockDim.x) {
+    const unsigned b = g / npix, i = g - b * npix;
+    const OT* src = offsets + (size_t)b * npix * 2 + i;
+    staged[2 * (size_t)g] = src[0];
+    staged[2 * (size_t)g + 1] = src[npix];
+  }
+}
+
 template <int D>
 static bool make_shape(const int64_t* spatial, Shape<D>& s) {
   int64_t npix = 1;

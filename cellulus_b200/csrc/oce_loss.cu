@@ -230,20 +230,6 @@ oce_loss_fused_kernel(const OT* __restrict__ offsets, const CT* __restrict__ anc
 // reduction per run of equal anchors -- stays planar.  ONE launch per step.
 // (The same in-kernel clearing for the other layouts was built and measured: 49.5 us against 49.4 us behind the
 // zero-fill grid with an identical body -- programmatic dependent launch already hides the zero-fill.)
-template <int D, typename OT>
-__device__ __forceinline__ void gather_staged(const OT* base, unsigned first, unsigned pix, float (&o)[D]) {
-  static_assert(D == 2, "staged gathers are built for 2-D embeddings");
-  // the copy was written by other CTAs of THIS launch: plain (coherent) loads, not ld.global.nc
-  if constexpr (sizeof(OT) == 4) {
-    asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(o[0]), "=f"(o[1]) : "l"(reinterpret_cast<const float2*>(base) + (first + pix)));
-  } else {
-    unsigned v;
-    asm volatile("ld.global.b32 %0, [%1];" : "=r"(v) : "l"(reinterpret_cast<const unsigned*>(base) + (first + pix)));
-    o[0] = __uint_as_float(v << 16);
-    o[1] = __uint_as_float(v & 0xffff0000u);
-  }
-}
-
 template <typename OT>
 __device__ __forceinline__ void chunk_gather_staged(Chunk<2>& c, const OT* staged, unsigned first, const Shape<2>& shape,
                                                     int& bad) {

@@ -25,14 +25,35 @@ namespace cb200 {
 constexpr int SMP_THREADS = 256;
 constexpr int SMP_MIN_BLOCKS = 5;  // 709 blocks of 8 anchor-warps at configs[1]: one wave needs 5 per SM
 
-template <int D, typename OT, bool IL, bool BWD, bool DUMP>
+// LY_STAGED (planar 2-D offsets + caller scratch): every CTA first writes its share of a channels-last copy of the
+// offsets into `staged` and counts itself in; the gathers read the copy (one 8-byte access per pixel instead of one
+// wavefront per lane PER CHANNEL), the gradient stays planar.  The grid is one resident wave, so the wait for the
+// other CTAs cannot starve.
+template <int D, typename OT, int LY, bool BWD, bool DUMP>
 __global__ void __launch_bounds__(SMP_THREADS, SMP_MIN_BLOCKS)
 oce_loss_sampled_kernel(const OT* __restrict__ offsets, PairStreamParams p, Shape<D> shape, unsigned batch,
                         unsigned blocks_per_sample /* of 32 anchors */, float neg_log2e_over_t, float two_over_t, float w,
                         float* __restrict__ grad, LossWorkspace* ws, float* out, void* dump_anchors, void* dump_refs,
-                        int dump_dtype) {
+                        int dump_dtype, OT* staged, unsigned stage_vec) {
   extern __shared__ uint32_t s_table[];
+  if constexpr (LY == LY_STAGED && D == 2) {
+    stage_interleaved_slice<OT>(offsets, staged, batch, (unsigned)shape.npix, stage_vec != 0);
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&ws->arrived[0]) : "memory");
+  }
   build_offset_table<D>(s_table, p);  // overlaps the zero-fill grid in front of us
+  if constexpr (LY == LY_STAGED && D == 2) {
+    if (threadIdx.x == 0) {
+      unsigned seen;
+      for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&ws->arrived[0]) : "memory");
+        if (seen >= gridDim.x) break;
+        __nanosleep(40);
+      }
+    }
+    __syncthreads();
+  }
+  const OT* gather_base = LY == LY_STAGED ? staged : offsets;
   const Philox rng(p.seed);
   const unsigned lane = lane_id();
   const unsigned warps_per_block = SMP_THREADS / 32;
@@ -61,7 +82,11 @@ oce_loss_sampled_kernel(const OT* __restrict__ offsets, PairStreamParams p, Shap
     const unsigned pa = ok_a ? (unsigned)pixel_of<D>(anc, shape) : 0u;
     float oa[D], ea[D], g[D];
     if (ok_a) {
-      gather_pixel<D, OT, IL>(offsets, npix, first, pa, oa);
+      if constexpr (LY == LY_STAGED) {
+        if constexpr (D == 2) gather_staged<D, OT>(gather_base, first, pa, oa);
+      } else {
+        gather_pixel<D, OT, LY == LY_CL>(gather_base, npix, first, pa, oa);
+      }
     } else {
 #pragma unroll
       for (int k = 0; k < D; ++k) oa[k] = 0.f;
@@ -102,7 +127,11 @@ oce_loss_sampled_kernel(const OT* __restrict__ offsets, PairStreamParams p, Shap
       if (want && !ok) ++bad;
       okm = ok ? (okm | (1u << j)) : (okm & ~(1u << j));
       if (ok) {
-        gather_pixel<D, OT, IL>(offsets, npix, first, (unsigned)pixel_of<D>(ref, shape), orf[j]);
+        if constexpr (LY == LY_STAGED) {
+          if constexpr (D == 2) gather_staged<D, OT>(gather_base, first, (unsigned)pixel_of<D>(ref, shape), orf[j]);
+        } else {
+          gather_pixel<D, OT, LY == LY_CL>(gather_base, npix, first, (unsigned)pixel_of<D>(ref, shape), orf[j]);
+        }
       } else {
 #pragma unroll
         for (int k = 0; k < D; ++k) orf[j][k] = 0.f;
@@ -172,7 +201,7 @@ oce_loss_sampled_kernel(const OT* __restrict__ offsets, PairStreamParams p, Shap
         const float gr = fn * w * rs;
 #pragma unroll
         for (int k = 0; k < D; ++k) g[k] = fmaf(gr, ea[k], g[k]);
-        scatter_pixel<D, IL>(grad, npix, first, pa, g);
+        scatter_pixel<D, LY == LY_CL>(grad, npix, first, pa, g);
       }
     }
   }
@@ -182,11 +211,11 @@ oce_loss_sampled_kernel(const OT* __restrict__ offsets, PairStreamParams p, Shap
   block_reduce_to_workspace(acc_oce, acc_nrm, bad, ws, w, out);
 }
 
-template <int D, typename OT, bool IL, bool BWD, bool DUMP>
+template <int D, typename OT, int LY, bool BWD, bool DUMP>
 static int launch_sampled_variant(const void* offsets, const PairStreamParams& p, const Shape<D>& shape, int batch,
                                   float T, float w, float* grad, float* out, LossWorkspace* ws, void* dump_anchors,
-                                  void* dump_refs, int dump_dtype, cudaStream_t st) {
-  auto kernel = oce_loss_sampled_kernel<D, OT, IL, BWD, DUMP>;
+                                  void* dump_refs, int dump_dtype, void* staged, cudaStream_t st) {
+  auto kernel = oce_loss_sampled_kernel<D, OT, LY, BWD, DUMP>;
   const size_t table_bytes = (size_t)p.n_table * sizeof(uint32_t);
   static int occupancy = 0;  // per template instantiation
   static size_t occupancy_for = 0;
@@ -217,8 +246,11 @@ static int launch_sampled_variant(const void* offsets, const PairStreamParams& p
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.numAttrs = (BWD && g_loss_pdl) ? 1 : 0;  // only behind our own zero-fill grid
+  const unsigned stage_vec = (LY == LY_STAGED && shape.npix % 2 == 0 && reinterpret_cast<uintptr_t>(offsets) % 8 == 0 &&
+                              reinterpret_cast<uintptr_t>(staged) % 16 == 0) ? 1u : 0u;
   CB200_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, (const OT*)offsets, p, shape, (unsigned)batch, blocks_per_sample,
-                                    -log2e / T, 2.0f / T, w, grad, ws, out, dump_anchors, dump_refs, dump_dtype));
+                                    -log2e / T, 2.0f / T, w, grad, ws, out, dump_anchors, dump_refs, dump_dtype,
+                                    (OT*)staged, stage_vec));
   return CB200_OK;
 }
 
@@ -226,7 +258,7 @@ template <int D, typename OT>
 static int launch_sampled(const void* offsets, int layout, int batch, const int64_t* spatial, const int64_t* extent,
                           double kappa, int64_t num_anchors, int num_refs, uint64_t seed, uint64_t sequence, float T,
                           float w, float* grad, float* out, void* workspace, void* dump_anchors, void* dump_refs,
-                          int dump_dtype, cudaStream_t st) {
+                          int dump_dtype, void* staging, int64_t staging_bytes, cudaStream_t st) {
   Shape<D> shape;
   if (!make_shape<D>(spatial, shape)) return CB200_EINVAL;
   if ((int64_t)batch * D * shape.npix > INT32_MAX || batch > 65535) return CB200_EUNSUPPORTED;  // 32-bit element indices
@@ -247,13 +279,20 @@ static int launch_sampled(const void* offsets, int layout, int batch, const int6
   const bool il = layout == CB200_LAYOUT_CHANNELS_LAST;
   if (il && D == 2 && (reinterpret_cast<uintptr_t>(offsets) % (2 * sizeof(OT)) || reinterpret_cast<uintptr_t>(grad) % 8))
     return CB200_EINVAL;  // vector gathers / vector reductions need pixel-aligned bases
-#define CB200_SAMPLED(BWD, IL)                                                                                       \
-  (dump_anchors ? launch_sampled_variant<D, OT, IL, BWD, true>(offsets, p, shape, batch, T, w, grad, out, ws,            \
-                                                                dump_anchors, dump_refs, dump_dtype, st)                 \
-                : launch_sampled_variant<D, OT, IL, BWD, false>(offsets, p, shape, batch, T, w, grad, out, ws, nullptr, \
-                                                                 nullptr, 0, st))
-  if (grad) return il ? CB200_SAMPLED(true, true) : CB200_SAMPLED(true, false);
-  return il ? CB200_SAMPLED(false, true) : CB200_SAMPLED(false, false);
+#define CB200_SAMPLED(BWD, LY)                                                                                       \
+  (dump_anchors ? launch_sampled_variant<D, OT, LY, BWD, true>(offsets, p, shape, batch, T, w, grad, out, ws,            \
+                                                                dump_anchors, dump_refs, dump_dtype, staging, st)        \
+                : launch_sampled_variant<D, OT, LY, BWD, false>(offsets, p, shape, batch, T, w, grad, out, ws, nullptr, \
+                                                                 nullptr, 0, staging, st))
+  if constexpr (D == 2) {
+    // planar tensors + caller scratch: gather from a channels-last copy made inside the kernel
+    static const bool staged_ok = [] { const char* e = getenv("CB200_LOSS_STAGED"); return !(e && e[0] == '0'); }();
+    if (!il && staged_ok && staging && staging_bytes >= (int64_t)sizeof(OT) * batch * D * shape.npix &&
+        reinterpret_cast<uintptr_t>(staging) % (2 * sizeof(OT)) == 0)
+      return grad ? CB200_SAMPLED(true, LY_STAGED) : CB200_SAMPLED(false, LY_STAGED);
+  }
+  if (grad) return il ? CB200_SAMPLED(true, LY_CL) : CB200_SAMPLED(true, LY_PLANAR);
+  return il ? CB200_SAMPLED(false, LY_CL) : CB200_SAMPLED(false, LY_PLANAR);
 #undef CB200_SAMPLED
 }
 
@@ -266,6 +305,17 @@ extern "C" int cb200_oce_loss_sampled(const void* offsets, int offsets_dtype, in
                                       int num_references, uint64_t seed, uint64_t sequence, float temperature,
                                       float regularization_weight, float* grad, float* out, void* workspace,
                                       void* dump_anchors, void* dump_refs, int dump_dtype, void* stream) {
+  return cb200_oce_loss_sampled_staged(offsets, offsets_dtype, offsets_layout, batch, num_dims, spatial, extent, kappa,
+                                       num_anchors, num_references, seed, sequence, temperature, regularization_weight,
+                                       grad, out, workspace, dump_anchors, dump_refs, dump_dtype, nullptr, 0, stream);
+}
+
+extern "C" int cb200_oce_loss_sampled_staged(const void* offsets, int offsets_dtype, int offsets_layout, int batch,
+                                             int num_dims, const int64_t* spatial, const int64_t* extent, double kappa,
+                                             int64_t num_anchors, int num_references, uint64_t seed, uint64_t sequence,
+                                             float temperature, float regularization_weight, float* grad, float* out,
+                                             void* workspace, void* dump_anchors, void* dump_refs, int dump_dtype,
+                                             void* staging, int64_t staging_bytes, void* stream) {
   if (!offsets || !spatial || !extent || !out || !workspace) return CB200_EINVAL;
   if (batch <= 0 || num_anchors < 0 || num_references < 0 || !(temperature != 0.f)) return CB200_EINVAL;
   if ((dump_anchors == nullptr) != (dump_refs == nullptr)) return CB200_EINVAL;
@@ -279,11 +329,12 @@ extern "C" int cb200_oce_loss_sampled(const void* offsets, int offsets_dtype, in
   if (offsets_dtype == CB200_F32)                                                                                        \
     return launch_sampled<DD, float>(offsets, offsets_layout, batch, spatial, extent, kappa, num_anchors, num_references, \
                                      seed, sequence, temperature, regularization_weight, grad, out, workspace,          \
-                                     dump_anchors, dump_refs, dump_dtype, st);                                           \
+                                     dump_anchors, dump_refs, dump_dtype, staging, staging_bytes, st);                   \
   if (offsets_dtype == CB200_BF16)                                                                                       \
     return launch_sampled<DD, __nv_bfloat16>(offsets, offsets_layout, batch, spatial, extent, kappa, num_anchors,        \
                                              num_references, seed, sequence, temperature, regularization_weight, grad,  \
-                                             out, workspace, dump_anchors, dump_refs, dump_dtype, st);                   \
+                                             out, workspace, dump_anchors, dump_refs, dump_dtype, staging,              \
+                                             staging_bytes, st);                                                        \
   return CB200_EUNSUPPORTED;
   if (num_dims == 2) { CB200_DISPATCH(2) }
   if (num_dims == 3) { CB200_DISPATCH(3) }

@@ -227,9 +227,10 @@ def sample_pairs(batch, extent_xyz, kappa, num_anchors, num_references, seed, se
 
 
 def oce_loss_sampled(offsets, kappa, num_anchors, num_references, seed, sequence, temperature,
-                     regularization_weight, extent_xyz=None, want_grad=True, dump_dtype=None):
-    """`cb200_oce_loss_sampled`: the loss on the pair stream (seed, sequence), pairs drawn inside the kernel.
-    Returns `(out4, grad, (anchors, refs) | None)`; the lists are only written when `dump_dtype` is given."""
+                     regularization_weight, extent_xyz=None, want_grad=True, dump_dtype=None, staged=True):
+    """`cb200_oce_loss_sampled_staged`: the loss on the pair stream (seed, sequence), pairs drawn inside the kernel.
+    Returns `(out4, grad, (anchors, refs) | None)`; the lists are only written when `dump_dtype` is given.
+    `staged=False`: planar offsets are gathered in place (no staging scratch)."""
     _require_cuda(offsets)
     if offsets.ndim not in (4, 5) or offsets.shape[1] != offsets.ndim - 2:
         raise ValueError("offsets must be (B, D, *S) with one offset channel per spatial dim")
@@ -250,12 +251,14 @@ def oce_loss_sampled(offsets, kappa, num_anchors, num_references, seed, sequence
         lists = (torch.empty((B, P, D), dtype=dump_dtype, device=offsets.device),
                  torch.empty((B, P, D), dtype=dump_dtype, device=offsets.device))
         ddt = _code(lists[0], _COORD_DTYPES)
-    rc = _lib().cb200_oce_loss_sampled(
+    staging_bytes = _lib().cb200_oce_loss_staging_bytes(odt, layout, B, D, spatial_array(spatial)) if staged else 0
+    staging = torch.empty(staging_bytes, dtype=torch.uint8, device=offsets.device) if staging_bytes > 0 else None
+    rc = _lib().cb200_oce_loss_sampled_staged(
         _ptr(offsets), odt, layout, B, D, spatial_array(spatial), spatial_array(extent_xyz), float(kappa),
         int(num_anchors), int(num_references), int(seed) & (2**64 - 1), int(sequence), float(temperature),
         float(regularization_weight), _ptr(grad), _ptr(out), _ptr(ws), _ptr(lists[0] if lists else None),
-        _ptr(lists[1] if lists else None), ddt, _stream(offsets))
-    check(rc, "cb200_oce_loss_sampled")
+        _ptr(lists[1] if lists else None), ddt, _ptr(staging), staging_bytes, _stream(offsets))
+    check(rc, "cb200_oce_loss_sampled_staged")
     launch_counter["calls"] += 1
     return out, grad, lists
 

@@ -191,6 +191,15 @@ CB200_API int cb200_oce_loss_sampled(const void* offsets, int offsets_dtype, int
                            int num_references, uint64_t seed, uint64_t sequence, float temperature,
                            float regularization_weight, float* grad, float* out, void* workspace,
                            void* dump_anchors, void* dump_refs, int dump_dtype, void* stream);
+/* Same call with optional staging scratch (cb200_oce_loss_staging_bytes): planar 2-D offsets are gathered from a
+ * channels-last copy that the kernel writes at the start of its own launch (see cb200_oce_loss_fwd_bwd_staged);
+ * staging == NULL behaves exactly like cb200_oce_loss_sampled. */
+CB200_API int cb200_oce_loss_sampled_staged(const void* offsets, int offsets_dtype, int offsets_layout, int batch, int num_dims,
+                           const int64_t* spatial, const int64_t* extent, double kappa, int64_t num_anchors,
+                           int num_references, uint64_t seed, uint64_t sequence, float temperature,
+                           float regularization_weight, float* grad, float* out, void* workspace,
+                           void* dump_anchors, void* dump_refs, int dump_dtype,
+                           void* staging, int64_t staging_bytes, void* stream);
 
 /* ===================================================================== *
  *  Detect slice (inference)                                             *

@@ -397,6 +397,29 @@ def test_device_sampler_bit_exact_to_stream_oracle(nd, ext, kappa, na, nr, dtype
     assert np.array_equal(r.cpu().numpy().astype(np.int64), r_ref)
 
 
+@pytest.mark.parametrize("odt", [torch.float32, torch.bfloat16])
+def test_sampled_loss_planar_staged_and_in_place_agree(odt):
+    """Planar 2-D offsets through the sampled kernel: gathered from the kernel's own channels-last copy (staging
+    scratch, the default) and gathered in place, against the oracle on the pairs of the same stream; odd extents
+    exercise the scalar transposition, a repeat call the reset of the arrival counter."""
+    dev = _dev()
+    for B, out_shape, na in ((3, (61, 75), 120), (2, (64, 96), 300)):
+        offsets = torch.from_numpy(synthetic.loss_offsets(B, 2, out_shape, seed=8)).to(odt)
+        ext = (out_shape[1], out_shape[0])
+        a, r = K.sample_pairs(B, ext, 6.0, na, 11, seed=3, sequence=2, device=dev)
+        l_ref, _, r_ref, g_ref = oloss.loss_step(offsets.float(), a.cpu(), r.cpu(), 10.0, 1e-3)
+        off_d = offsets.to(dev)
+        for staged in (True, False, True):
+            for want_grad in (True, False):
+                out, grad, _ = K.oce_loss_sampled(off_d, 6.0, na, 11, 3, 2, 10.0, 1e-3, extent_xyz=ext, want_grad=want_grad,
+                                                  staged=staged)
+                out = out.cpu().numpy()
+                assert abs(out[0] - l_ref.item()) <= LOSS_RTOL * abs(l_ref.item()), (B, staged, want_grad)
+                assert abs(out[2] - r_ref.item()) <= LOSS_RTOL * abs(r_ref.item()) and out[3] == 0
+                if want_grad:
+                    assert grad.is_contiguous() and _rel(grad.cpu().numpy(), g_ref.numpy()) <= LOSS_RTOL, (B, staged)
+
+
 @pytest.mark.parametrize("nd,layout,odt", [(2, "planar", torch.float32), (2, "cl", torch.float32),
                                            (2, "cl", torch.bfloat16), (3, "planar", torch.float32),
                                            (3, "cl", torch.float32)])
