@@ -424,7 +424,8 @@ def bench_post(dev, with_cpu):
         "workload": f"{shape[0]}x{shape[1]} label image, {int(seg_np.max())} objects, uint16 raw",
         "grow_shrink": {"ms": t_gs * 1e3, "Mpx/s": n / t_gs / 1e6, "note": "device tensor in place (segment.py:46-50)"},
         "size_filter": {"ms": t_sf * 1e3, "Mpx/s": n / t_sf / 1e6, "note": "device tensor (utils/misc.py:11-25)"},
-        "nucleus": {"ms": t_nuc * 1e3, "Mpx/s": n / t_nuc / 1e6, "note": "numpy in/out incl. the host<->device copies (per-instance Otsu runs on the device)"},
+        "nucleus": {"ms": t_nuc * 1e3, "Mpx/s": n / t_nuc / 1e6, "note": "numpy in/out incl. the host<->device copies (per-instance Otsu runs on the device; the Otsu rule "
+                            "is the restated scikit-image threshold_otsu: parity unpinned, DESIGN 2)"},
         "evaluate_tables": {"ms": t_ev * 1e3, "Mpx/s": n / t_ev / 1e6, "note": "numpy in/out, IoU table of all id pairs"},
     }
     if with_cpu:

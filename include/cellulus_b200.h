@@ -12,9 +12,15 @@
  * Conventions
  *   - return value: 0 = ok; CB200_EINVAL (-1) bad argument; CB200_EUNSUPPORTED
  *     (-2) unsupported dtype/dims; otherwise a positive cudaError_t.
- *   - nothing here synchronises the stream or allocates device memory; every
- *     scratch buffer is passed in (sizes from the *_workspace_bytes queries).
+ *   - nothing here allocates device memory: every scratch buffer is passed in
+ *     (sizes from the *_workspace_bytes queries).  No entry synchronises the
+ *     stream EXCEPT the one composite whose control flow depends on counts
+ *     that only exist on the device, and which says so at its declaration:
+ *     cb200_detect_volume (four blocking count reads per call).
  *   - re-entrant across streams as long as workspaces are not shared.
+ *   - the staged loss entries (cb200_oce_loss_*_staged with staging scratch)
+ *     launch ONE resident wave whose thread blocks wait for each other inside
+ *     the launch; everything else is ordinary fire-and-forget.
  *   - spatial shapes are passed in tensor-axis order ([z,] y, x); coordinate /
  *     channel columns are in the reference's (x, y[, z]) order: column 0
  *     indexes the LAST tensor axis (models/unet.py:114-118).
