@@ -141,6 +141,14 @@ inline int grid_for(int64_t work_items, int threads, int per_thread = 1, int max
   return (int)blocks;
 }
 
+// detect.cu: forms of cb200_minmax / cb200_select_points whose element count is read ON THE DEVICE (*n_dev), so that a
+// composite can enqueue them before it has read that count (n_max sizes the launch; n_dev == NULL: exactly n_max)
+int minmax_counted(const void* x, int dtype, int64_t n_max, const long long* n_dev, double* out2, void* workspace,
+                   cudaStream_t st);
+int select_points_counted(const double* src, int64_t n_max, const long long* n_dev, int64_t src_stride, int num_dims,
+                          const uint8_t* flags, double* dst, int64_t dst_stride, long long* n_out, void* workspace,
+                          cudaStream_t st);
+
 // ------------------------------------------------------------------ mbarrier / 1-D TMA helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

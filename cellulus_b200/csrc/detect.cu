@@ -23,7 +23,9 @@ struct ReduceWorkspace {
 
 template <typename T>
 __global__ void __launch_bounds__(RED_THREADS)
-minmax_kernel(const T* __restrict__ x, int64_t n, double* __restrict__ out2, ReduceWorkspace* ws) {
+minmax_kernel(const T* __restrict__ x, int64_t n, const long long* __restrict__ n_dev, double* __restrict__ out2,
+              ReduceWorkspace* ws) {
+  if (n_dev) n = min(n, (int64_t)__ldg(n_dev));  // the element count lives on the device: n is only its upper bound
   double lo = INFINITY, hi = -INFINITY;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -255,7 +257,11 @@ mask_kernel(const T* __restrict__ std_channel, double threshold, int64_t n, M* _
 
 struct FlagPred {
   const uint8_t* flags;
-  __device__ __forceinline__ bool operator()(int64_t i) const { return __ldg(flags + i) != 0; }
+  const long long* n_dev;  // optional: only the first *n_dev flags are meaningful
+  __device__ __forceinline__ bool operator()(int64_t i) const {
+    if (n_dev && i >= __ldg(n_dev)) return false;
+    return __ldg(flags + i) != 0;
+  }
 };
 struct SelectEmit {
   const double* src;
@@ -313,6 +319,32 @@ static int fg_compact_typed(const void* emb_v, int num_dims, const int64_t* spat
   return run_compaction(pred, emit, n_pix, capacity, n_out, workspace, st);
 }
 
+// min / max of the first min(n_max, *n_dev) elements (n_dev == NULL: of n_max elements); the launch is sized for n_max
+int minmax_counted(const void* x, int dtype, int64_t n_max, const long long* n_dev, double* out2, void* workspace,
+                   cudaStream_t st) {
+  if (!x || !out2 || !workspace || n_max <= 0) return CB200_EINVAL;
+  auto* ws = static_cast<ReduceWorkspace*>(workspace);
+  const int blocks = grid_for(n_max, RED_THREADS, 8, 8);
+  if (dtype == CB200_F32)
+    minmax_kernel<float><<<blocks, RED_THREADS, 0, st>>>((const float*)x, n_max, n_dev, out2, ws);
+  else if (dtype == CB200_F64)
+    minmax_kernel<double><<<blocks, RED_THREADS, 0, st>>>((const double*)x, n_max, n_dev, out2, ws);
+  else
+    return CB200_EUNSUPPORTED;
+  CB200_LAUNCH_CHECK();
+  return CB200_OK;
+}
+
+// cb200_select_points over the first min(n_max, *n_dev) source points
+int select_points_counted(const double* src, int64_t n_max, const long long* n_dev, int64_t src_stride, int num_dims,
+                          const uint8_t* flags, double* dst, int64_t dst_stride, long long* n_out, void* workspace,
+                          cudaStream_t st) {
+  if (!src || !flags || !dst || !n_out || !workspace || n_max < 0 || num_dims < 1 || num_dims > 3) return CB200_EINVAL;
+  FlagPred pred{flags, n_dev};
+  SelectEmit emit{src, src_stride, dst, dst_stride, num_dims};
+  return run_compaction(pred, emit, n_max, dst_stride, n_out, workspace, st);
+}
+
 }  // namespace cb200
 
 using namespace cb200;
@@ -322,18 +354,7 @@ extern "C" {
 int64_t cb200_reduce_workspace_bytes(void) { return (int64_t)sizeof(ReduceWorkspace); }
 
 int cb200_minmax(const void* x, int dtype, int64_t n, double* out2, void* workspace, void* stream) {
-  if (!x || !out2 || !workspace || n <= 0) return CB200_EINVAL;
-  cudaStream_t st = (cudaStream_t)stream;
-  auto* ws = static_cast<ReduceWorkspace*>(workspace);
-  const int blocks = grid_for(n, RED_THREADS, 8, 8);
-  if (dtype == CB200_F32)
-    minmax_kernel<float><<<blocks, RED_THREADS, 0, st>>>((const float*)x, n, out2, ws);
-  else if (dtype == CB200_F64)
-    minmax_kernel<double><<<blocks, RED_THREADS, 0, st>>>((const double*)x, n, out2, ws);
-  else
-    return CB200_EUNSUPPORTED;
-  CB200_LAUNCH_CHECK();
-  return CB200_OK;
+  return minmax_counted(x, dtype, n, nullptr, out2, workspace, (cudaStream_t)stream);
 }
 
 int cb200_histogram(const void* x, int dtype, int64_t n, const double* edges, int nbins, unsigned long long* counts,
@@ -395,10 +416,8 @@ int cb200_fg_compact(const void* emb, int dtype, int num_dims, const int64_t* sp
 
 int cb200_select_points(const double* src, int64_t n, int64_t src_stride, int num_dims, const uint8_t* flags,
                         double* dst, int64_t dst_stride, long long* n_out, void* workspace, void* stream) {
-  if (!src || !flags || !dst || !n_out || !workspace || n < 0 || num_dims < 1 || num_dims > 3) return CB200_EINVAL;
-  FlagPred pred{flags};
-  SelectEmit emit{src, src_stride, dst, dst_stride, num_dims};
-  return run_compaction(pred, emit, n, dst_stride, n_out, workspace, (cudaStream_t)stream);
+  return select_points_counted(src, n, nullptr, src_stride, num_dims, flags, dst, dst_stride, n_out, workspace,
+                               (cudaStream_t)stream);
 }
 
 int cb200_bernoulli_flags(uint8_t* flags, int64_t n, double p, uint64_t seed, void* stream) {

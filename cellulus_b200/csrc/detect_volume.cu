@@ -3,9 +3,10 @@
 // The step-by-step entry points (cb200_fg_compact ... cb200_assign_labels) neither allocate nor synchronise;
 // a caller that drives them from an interpreter pays for ~11 calls, ~30 small allocations and 4 blocking count
 // reads per volume, which costs more wall time than the ~45 small kernels between the big ones.  This
-// composite runs the identical sequence from C++: scratch comes from a library-owned arena that is kept
-// between calls, the four data-dependent counts (foreground, fit subset, bounding box, centres) are read
-// with a stream synchronise each, everything else is enqueued back to back.  Same kernels, same results.
+// composite runs the identical sequence from C++ out of ONE caller-provided workspace.  The data-dependent counts
+// are read with TWO stream synchronisations: foreground count + fit count + bounding box together (the subset and
+// box kernels are enqueued before the counts are known, sized for the capacity, and read the counts on the
+// device), then the number of centres; everything else is enqueued back to back.  Same kernels, same results.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -48,7 +49,7 @@ static int64_t detect_bytes(int D, int64_t n_pix, int64_t n_fg, int64_t n_fit, i
   auto al = [](int64_t b) { return (b + 255) / 256 * 256 + 256; };
   int64_t t = 512;
   t += al((int64_t)D * 8 * ((n_fg + 1) & ~(int64_t)1)) + al(4 * n_fg) + al(16) + al(cb200_compact_workspace_bytes(n_pix));
-  t += al(n_fg) + al((int64_t)D * 8 * ((n_fit + 1) & ~(int64_t)1));                       // flags, fit subset
+  t += al(n_fg) + al((int64_t)D * 8 * ((n_fit + 4096 + 1) & ~(int64_t)1));                // flags, fit subset (with headroom)
   t += al(48) + al(cb200_reduce_workspace_bytes());                                          // bounding box
   t += 2 * al((int64_t)D * 8 * ((n_fit + 1) & ~(int64_t)1)) + al(4 * (n_cells + 1)) + 2 * al(4 * n_fit) + al(32);
   t += al(cb200_grid_build_workspace_bytes(n_fit, n_cells));
@@ -137,58 +138,65 @@ extern "C" int cb200_detect_volume(const void* emb, int dtype, int num_dims, con
   CB200_CUDA_TRY(cudaMemsetAsync(counts_dev, 0, 2 * sizeof(long long), st));
   CB200_TRY_RC(cb200_fg_compact(emb, dtype, D, spatial, threshold, pts, pix, cap, counts_dev, mask_out, mask_dtype,
                                 compact_ws, st));
-  long long n = 0;
-  CB200_CUDA_TRY(cudaMemcpyAsync(&n, counts_dev, sizeof(long long), cudaMemcpyDeviceToHost, st));
-  CB200_CUDA_TRY(cudaStreamSynchronize(st));
-  info->n_foreground = n;
-  known_fg = n;
-  known_fit = reduction_probability < 1.0 ? (int64_t)(1.1 * reduction_probability * (double)n) + 4096 : n;
-  known_nms = 64 * known_fit + (1 << 20);
-  lap("compact");
-  if (n > cap) {  // more foreground than the caller made room for: nothing beyond `cap` was written
-    info->workspace_needed = detect_bytes(D, n_pix, known_fg, known_fit, known_cells, known_nms);
-    return CB200_ENOSPACE;
-  }
-  if (n == 0) return CB200_OK;  // all background (utils/mean_shift.py:83-84)
 
-  // ---- fit subset (utils/mean_shift.py:67-70), Bernoulli flags from the device Philox stream
+  // ---- fit subset (utils/mean_shift.py:67-70; Bernoulli flags from the device Philox stream) and its bounding box,
+  // enqueued BEFORE the foreground count is known on the host: the kernels are sized for the capacity and read the
+  // counts where they are (the flag of point i depends on i only).  ONE blocking read then returns the foreground
+  // count, the fit count and the box together.
+  const bool subsample = reduction_probability < 1.0;
   const double* fit = pts;
   int64_t fit_stride = cap;
-  long long n_fit = n;
-  if (reduction_probability < 1.0) {
+  int64_t sub_cap = 0;
+  const long long* n_fit_dev = counts_dev;  // all foreground points take part
+  if (subsample) {
     uint8_t* flags;
     double* subset;
-    const int64_t sub_cap = (n + 1) & ~(int64_t)1;
-    POOL_GET(&flags, (size_t)n);
+    sub_cap = (std::min<int64_t>(cap, (int64_t)(1.1 * reduction_probability * (double)cap) + 4096) + 1) & ~(int64_t)1;
+    POOL_GET(&flags, (size_t)cap);
     POOL_GET(&subset, (size_t)D * sub_cap);
-    CB200_TRY_RC(cb200_bernoulli_flags(flags, n, reduction_probability, philox_seed, st));
-    CB200_TRY_RC(cb200_select_points(pts, n, cap, D, flags, subset, sub_cap, counts_dev + 1, compact_ws, st));
-    CB200_CUDA_TRY(cudaMemcpyAsync(&n_fit, counts_dev + 1, sizeof(long long), cudaMemcpyDeviceToHost, st));
-    CB200_CUDA_TRY(cudaStreamSynchronize(st));
+    CB200_TRY_RC(cb200_bernoulli_flags(flags, cap, reduction_probability, philox_seed, st));
+    CB200_TRY_RC(select_points_counted(pts, cap, counts_dev, cap, D, flags, subset, sub_cap, counts_dev + 1, compact_ws, st));
     fit = subset;
     fit_stride = sub_cap;
+    n_fit_dev = counts_dev + 1;
   }
-  info->n_fit = n_fit;
-  known_fit = n_fit;
-  known_nms = 64 * known_fit + (1 << 20);
-  lap("subset");
-  if (n_fit == 0) return CB200_ENOFIT;  // sklearn: "Found array with 0 sample(s)"
-
-  // ---- bounding box of the fit points -> cell grid
   double* box_dev;
   uint8_t* reduce_ws;
   POOL_GET(&box_dev, 6);
   POOL_GET(&reduce_ws, (size_t)cb200_reduce_workspace_bytes());
   CB200_CUDA_TRY(cudaMemsetAsync(reduce_ws, 0, (size_t)cb200_reduce_workspace_bytes(), st));
   for (int k = 0; k < D; ++k)
-    CB200_TRY_RC(cb200_minmax(fit + (size_t)k * fit_stride, CB200_F64, n_fit, box_dev + 2 * k, reduce_ws, st));
-  double box[6];
-  CB200_CUDA_TRY(cudaMemcpyAsync(box, box_dev, sizeof(double) * 2 * D, cudaMemcpyDeviceToHost, st));
+    CB200_TRY_RC(minmax_counted(fit + (size_t)k * fit_stride, CB200_F64, subsample ? sub_cap : cap, n_fit_dev,
+                                box_dev + 2 * k, reduce_ws, st));
+  struct {
+    long long counts[2];
+    double box[6];
+  } head;
+  CB200_CUDA_TRY(cudaMemcpyAsync(head.counts, counts_dev, sizeof(head.counts), cudaMemcpyDeviceToHost, st));
+  CB200_CUDA_TRY(cudaMemcpyAsync(head.box, box_dev, sizeof(double) * 2 * D, cudaMemcpyDeviceToHost, st));
   CB200_CUDA_TRY(cudaStreamSynchronize(st));
+  const long long n = head.counts[0];
+  const long long n_fit = subsample ? head.counts[1] : n;
+  info->n_foreground = n;
+  known_fg = n;
+  known_fit = subsample ? std::max<int64_t>(n_fit, (int64_t)(1.1 * reduction_probability * (double)n) + 4096) : n;
+  known_nms = 64 * known_fit + (1 << 20);
+  lap("compact+subset+bbox");
+  if (n > cap || (subsample && n_fit > sub_cap)) {  // more points than the caller made room for: nothing beyond was written
+    info->workspace_needed = detect_bytes(D, n_pix, known_fg + (known_fg >> 3), known_fit, known_cells, known_nms);
+    return CB200_ENOSPACE;
+  }
+  if (n == 0) return CB200_OK;  // all background (utils/mean_shift.py:83-84)
+  info->n_fit = n_fit;
+  known_fit = n_fit;
+  known_nms = 64 * known_fit + (1 << 20);
+  if (n_fit == 0) return CB200_ENOFIT;  // sklearn: "Found array with 0 sample(s)"
+
+  // ---- cell grid over the bounding box of the fit points
   double lo[3], hi[3];
   for (int k = 0; k < D; ++k) {
-    lo[k] = box[2 * k];
-    hi[k] = box[2 * k + 1];
+    lo[k] = head.box[2 * k];
+    hi[k] = head.box[2 * k + 1];
   }
   cb200_grid grid;
   CB200_TRY_RC(cb200_grid_plan(lo, hi, D, bandwidth, (int64_t)1 << 26, &grid));

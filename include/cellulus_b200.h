@@ -16,7 +16,7 @@
  *     (sizes from the *_workspace_bytes queries).  No entry synchronises the
  *     stream EXCEPT the one composite whose control flow depends on counts
  *     that only exist on the device, and which says so at its declaration:
- *     cb200_detect_volume (four blocking count reads per call).
+ *     cb200_detect_volume (two blocking count reads per call).
  *   - re-entrant across streams as long as workspaces are not shared.
  *   - the staged loss entries (cb200_oce_loss_*_staged with staging scratch)
  *     launch ONE resident wave whose thread blocks wait for each other inside
@@ -411,7 +411,7 @@ CB200_API int cb200_assign_labels(const double* points, int64_t n_points, int64_
  *   stream; 1.0 = all points) -> cell grid -> modes -> centres -> labels (+1, 0 = background).
  * Same kernels and results as the step-by-step entry points above.  It allocates nothing: all scratch comes from the
  * caller's `workspace`.  Its sizes depend on counts that only exist on the device (foreground pixels, fit subset,
- * cells, centres), so unlike the other entry points this one SYNCHRONISES the stream to read them (four small
+ * cells, centres), so unlike the other entry points this one SYNCHRONISES the stream to read them (two small
  * device -> host reads per volume) and is therefore not graph-capturable.  Protocol:
  *   workspace_bytes = cb200_detect_volume_workspace_bytes(num_dims, spatial, expected_foreground, reduction_probability)
  *   foreground_capacity = the expected_foreground the workspace was sized for (<= 0: every pixel)
