@@ -1,6 +1,7 @@
 """Dataset factory with the reference's call signature (`cellulus/datasets/__init__.py:8-27`)."""
 
 from cellulus_b200.datasets.meta_data import DatasetMetaData  # noqa: F401
+from cellulus_b200.datasets.staging import PairListStager  # noqa: F401
 from cellulus_b200.datasets.zarr_dataset import ZarrDataset
 
 
