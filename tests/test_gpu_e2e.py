@@ -119,6 +119,30 @@ def test_use_seeds_bandwidth_loop_reproduces_reference_side_effect():
         detect_with_seeds(d, 6.0, thr, 2, rp, label_dtype=torch.int32)
 
 
+def test_pair_list_stager_narrows_on_the_host():
+    """int64 host lists -> pinned int16 staging -> device: same coordinates, same loss as the int64 lists; a second
+    use of the same slot waits for the first copy; extents beyond int16 are refused."""
+    from cellulus_b200.criterions import oce_loss_fused
+    from cellulus_b200.datasets import PairListStager
+    from oracle import sampler as osampler
+
+    np.random.seed(2)
+    pairs = [osampler.sample_coordinates((60, 60), 10.0, 0.1, 2) for _ in range(2)]
+    anchors = torch.from_numpy(np.stack([p[0] for p in pairs])).long()
+    refs = torch.from_numpy(np.stack([p[1] for p in pairs])).long()
+    stager = PairListStager(anchors.shape, "cuda:0", max_extent=60)
+    for slot in (0, 1, 0):
+        a16, r16 = stager.upload(anchors, refs, slot)
+        assert a16.dtype == torch.int16 and a16.is_cuda
+        assert torch.equal(a16.long().cpu(), anchors) and torch.equal(r16.long().cpu(), refs)
+    offsets = torch.from_numpy(synthetic.loss_offsets(2, 2, (60, 60), seed=1)).cuda()
+    l16, _, _ = oce_loss_fused(offsets, a16, r16, 10.0, 1e-5)
+    l64, _, _ = oce_loss_fused(offsets, anchors.cuda(), refs.cuda(), 10.0, 1e-5)
+    assert abs(l16.item() - l64.item()) <= 1e-6 * abs(l64.item())
+    with pytest.raises(ValueError):
+        PairListStager(anchors.shape, "cuda:0", max_extent=40000)
+
+
 def test_salt_pepper_statistics():
     from cellulus_b200 import kernels as K
 
