@@ -42,7 +42,13 @@ template <typename T> __device__ __forceinline__ T t_exp(T x);
 template <> __device__ __forceinline__ float t_exp<float>(float x) { return expf(x); }
 template <> __device__ __forceinline__ double t_exp<double>(double x) { return exp(x); }
 
-constexpr int GREEDY_THREADS = 256;
+#ifndef CB200_GREEDY_BPS
+#define CB200_GREEDY_BPS 2  // thread blocks per SM of the persistent grid (4 x 256: 11.0 ms, 2 x 512: 9.7 ms, 1 x 1024: 9.9 ms per configs[2] volume)
+#endif
+#ifndef CB200_GREEDY_THREADS
+#define CB200_GREEDY_THREADS 512
+#endif
+constexpr int GREEDY_THREADS = CB200_GREEDY_THREADS;
 
 template <typename T, int D>
 __global__ void __launch_bounds__(GREEDY_THREADS)
@@ -230,7 +236,7 @@ static int greedy_run(const void* emb, int64_t stride, const void* seed_map, int
   int occ = 0;
   CB200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, GREEDY_THREADS, 0));
   if (occ < 1) return CB200_EINVAL;
-  int blocks = std::min(CB200_SM_COUNT * std::min(occ, 4), std::max(1, (n + GREEDY_THREADS - 1) / GREEDY_THREADS));
+  int blocks = std::min(CB200_SM_COUNT * std::min(occ, CB200_GREEDY_BPS), std::max(1, (n + GREEDY_THREADS - 1) / GREEDY_THREADS));
   char* w = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
   GreedyState* state = (GreedyState*)w;                 w += 256;
   uint8_t* unclustered = (uint8_t*)w;                   w += ((size_t)n + 255) / 256 * 256;
