@@ -43,6 +43,7 @@ class DetectInfo(C.Structure):
         ("distance_tests", C.c_int64),
         ("climb_steps", C.c_int64),
         ("workspace_needed", C.c_int64),
+        ("n_distinct_modes", C.c_int64),
     ]
 
 
@@ -98,6 +99,8 @@ PROTOTYPES = {
     "cb200_ms_grid_modes": (_i, [_p, _i64, _i64, C.POINTER(Grid), _p, _p, _i64, _i64, _d, _i, _p, _p, _p, _p]),
     "cb200_bin_seeds_workspace_bytes": (_i64, [_i64]),
     "cb200_bin_seeds": (_i, [_p, _i64, _i64, _i, _d, _p, _i64, _p, _p, _p, _i64, _p]),
+    "cb200_unique_modes_workspace_bytes": (_i64, [_i64]),
+    "cb200_unique_modes": (_i, [_p, _i64, _i, _p, _i64, _p, _i64, _p, _p, _p, _i64, _p]),
     "cb200_nms_workspace_bytes": (_i64, [_i64, C.POINTER(Grid), _d]),
     "cb200_nms_suppress": (_i, [_p, _i64, _i, _p, _i64, _d, C.POINTER(Grid), _i, _i, _p, _p, _i64, _p]),
     "cb200_nms_emit": (_i, [_p, _i64, _i, _p, _i64, _d, C.POINTER(Grid), _i, _p, _i64, _p, _i64, _p]),

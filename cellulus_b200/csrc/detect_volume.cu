@@ -4,9 +4,9 @@
 // a caller that drives them from an interpreter pays for ~11 calls, ~30 small allocations and 4 blocking count
 // reads per volume, which costs more wall time than the ~45 small kernels between the big ones.  This
 // composite runs the identical sequence from C++ out of ONE caller-provided workspace.  The data-dependent counts
-// are read with TWO stream synchronisations: foreground count + fit count + bounding box together (the subset and
+// are read with THREE stream synchronisations: foreground count + fit count + bounding box together (the subset and
 // box kernels are enqueued before the counts are known, sized for the capacity, and read the counts on the
-// device), then the number of centres; everything else is enqueued back to back.  Same kernels, same results.
+// device), the number of distinct modes, the number of centres; everything else is enqueued back to back.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -54,6 +54,7 @@ static int64_t detect_bytes(int D, int64_t n_pix, int64_t n_fg, int64_t n_fit, i
   t += 2 * al((int64_t)D * 8 * ((n_fit + 1) & ~(int64_t)1)) + al(4 * (n_cells + 1)) + 2 * al(4 * n_fit) + al(32);
   t += al(cb200_grid_build_workspace_bytes(n_fit, n_cells));
   t += al(nms_bytes) + al(8) + al((int64_t)D * 8 * ((n_fit + 1) & ~(int64_t)1));            // suppression, centres
+  t += al((int64_t)D * 8 * ((n_fit + 1) & ~(int64_t)1)) + al(4 * n_fit) + al(8) + al(cb200_unique_modes_workspace_bytes(n_fit));  // distinct modes
   t += al(cb200_assign_workspace_bytes(n_fg, (int)std::min<int64_t>(n_fit, INT32_MAX), n_cells));
   return t;
 }
@@ -230,24 +231,54 @@ extern "C" int cb200_detect_volume(const void* emb, int dtype, int num_dims, con
   info->n_seeds = n_fit;
   lap("modes");
 
-  // ---- centres: dedupe + greedy suppression (sklearn:511-547)
-  const int64_t nms_bytes = cb200_nms_workspace_bytes(n_fit, &grid, bandwidth);
-  if (nms_bytes < 0) return CB200_EUNSUPPORTED;
-  known_nms = nms_bytes;
-  uint8_t* nms_ws;
-  int* keep_dev;
-  POOL_GET(&nms_ws, (size_t)nms_bytes);
-  POOL_GET(&keep_dev, 2);
-  CB200_CUDA_TRY(cudaMemsetAsync(keep_dev, 0, 2 * sizeof(int), st));
-  int keep[2] = {0, 1};
+  // ---- centres: merge bit-identical modes, then greedy suppression (sklearn:511-547)
   long long stats[2] = {0, 0};  // the hill climb's work statistics ride on the first count read
   CB200_CUDA_TRY(cudaMemcpyAsync(stats, work + 2, sizeof(stats), cudaMemcpyDeviceToHost, st));
-  for (int call = 0; call < 64 && keep[1] != 0; ++call) {
-    CB200_TRY_RC(cb200_nms_suppress(modes, fit_cap, D, counts, n_fit, bandwidth, &grid, 4, call > 0, keep_dev, nms_ws,
-                                    nms_bytes, st));
-    CB200_CUDA_TRY(cudaMemcpyAsync(keep, keep_dev, sizeof(keep), cudaMemcpyDeviceToHost, st));
+  // CB200_DETECT_DEDUPE=0: suppression over all converged seeds (A/B switch).  Default: seeds that end in the same
+  // window end in the SAME mean, so one exact pass leaves hundreds of candidates out of hundreds of thousands.
+  static const bool dedupe = [] { const char* e = getenv("CB200_DETECT_DEDUPE"); return !(e && e[0] == '0'); }();
+  const double* cand = modes;
+  const int* cand_counts = counts;
+  long long n_cand = n_fit;
+  if (dedupe) {
+    double* umodes;
+    int* ucounts;
+    long long* n_unique_dev;
+    uint8_t* unique_ws;
+    const int64_t unique_bytes = cb200_unique_modes_workspace_bytes(n_fit);
+    POOL_GET(&umodes, (size_t)D * fit_cap);
+    POOL_GET(&ucounts, (size_t)n_fit);
+    POOL_GET(&n_unique_dev, 1);
+    POOL_GET(&unique_ws, (size_t)unique_bytes);
+    CB200_TRY_RC(cb200_unique_modes(modes, fit_cap, D, counts, n_fit, umodes, fit_cap, ucounts, n_unique_dev, unique_ws,
+                                    unique_bytes, st));
+    CB200_CUDA_TRY(cudaMemcpyAsync(&n_cand, n_unique_dev, sizeof(long long), cudaMemcpyDeviceToHost, st));
     CB200_CUDA_TRY(cudaStreamSynchronize(st));
-    ++info->suppress_calls;
+    cand = umodes;
+    cand_counts = ucounts;
+    lap("unique");
+  }
+  info->n_distinct_modes = n_cand;
+  int keep[2] = {0, n_cand > 0 ? 1 : 0};
+  uint8_t* nms_ws = nullptr;
+  int64_t nms_bytes = 0;
+  if (n_cand > 0) {
+    nms_bytes = cb200_nms_workspace_bytes(n_cand, &grid, bandwidth);
+    if (nms_bytes < 0) return CB200_EUNSUPPORTED;
+    known_nms = nms_bytes;
+    int* keep_dev;
+    POOL_GET(&nms_ws, (size_t)nms_bytes);
+    POOL_GET(&keep_dev, 2);
+    CB200_CUDA_TRY(cudaMemsetAsync(keep_dev, 0, 2 * sizeof(int), st));
+    for (int call = 0; call < 64 && keep[1] != 0; ++call) {
+      CB200_TRY_RC(cb200_nms_suppress(cand, fit_cap, D, cand_counts, n_cand, bandwidth, &grid, 4, call > 0, keep_dev,
+                                      nms_ws, nms_bytes, st));
+      CB200_CUDA_TRY(cudaMemcpyAsync(keep, keep_dev, sizeof(keep), cudaMemcpyDeviceToHost, st));
+      CB200_CUDA_TRY(cudaStreamSynchronize(st));
+      ++info->suppress_calls;
+    }
+  } else {
+    CB200_CUDA_TRY(cudaStreamSynchronize(st));  // the statistics copy
   }
   lap("suppress");
   info->distance_tests = stats[0];
@@ -265,8 +296,8 @@ extern "C" int cb200_detect_volume(const void* emb, int dtype, int num_dims, con
   } else {
     POOL_GET(&centres, (size_t)D * c_cap);
   }
-  CB200_TRY_RC(cb200_nms_emit(modes, fit_cap, D, counts, n_fit, bandwidth, &grid, k_centres, centres, c_stride, nms_ws,
-                              nms_bytes, st));
+  CB200_TRY_RC(cb200_nms_emit(cand, fit_cap, D, cand_counts, n_cand, bandwidth, &grid, k_centres, centres, c_stride,
+                              nms_ws, nms_bytes, st));
 
   // ---- predict on ALL foreground points, scatter, +1 (utils/mean_shift.py:74,101-104,57)
   uint8_t* assign_ws;

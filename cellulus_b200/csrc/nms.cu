@@ -624,6 +624,102 @@ assign_grid_kernel(const double* __restrict__ points, int64_t n, int64_t pts_str
   }
 }
 
+// ---- exact duplicates first ------------------------------------------------------------------------
+// A flat-kernel hill climb has finitely many fixed points: seeds that end in the same window of points end in the SAME
+// mean, bit for bit (same points, same summation order).  At BASELINE configs[2] 148 228 converged seeds are 395 distinct
+// modes; on the 272^3 sharded volume 3.23 M seeds are 963.  scikit-learn merges them in a dict (sklearn:514-521); the
+// suppression rounds above treat them as candidates that remove each other.  This pass keeps ONE copy of every distinct
+// mode -- the one the suppression would keep anyway: highest count, then lowest index (has_priority) -- so that the rounds
+// run on hundreds of modes instead of hundreds of thousands.  A removed copy can never influence another mode (it is
+// removed by its own kept copy, or by whatever removes that), so the surviving centres and their order are unchanged.
+// Open-addressing table keyed by the modes' bit patterns; a slot holds the best (count, index) seen for its mode.
+__device__ __forceinline__ uint64_t mode_hash(const double* __restrict__ modes, int64_t stride, int D, int64_t i) {
+  uint64_t h = 0x9E3779B97F4A7C15ull;
+  for (int k = 0; k < D; ++k) {
+    uint64_t x = (uint64_t)__double_as_longlong(modes[k * stride + i]);
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    h = (h ^ x) * 0x9E3779B97F4A7C15ull;
+  }
+  return h ^ (h >> 32);
+}
+__device__ __forceinline__ bool same_mode(const double* __restrict__ modes, int64_t stride, int D, int64_t i, int64_t j) {
+  for (int k = 0; k < D; ++k)
+    if (__double_as_longlong(modes[k * stride + i]) != __double_as_longlong(modes[k * stride + j])) return false;
+  return true;
+}
+// packed priority: larger = kept; 0 = empty slot
+__device__ __forceinline__ unsigned long long mode_priority(int count, int64_t i) {
+  return ((unsigned long long)(unsigned)(count + 1) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
+}
+__device__ __forceinline__ int64_t priority_index(unsigned long long p) { return (int64_t)(0xffffffffu - (unsigned)(p & 0xffffffffull)); }
+
+__global__ void __launch_bounds__(256)
+unique_insert_kernel(const double* __restrict__ modes, int64_t stride, int D, const int* __restrict__ counts, int64_t n,
+                     unsigned long long* __restrict__ table, uint64_t mask) {
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
+    const int cnt = counts[i];
+    if (cnt <= 0) continue;  // a seed without neighbours is dropped (sklearn:511-513)
+    const unsigned long long mine = mode_priority(cnt, i);
+    uint64_t slot = mode_hash(modes, stride, D, i) & mask;
+    while (true) {
+      unsigned long long cur = *((volatile unsigned long long*)&table[slot]);
+      if (cur == 0ull) {
+        cur = atomicCAS(&table[slot], 0ull, mine);
+        if (cur == 0ull) break;  // claimed an empty slot for this mode
+      }
+      if (same_mode(modes, stride, D, i, priority_index(cur))) {  // the occupant is a copy of this mode (copies only
+        if (mine > cur) atomicMax(&table[slot], mine);             // replace copies, so the test stays valid)
+        break;
+      }
+      slot = (slot + 1) & mask;
+    }
+  }
+}
+
+// a mode is kept iff it is the best copy recorded for its bit pattern
+struct UniquePred {
+  const double* modes;
+  int64_t stride;
+  int D;
+  const int* counts;
+  const unsigned long long* table;
+  uint64_t mask;
+  __device__ __forceinline__ bool operator()(int64_t i) const {
+    if (counts[i] <= 0) return false;
+    uint64_t slot = mode_hash(modes, stride, D, i) & mask;
+    while (true) {
+      const unsigned long long cur = table[slot];
+      if (cur == 0ull) return false;  // cannot happen: every live mode was inserted
+      const int64_t j = priority_index(cur);
+      if (j == i) return true;
+      if (same_mode(modes, stride, D, i, j)) return false;
+      slot = (slot + 1) & mask;
+    }
+  }
+};
+struct UniqueEmit {
+  const double* modes;
+  int64_t stride;
+  int D;
+  const int* counts;
+  double* out;
+  int64_t out_stride;
+  int* counts_out;
+  __device__ __forceinline__ void operator()(int64_t i, long long d) const {
+    for (int k = 0; k < D; ++k) out[k * out_stride + d] = modes[k * stride + i];
+    counts_out[d] = counts[i];
+  }
+};
+
+static uint64_t unique_table_slots(int64_t n) {
+  uint64_t slots = 1024;
+  while (slots < (uint64_t)(2 * n)) slots <<= 1;
+  return slots;
+}
+
 }  // namespace cb200
 
 using namespace cb200;
@@ -716,6 +812,35 @@ int cb200_assign_labels(const double* points, int64_t n_points, int64_t pts_stri
 #undef CB200_BRUTE
   CB200_LAUNCH_CHECK();
   return CB200_OK;
+}
+
+int64_t cb200_unique_modes_workspace_bytes(int64_t n_seeds) {
+  if (n_seeds < 0) return -1;
+  return (int64_t)(unique_table_slots(n_seeds) * sizeof(unsigned long long)) + CompactWorkspace::bytes(n_seeds) + 512;
+}
+
+int cb200_unique_modes(const double* modes, int64_t seed_stride, int num_dims, const int* counts, int64_t n_seeds,
+                       double* modes_out, int64_t out_stride, int* counts_out, long long* n_out, void* workspace,
+                       int64_t workspace_bytes, void* stream) {
+  if (!modes || !counts || !modes_out || !counts_out || !n_out || !workspace || n_seeds < 0 || num_dims < 1 || num_dims > 3)
+    return CB200_EINVAL;
+  if (n_seeds >= ((int64_t)1 << 32) - 1 || workspace_bytes < cb200_unique_modes_workspace_bytes(n_seeds)) return CB200_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_seeds == 0) {
+    CB200_CUDA_TRY(cudaMemsetAsync(n_out, 0, sizeof(long long), st));
+    return CB200_OK;
+  }
+  char* w = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
+  const uint64_t slots = unique_table_slots(n_seeds);
+  auto* table = reinterpret_cast<unsigned long long*>(w);
+  void* compact_ws = w + slots * sizeof(unsigned long long);
+  CB200_CUDA_TRY(cudaMemsetAsync(table, 0, slots * sizeof(unsigned long long), st));
+  unique_insert_kernel<<<grid_for(n_seeds, 256, 1, 16), 256, 0, st>>>(modes, seed_stride, num_dims, counts, n_seeds, table,
+                                                                      slots - 1);
+  CB200_LAUNCH_CHECK();
+  UniquePred pred{modes, seed_stride, num_dims, counts, table, slots - 1};
+  UniqueEmit emit{modes, seed_stride, num_dims, counts, modes_out, out_stride, counts_out};
+  return run_compaction(pred, emit, n_seeds, out_stride, n_out, compact_ws, st);
 }
 
 }  // extern "C"

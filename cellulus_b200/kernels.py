@@ -596,11 +596,35 @@ def bin_seeds(points: torch.Tensor, n: int, bin_size: float):
     return seeds, k
 
 
-def nms_centres(modes_soa, counts, n_seeds, bandwidth, grid: Grid, rounds_per_call: int = 4):
-    """sklearn:511-547 on the device.  Returns `(centres (D, cap) SoA in `cluster_centers_` order, K)`.
-    One host sync per call of `rounds_per_call` rounds (the fix-point takes 2-3 rounds in practice)."""
+def unique_modes(modes_soa, counts, n_seeds):
+    """`cb200_unique_modes`: one copy of every bit-identical mode with count > 0 (the copy the suppression would keep).
+    Returns `(modes (D, cap) SoA, counts, n_unique)`; one host sync for the count."""
     dev = modes_soa.device
     D = modes_soa.shape[0]
+    cap = max(2, (n_seeds + 1) & ~1)
+    out = torch.empty((D, cap), dtype=torch.float64, device=dev)
+    counts_out = torch.empty(max(n_seeds, 1), dtype=torch.int32, device=dev)
+    n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+    nbytes = _lib().cb200_unique_modes_workspace_bytes(n_seeds)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    rc = _lib().cb200_unique_modes(_ptr(modes_soa), modes_soa.stride(0), D, _ptr(counts), n_seeds, _ptr(out), cap,
+                                   _ptr(counts_out), _ptr(n_out), _ptr(ws), nbytes, _stream(modes_soa))
+    check(rc, "cb200_unique_modes")
+    launch_counter["calls"] += 1
+    return out, counts_out, int(n_out.item())
+
+
+def nms_centres(modes_soa, counts, n_seeds, bandwidth, grid: Grid, rounds_per_call: int = 4, dedupe: bool = True):
+    """sklearn:511-547 on the device.  Returns `(centres (D, cap) SoA in `cluster_centers_` order, K)`.
+    One host sync per call of `rounds_per_call` rounds (the fix-point takes 2-3 rounds in practice).
+    `dedupe`: merge bit-identical modes first (`cb200_unique_modes`; same centres, in the same order, from far fewer
+    candidates)."""
+    dev = modes_soa.device
+    D = modes_soa.shape[0]
+    if dedupe and n_seeds > 1024:
+        modes_soa, counts, n_seeds = unique_modes(modes_soa, counts, n_seeds)
+        if n_seeds == 0:
+            return torch.zeros((D, 2), dtype=torch.float64, device=dev), 0
     out2 = torch.zeros(2, dtype=torch.int32, device=dev)
     nbytes = _lib().cb200_nms_workspace_bytes(n_seeds, C.byref(grid), float(bandwidth))
     if nbytes < 0:
@@ -895,7 +919,8 @@ def detect_volume(emb: torch.Tensor, bandwidth: float, threshold: float, reducti
     return labels, mask, centres, {"n_fg": int(info.n_foreground), "n_fit": int(info.n_fit),
                                    "n_seeds": int(info.n_seeds), "k": int(info.n_centres), "method": "grid",
                                    "grid_cells": int(info.grid.n_cells), "suppress_calls": int(info.suppress_calls),
-                                   "distance_tests": int(info.distance_tests), "climb_steps": int(info.climb_steps)}
+                                   "distance_tests": int(info.distance_tests), "climb_steps": int(info.climb_steps),
+                                   "distinct_modes": int(info.n_distinct_modes)}
 
 
 def release_scratch(device=None) -> None:

@@ -117,11 +117,15 @@ class MeanShiftOps:
     climb(points (D,n), seeds (D,s), bandwidth)           -> (modes (D,s), counts (s,), iters (s,))
     suppress(modes (D,s), counts (s,), bandwidth, points)  -> centres (D,k) in priority order
     assign(points (D,n), centres (D,k))                    -> labels (n,) int, 1 + nearest centre
+    dedupe(modes (D,s), counts (s,))                       -> (modes (D,u), counts (u,)): one copy of every
+        bit-identical mode with count > 0 (optional; seeds that end in the same window end in the SAME mean, so a
+        rank's share of the modes shrinks by orders of magnitude before it is gathered and suppressed)
     """
 
     climb: Callable
     suppress: Callable
     assign: Callable
+    dedupe: Optional[Callable] = None
 
 
 class _PhaseTimer:
@@ -178,11 +182,18 @@ def sharded_mean_shift(local_points: torch.Tensor, n_local: int, bandwidth: floa
     seeds = fit_all[:, mine].contiguous() if world > 1 else fit_all.clone()
     modes, counts, _ = ops.climb(fit_all, seeds, bandwidth)
     clock.mark("climb")
-    # exchange 2: converged (mode, count) of every seed; put back into global seed order
+    # exchange 2: converged (mode, count) of every seed.  With a dedupe op every rank first merges its bit-identical
+    # modes (exact: the suppression keeps the same copy); the order of the gathered modes does not matter to the
+    # suppression (it orders them by (count, coordinates) itself).  Without one they go back into global seed order.
     n_mine = int(mine.numel())
-    packed = torch.cat([modes[:, :n_mine], counts[:n_mine].to(modes.dtype)[None]], dim=0)
+    modes_mine, counts_mine = modes[:, :n_mine], counts[:n_mine]
+    deduped = ops.dedupe is not None and n_mine > 0
+    if deduped:
+        modes_mine, counts_mine = ops.dedupe(modes_mine, counts_mine)
+        n_mine = int(modes_mine.shape[1])
+    packed = torch.cat([modes_mine[:, :n_mine], counts_mine[:n_mine].to(modes.dtype)[None]], dim=0)
     packed_all, _ = all_gather_columns(packed.contiguous(), n_mine, group)
-    if world > 1:
+    if world > 1 and ops.dedupe is None:
         ordered = torch.empty_like(packed_all)
         ordered[:, torch.cat(idx)] = packed_all
         packed_all = ordered
@@ -253,4 +264,9 @@ def cuda_ops(method: str = "auto") -> MeanShiftOps:
             K.assign_labels(pad(points), n, pad(centres), centres.shape[1], None, labels, grid=ctx.get("grid"))
         return labels[:n]
 
-    return MeanShiftOps(climb, suppress, assign)
+    def dedupe(modes, counts):
+        s = modes.shape[1]
+        m, c, u = K.unique_modes(pad(modes), counts.contiguous(), s)
+        return m[:, :u], c[:u]
+
+    return MeanShiftOps(climb, suppress, assign, dedupe)

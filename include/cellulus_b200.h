@@ -16,7 +16,7 @@
  *     (sizes from the *_workspace_bytes queries).  No entry synchronises the
  *     stream EXCEPT the one composite whose control flow depends on counts
  *     that only exist on the device, and which says so at its declaration:
- *     cb200_detect_volume (two blocking count reads per call).
+ *     cb200_detect_volume (three blocking count reads per call).
  *   - re-entrant across streams as long as workspaces are not shared.
  *   - the staged loss entries (cb200_oce_loss_*_staged with staging scratch)
  *     launch ONE resident wave whose thread blocks wait for each other inside
@@ -380,6 +380,16 @@ CB200_API int cb200_bin_seeds(const double* points, int64_t n_points, int64_t pt
  * cb200_nms_emit: writes the n_keep survivors in sklearn's `cluster_centers_` order
  *   into centres_out SoA (D x centre_stride).  n_keep is the host copy of [0].
  */
+/* Exact duplicates first (optional, in front of cb200_nms_suppress): a flat-kernel hill climb has finitely many fixed
+ * points -- 148 228 converged seeds of BASELINE configs[2] are 395 distinct modes -- and scikit-learn merges them in a
+ * dict (sklearn:514-521).  Keeps ONE copy of every bit-identical mode with count > 0: the copy the suppression would
+ * keep (highest count, then lowest index), in input order; the surviving centres and their order are the same with or
+ * without this pass.  modes_out SoA (D x out_stride, out_stride >= n_seeds may alias nothing), counts_out (n_seeds),
+ * *n_out (device int64) = number of distinct modes. */
+CB200_API int64_t cb200_unique_modes_workspace_bytes(int64_t n_seeds);
+CB200_API int cb200_unique_modes(const double* modes, int64_t seed_stride, int num_dims, const int* counts, int64_t n_seeds,
+                       double* modes_out, int64_t out_stride, int* counts_out, long long* n_out, void* workspace,
+                       int64_t workspace_bytes, void* stream);
 CB200_API int64_t cb200_nms_workspace_bytes(int64_t n_seeds, const cb200_grid* grid, double bandwidth);
 CB200_API int cb200_nms_suppress(const double* modes, int64_t seed_stride, int num_dims, const int* counts, int64_t n_seeds,
                        double bandwidth, const cb200_grid* grid, int rounds, int resume,
@@ -411,7 +421,7 @@ CB200_API int cb200_assign_labels(const double* points, int64_t n_points, int64_
  *   stream; 1.0 = all points) -> cell grid -> modes -> centres -> labels (+1, 0 = background).
  * Same kernels and results as the step-by-step entry points above.  It allocates nothing: all scratch comes from the
  * caller's `workspace`.  Its sizes depend on counts that only exist on the device (foreground pixels, fit subset,
- * cells, centres), so unlike the other entry points this one SYNCHRONISES the stream to read them (two small
+ * cells, centres), so unlike the other entry points this one SYNCHRONISES the stream to read them (three small
  * device -> host reads per volume) and is therefore not graph-capturable.  Protocol:
  *   workspace_bytes = cb200_detect_volume_workspace_bytes(num_dims, spatial, expected_foreground, reduction_probability)
  *   foreground_capacity = the expected_foreground the workspace was sized for (<= 0: every pixel)
@@ -431,6 +441,7 @@ typedef struct cb200_detect_info {
   int64_t distance_tests; /* seed x candidate evaluations of the hill climb (its algorithmic work) */
   int64_t climb_steps;    /* sum over seeds of (iterations + 1): window evaluations */
   int64_t workspace_needed; /* set with CB200_ENOSPACE */
+  int64_t n_distinct_modes; /* bit-distinct converged modes with count > 0: what the suppression ran on */
 } cb200_detect_info;
 
 CB200_API int64_t cb200_detect_volume_workspace_bytes(int num_dims, const int64_t* spatial, int64_t expected_foreground,

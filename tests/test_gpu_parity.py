@@ -775,6 +775,51 @@ def test_mean_shift_matches_oracle_larger_scene():
         assert np.array_equal(labels.cpu().numpy() > 0, ref > 0)
 
 
+def test_unique_modes_keeps_the_copy_the_suppression_keeps():
+    """`cb200_unique_modes`: one copy per bit-identical mode with count > 0 -- the one with the highest count, then
+    the lowest index -- in input order; against numpy on crafted duplicates, and the suppression gives the same
+    centres in the same order with and without the pass on a real scene."""
+    dev = _dev()
+    rng = np.random.default_rng(0)
+    base = rng.normal(size=(3, 37)) * 50
+    pick = rng.integers(0, 37, size=5000)
+    modes = base[:, pick].copy()
+    modes[0, 100] = -0.0  # a different bit pattern than +0.0: its own mode (the suppression merges the two anyway)
+    modes[0, 101] = 0.0
+    counts = rng.integers(0, 4, size=5000).astype(np.int32)  # zeros are dropped
+    m = torch.zeros((3, 5000), dtype=torch.float64, device=dev)
+    m[:] = torch.from_numpy(modes).to(dev)
+    out, c_out, n_u = K.unique_modes(m, torch.from_numpy(counts).to(dev), 5000)
+    best = {}
+    for i in range(5000):
+        if counts[i] <= 0:
+            continue
+        key = modes[:, i].tobytes()
+        if key not in best or counts[i] > counts[best[key]]:
+            best[key] = i
+    keep = sorted(best.values())
+    assert n_u == len(keep)
+    assert np.array_equal(out[:, :n_u].cpu().numpy().view(np.int64), modes[:, keep].view(np.int64))
+    assert np.array_equal(c_out[:n_u].cpu().numpy(), counts[keep])
+    # all-empty and tiny inputs
+    _, _, n0 = K.unique_modes(m, torch.zeros(5000, dtype=torch.int32, device=dev), 5000)
+    assert n0 == 0
+    # same centres, same order, with and without the pass
+    emb_np, _, _ = synthetic.blob_scene((40, 96, 96), 30, radius=8.0, seed=4)
+    emb = torch.from_numpy(emb_np).to(dev)
+    pts, _, n, _ = K.fg_compact(emb, 0.5)
+    lo, hi = K.bounding_box(pts, n)
+    grid = K.plan_grid(lo, hi, 6.0)
+    sorted_pts, cell_start, _ = K.grid_build(pts, n, grid)
+    seeds = pts.clone()
+    cnt, _ = K.ms_grid_modes(sorted_pts, n, grid, cell_start, seeds, n, 6.0)
+    a, ka = K.nms_centres(seeds, cnt, n, 6.0, grid, dedupe=True)
+    b, kb = K.nms_centres(seeds, cnt, n, 6.0, grid, dedupe=False)
+    assert ka == kb and ka >= 20 and torch.equal(a[:, :ka], b[:, :kb])
+    _, _, n_u = K.unique_modes(seeds, cnt, n)
+    assert ka <= n_u < n // 10  # orders of magnitude fewer candidates than seeds
+
+
 def test_mean_shift_kats_and_edges():
     """Known answers verified on the reference: inclusive radius, orphans labelled by predict,
     ties -> lowest index, empty-window seeds dropped, empty mask -> all background."""
