@@ -149,6 +149,13 @@ int select_points_counted(const double* src, int64_t n_max, const long long* n_d
                           const uint8_t* flags, double* dst, int64_t dst_stride, long long* n_out, void* workspace,
                           cudaStream_t st);
 
+// meanshift.cu: cb200_ms_grid_modes with its optional modes (unfinished hand-over after `eval_limit` evaluations; resume
+// of the seeds in `worklist`, their number read on the device)
+int ms_grid_modes_launch(const double* points_sorted, int64_t n_points, int64_t sorted_stride, const cb200_grid* grid,
+                         const int* cell_start, double* means, int64_t seed_stride, int64_t n_seeds, double bandwidth,
+                         int max_iter, int* counts, int* iters, int* work_counter, const int* worklist,
+                         const long long* n_work_dev, int eval_limit, cudaStream_t st);
+
 // ------------------------------------------------------------------ mbarrier / 1-D TMA helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -52,7 +52,7 @@ static int64_t detect_bytes(int D, int64_t n_pix, int64_t n_fg, int64_t n_fit, i
   t += al(n_fg) + al((int64_t)D * 8 * ((n_fit + 4096 + 1) & ~(int64_t)1));                // flags, fit subset (with headroom)
   t += al(48) + al(cb200_reduce_workspace_bytes());                                          // bounding box
   t += 2 * al((int64_t)D * 8 * ((n_fit + 1) & ~(int64_t)1)) + al(4 * (n_cells + 1)) + 2 * al(4 * n_fit) + al(32);
-  t += al(cb200_grid_build_workspace_bytes(n_fit, n_cells));
+  t += al(cb200_grid_build_workspace_bytes(n_fit, n_cells)) + al(cb200_ms_distinct_workspace_bytes(n_fit)) + al(64);
   t += al(nms_bytes) + al(8) + al((int64_t)D * 8 * ((n_fit + 1) & ~(int64_t)1));            // suppression, centres
   t += al((int64_t)D * 8 * ((n_fit + 1) & ~(int64_t)1)) + al(4 * n_fit) + al(8) + al(cb200_unique_modes_workspace_bytes(n_fit));  // distinct modes
   t += al(cb200_assign_workspace_bytes(n_fg, (int)std::min<int64_t>(n_fit, INT32_MAX), n_cells));
@@ -216,24 +216,35 @@ extern "C" int cb200_detect_volume(const void* emb, int dtype, int num_dims, con
   POOL_GET(&cell_start, (size_t)grid.n_cells + 1);
   POOL_GET(&counts, (size_t)n_fit);
   POOL_GET(&iters, (size_t)n_fit);
-  POOL_GET(&work, 8);
+  POOL_GET(&work, 16);
   POOL_GET(&build_ws, (size_t)build_bytes);
   CB200_TRY_RC(cb200_grid_build(fit, n_fit, fit_stride, &grid, sorted, fit_cap, nullptr, cell_start, build_ws,
                                 build_bytes, st));
   for (int k = 0; k < D; ++k)
     CB200_CUDA_TRY(cudaMemcpyAsync(modes + (size_t)k * fit_cap, fit + (size_t)k * fit_stride, sizeof(double) * n_fit,
                                    cudaMemcpyDeviceToDevice, st));
-  CB200_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * n_fit, st));
-  CB200_CUDA_TRY(cudaMemsetAsync(iters, 0, sizeof(int) * n_fit, st));
-  CB200_CUDA_TRY(cudaMemsetAsync(work, 0, 8 * sizeof(int), st));
-  CB200_TRY_RC(cb200_ms_grid_modes(sorted, n_fit, fit_cap, &grid, cell_start, modes, fit_cap, n_fit, bandwidth,
-                                   max_iter > 0 ? max_iter : 300, counts, iters, work, st));
+  CB200_CUDA_TRY(cudaMemsetAsync(work, 0, 16 * sizeof(int), st));
+  // CB200_DETECT_CLIMB=all: every seed climbs to convergence on its own (A/B switch).  Default: one window evaluation
+  // per seed, then one representative of every distinct unfinished mean (cb200_ms_grid_modes_distinct) -- the centres
+  // only need the distinct modes, and copies of a trajectory end in copies of its mode.
+  static const bool climb_all = [] { const char* e = getenv("CB200_DETECT_CLIMB"); return e && e[0] == 'a'; }();
+  if (climb_all) {
+    CB200_TRY_RC(cb200_ms_grid_modes(sorted, n_fit, fit_cap, &grid, cell_start, modes, fit_cap, n_fit, bandwidth,
+                                     max_iter > 0 ? max_iter : 300, counts, iters, work, st));
+  } else {
+    uint8_t* distinct_ws;
+    const int64_t distinct_bytes = cb200_ms_distinct_workspace_bytes(n_fit);
+    POOL_GET(&distinct_ws, (size_t)distinct_bytes);
+    CB200_TRY_RC(cb200_ms_grid_modes_distinct(sorted, n_fit, fit_cap, &grid, cell_start, modes, fit_cap, n_fit, bandwidth,
+                                              max_iter > 0 ? max_iter : 300, counts, iters, work, distinct_ws,
+                                              distinct_bytes, st));
+  }
   info->n_seeds = n_fit;
   lap("modes");
 
   // ---- centres: merge bit-identical modes, then greedy suppression (sklearn:511-547)
-  long long stats[2] = {0, 0};  // the hill climb's work statistics ride on the first count read
-  CB200_CUDA_TRY(cudaMemcpyAsync(stats, work + 2, sizeof(stats), cudaMemcpyDeviceToHost, st));
+  long long stats[6] = {0, 0, 0, 0, 0, 0};  // the hill climb's work statistics ride on the first count read:
+  CB200_CUDA_TRY(cudaMemcpyAsync(stats, work + 2, sizeof(stats), cudaMemcpyDeviceToHost, st));  // tests, steps, -, -, tests, steps
   // CB200_DETECT_DEDUPE=0: suppression over all converged seeds (A/B switch).  Default: seeds that end in the same
   // window end in the SAME mean, so one exact pass leaves hundreds of candidates out of hundreds of thousands.
   static const bool dedupe = [] { const char* e = getenv("CB200_DETECT_DEDUPE"); return !(e && e[0] == '0'); }();
@@ -281,8 +292,8 @@ extern "C" int cb200_detect_volume(const void* emb, int dtype, int num_dims, con
     CB200_CUDA_TRY(cudaStreamSynchronize(st));  // the statistics copy
   }
   lap("suppress");
-  info->distance_tests = stats[0];
-  info->climb_steps = stats[1];
+  info->distance_tests = stats[0] + stats[4];
+  info->climb_steps = stats[1] + stats[5];
   if (keep[1] != 0) return CB200_ENOCONVERGE;
   const int k_centres = keep[0];
   info->n_centres = k_centres;

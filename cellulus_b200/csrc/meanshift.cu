@@ -266,19 +266,32 @@ __global__ void __launch_bounds__(MSG_THREADS, CB200_MSG_MINBLOCKS)
 ms_grid_modes_kernel(const double* __restrict__ pts, int64_t pts_stride, GridDev g,
                      const int* __restrict__ cell_start, double* __restrict__ means, int64_t seed_stride,
                      int64_t n_seeds, double r2, double stop, int max_iter, int* __restrict__ counts,
-                     int* __restrict__ iters, int* __restrict__ work_counter) {
+                     int* __restrict__ iters, int* __restrict__ work_counter, const int* __restrict__ worklist,
+                     const long long* __restrict__ n_work_dev, int eval_limit) {
+  // Two optional modes for the distinct-trajectory form (cb200_ms_grid_modes_distinct):
+  //   eval_limit > 0   a seed that has not converged after `eval_limit` window evaluations is left UNFINISHED: its
+  //                    current mean in `means`, iters[s] = -1 - (iterations done);
+  //   worklist != NULL only the seeds listed there (their number is read on the device) are climbed, each resuming
+  //                    from such an unfinished state.
   const int lane = lane_id();
   unsigned long long tests = 0;  // distance tests this lane made (statistics: the kernel's algorithmic work)
   unsigned long long steps = 0;  // window evaluations (iterations + 1 per seed), counted by lane 0
+  const int64_t n_claims = worklist ? (int64_t)__ldg(n_work_dev) : n_seeds;
   while (true) {
     int s = 0;
     if (lane == 0) s = atomicAdd(work_counter, 1);
     s = __shfl_sync(FULL, s, 0);
-    if (s >= n_seeds) break;
+    if (s >= n_claims) break;
+    int it = 0, n_within = 0;
+    if (worklist) {
+      s = __ldg(worklist + s);
+      it = -1 - iters[s];
+    }
+    const int it_first = it;
+    bool unfinished = false;
     double m[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) m[k] = means[k * seed_stride + s];
-    int it = 0, n_within = 0;
     while (true) {
       // cell of the current mean; neighbour block clipped to the grid
       int c[3] = {0, 0, 0};
@@ -341,13 +354,17 @@ ms_grid_modes_kernel(const double* __restrict__ pts, int64_t pts_stride, GridDev
       }
       if (sqrt(shift2) <= stop || it == max_iter) break;  // sklearn:120-125
       ++it;
+      if (eval_limit > 0 && it - it_first >= eval_limit) {
+        unfinished = true;
+        break;
+      }
     }
     if (lane == 0) {
 #pragma unroll
       for (int k = 0; k < D; ++k) means[k * seed_stride + s] = m[k];
       counts[s] = n_within;
-      iters[s] = it;
-      steps += (unsigned)it + 1u;
+      iters[s] = unfinished ? -1 - it : it;
+      steps += (unsigned)(it - it_first) + (unfinished ? 0u : 1u);
     }
   }
   // one statistics update per warp for the whole launch
@@ -360,6 +377,34 @@ ms_grid_modes_kernel(const double* __restrict__ pts, int64_t pts_stride, GridDev
     atomicAdd(reinterpret_cast<unsigned long long*>(work_counter + 2), tests);
     atomicAdd(reinterpret_cast<unsigned long long*>(work_counter + 4), steps);
   }
+}
+
+// the warp-per-seed climb with its optional modes (see the kernel); `n_seeds` sizes the launch in every mode
+int ms_grid_modes_launch(const double* points_sorted, int64_t n_points, int64_t sorted_stride, const cb200_grid* grid,
+                         const int* cell_start, double* means, int64_t seed_stride, int64_t n_seeds, double bandwidth,
+                         int max_iter, int* counts, int* iters, int* work_counter, const int* worklist,
+                         const long long* n_work_dev, int eval_limit, cudaStream_t st) {
+  if (!points_sorted || !grid || !cell_start || !means || !counts || !iters || !work_counter || n_seeds < 0)
+    return CB200_EINVAL;
+  if (n_seeds == 0) return CB200_OK;
+  if (n_seeds > INT32_MAX || !(grid->cell >= bandwidth)) return CB200_EINVAL;
+  (void)n_points;
+  const GridDev g = to_dev(*grid);
+  const int64_t warps_needed = n_seeds;
+  int64_t blocks = (warps_needed + MSG_THREADS / 32 - 1) / (MSG_THREADS / 32);
+  const int64_t cap = (int64_t)CB200_SM_COUNT * 8;  // persistent grid, dynamic seed claiming
+  if (blocks > cap) blocks = cap;
+  const double r2 = bandwidth * bandwidth, stop = 1e-3 * bandwidth;
+  if (grid->num_dims == 2)
+    ms_grid_modes_kernel<2><<<(int)blocks, MSG_THREADS, 0, st>>>(points_sorted, sorted_stride, g, cell_start, means,
+                                                                 seed_stride, n_seeds, r2, stop, max_iter, counts,
+                                                                 iters, work_counter, worklist, n_work_dev, eval_limit);
+  else
+    ms_grid_modes_kernel<3><<<(int)blocks, MSG_THREADS, 0, st>>>(points_sorted, sorted_stride, g, cell_start, means,
+                                                                 seed_stride, n_seeds, r2, stop, max_iter, counts,
+                                                                 iters, work_counter, worklist, n_work_dev, eval_limit);
+  CB200_LAUNCH_CHECK();
+  return CB200_OK;
 }
 
 }  // namespace cb200
@@ -511,28 +556,8 @@ int cb200_grid_build(const double* points, int64_t n_points, int64_t pts_stride,
 int cb200_ms_grid_modes(const double* points_sorted, int64_t n_points, int64_t sorted_stride, const cb200_grid* grid,
                         const int* cell_start, double* means, int64_t seed_stride, int64_t n_seeds, double bandwidth,
                         int max_iter, int* counts, int* iters, int* work_counter, void* stream) {
-  if (!points_sorted || !grid || !cell_start || !means || !counts || !iters || !work_counter || n_seeds < 0)
-    return CB200_EINVAL;
-  if (n_seeds == 0) return CB200_OK;
-  if (n_seeds > INT32_MAX || !(grid->cell >= bandwidth)) return CB200_EINVAL;
-  (void)n_points;
-  cudaStream_t st = (cudaStream_t)stream;
-  const GridDev g = to_dev(*grid);
-  const int64_t warps_needed = n_seeds;
-  int64_t blocks = (warps_needed + MSG_THREADS / 32 - 1) / (MSG_THREADS / 32);
-  const int64_t cap = (int64_t)CB200_SM_COUNT * 8;  // persistent grid, dynamic seed claiming
-  if (blocks > cap) blocks = cap;
-  const double r2 = bandwidth * bandwidth, stop = 1e-3 * bandwidth;
-  if (grid->num_dims == 2)
-    ms_grid_modes_kernel<2><<<(int)blocks, MSG_THREADS, 0, st>>>(points_sorted, sorted_stride, g, cell_start, means,
-                                                                 seed_stride, n_seeds, r2, stop, max_iter, counts,
-                                                                 iters, work_counter);
-  else
-    ms_grid_modes_kernel<3><<<(int)blocks, MSG_THREADS, 0, st>>>(points_sorted, sorted_stride, g, cell_start, means,
-                                                                 seed_stride, n_seeds, r2, stop, max_iter, counts,
-                                                                 iters, work_counter);
-  CB200_LAUNCH_CHECK();
-  return CB200_OK;
+  return ms_grid_modes_launch(points_sorted, n_points, sorted_stride, grid, cell_start, means, seed_stride, n_seeds, bandwidth,
+                              max_iter, counts, iters, work_counter, nullptr, nullptr, 0, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -714,6 +714,65 @@ struct UniqueEmit {
   }
 };
 
+// ---- distinct trajectories ---------------------------------------------------------------------------
+// Two seeds whose means are bit-identical after the same number of iterations follow the same trajectory from there on.
+// After ONE window evaluation most seeds of an object already share their mean (the window of every seed near the
+// centre holds the same points); cb200_ms_grid_modes_distinct climbs only one representative (the lowest seed index) of
+// every distinct unfinished mean and drops the copies (count = 0: they would end as copies of the representative's
+// mode, which the suppression merges anyway).
+__global__ void __launch_bounds__(256)
+unfinished_insert_kernel(const double* __restrict__ means, int64_t stride, int D, const int* __restrict__ iters, int64_t n,
+                         unsigned long long* __restrict__ table, uint64_t mask) {
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
+    if (iters[i] >= 0) continue;  // finished within the first evaluation
+    const unsigned long long mine = (unsigned long long)i + 1ull;
+    uint64_t slot = mode_hash(means, stride, D, i) & mask;
+    while (true) {
+      unsigned long long cur = *((volatile unsigned long long*)&table[slot]);
+      if (cur == 0ull) {
+        cur = atomicCAS(&table[slot], 0ull, mine);
+        if (cur == 0ull) break;
+      }
+      if (same_mode(means, stride, D, i, (int64_t)(cur - 1ull))) {
+        if (mine < cur) atomicMin(&table[slot], mine);
+        break;
+      }
+      slot = (slot + 1) & mask;
+    }
+  }
+}
+
+// representatives go to the worklist; the copies are dropped (idempotent side effect: the predicate runs twice)
+struct RepresentativePred {
+  const double* means;
+  int64_t stride;
+  int D;
+  const int* iters;
+  int* counts;
+  const unsigned long long* table;
+  uint64_t mask;
+  __device__ __forceinline__ bool operator()(int64_t i) const {
+    if (iters[i] >= 0) return false;
+    uint64_t slot = mode_hash(means, stride, D, i) & mask;
+    while (true) {
+      const unsigned long long cur = table[slot];
+      if (cur == 0ull) return false;  // cannot happen
+      const int64_t j = (int64_t)(cur - 1ull);
+      if (j == i) return true;
+      if (same_mode(means, stride, D, i, j)) {
+        counts[i] = 0;
+        return false;
+      }
+      slot = (slot + 1) & mask;
+    }
+  }
+};
+struct WorklistEmit {
+  int* worklist;
+  __device__ __forceinline__ void operator()(int64_t i, long long d) const { worklist[d] = (int)i; }
+};
+
 static uint64_t unique_table_slots(int64_t n) {
   uint64_t slots = 1024;
   while (slots < (uint64_t)(2 * n)) slots <<= 1;
@@ -841,6 +900,44 @@ int cb200_unique_modes(const double* modes, int64_t seed_stride, int num_dims, c
   UniquePred pred{modes, seed_stride, num_dims, counts, table, slots - 1};
   UniqueEmit emit{modes, seed_stride, num_dims, counts, modes_out, out_stride, counts_out};
   return run_compaction(pred, emit, n_seeds, out_stride, n_out, compact_ws, st);
+}
+
+int64_t cb200_ms_distinct_workspace_bytes(int64_t n_seeds) {
+  if (n_seeds < 0) return -1;
+  return (int64_t)(unique_table_slots(n_seeds) * sizeof(unsigned long long)) + ((4 * n_seeds + 255) / 256 * 256) +
+         CompactWorkspace::bytes(n_seeds) + 1024;
+}
+
+int cb200_ms_grid_modes_distinct(const double* points_sorted, int64_t n_points, int64_t sorted_stride, const cb200_grid* grid,
+                                 const int* cell_start, double* means, int64_t seed_stride, int64_t n_seeds,
+                                 double bandwidth, int max_iter, int* counts, int* iters, int* work, void* workspace,
+                                 int64_t workspace_bytes, void* stream) {
+  if (!workspace || !work || n_seeds < 0 || workspace_bytes < cb200_ms_distinct_workspace_bytes(n_seeds)) return CB200_EINVAL;
+  if (n_seeds == 0) return CB200_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = grid ? grid->num_dims : 0;
+  // pass 1: ONE window evaluation per seed; unconverged seeds are left with iters = -2
+  int rc = ms_grid_modes_launch(points_sorted, n_points, sorted_stride, grid, cell_start, means, seed_stride, n_seeds, bandwidth,
+                                max_iter, counts, iters, work, nullptr, nullptr, 1, st);
+  if (rc != CB200_OK) return rc;
+  char* w = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
+  const uint64_t slots = unique_table_slots(n_seeds);
+  auto* table = reinterpret_cast<unsigned long long*>(w);
+  w += slots * sizeof(unsigned long long);
+  int* worklist = reinterpret_cast<int*>(w);
+  w += (4 * n_seeds + 255) / 256 * 256;
+  long long* n_work = reinterpret_cast<long long*>(w);
+  w += 256;
+  CB200_CUDA_TRY(cudaMemsetAsync(table, 0, slots * sizeof(unsigned long long), st));
+  unfinished_insert_kernel<<<grid_for(n_seeds, 256, 1, 16), 256, 0, st>>>(means, seed_stride, D, iters, n_seeds, table, slots - 1);
+  CB200_LAUNCH_CHECK();
+  RepresentativePred pred{means, seed_stride, D, iters, counts, table, slots - 1};
+  WorklistEmit emit{worklist};
+  rc = run_compaction(pred, emit, n_seeds, n_seeds, n_work, w, st);
+  if (rc != CB200_OK) return rc;
+  // pass 2: the representatives, to convergence
+  return ms_grid_modes_launch(points_sorted, n_points, sorted_stride, grid, cell_start, means, seed_stride, n_seeds, bandwidth,
+                              max_iter, counts, iters, work + 8, worklist, n_work, 0, st);
 }
 
 }  // extern "C"

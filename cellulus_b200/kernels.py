@@ -541,6 +541,28 @@ def ms_grid_modes(sorted_pts, n, grid, cell_start, seeds_soa, n_seeds, bandwidth
     return counts, iters
 
 
+def ms_grid_modes_distinct(sorted_pts, n, grid, cell_start, seeds_soa, n_seeds, bandwidth, max_iter=300):
+    """`cb200_ms_grid_modes_distinct`: one window evaluation for every seed, then only one representative of every
+    distinct unfinished mean climbs on.  `seeds_soa` is updated in place; returns `(counts, iters)` where the merged
+    copies have count 0 and a negative `iters` (they would end as copies of their representative's mode)."""
+    dev = sorted_pts.device
+    counts = torch.zeros(max(n_seeds, 1), dtype=torch.int32, device=dev)
+    iters = torch.zeros(max(n_seeds, 1), dtype=torch.int32, device=dev)
+    work = torch.zeros(16, dtype=torch.int32, device=dev)
+    nbytes = _lib().cb200_ms_distinct_workspace_bytes(n_seeds)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    rc = _lib().cb200_ms_grid_modes_distinct(_ptr(sorted_pts), n, sorted_pts.stride(0), C.byref(grid), _ptr(cell_start),
+                                             _ptr(seeds_soa), seeds_soa.stride(0), n_seeds, float(bandwidth),
+                                             int(max_iter), _ptr(counts), _ptr(iters), _ptr(work), _ptr(ws), nbytes,
+                                             _stream(sorted_pts))
+    check(rc, "cb200_ms_grid_modes_distinct")
+    launch_counter["calls"] += 1
+    w = work.view(torch.int64)  # [1] tests, [2] steps of pass 1; [5], [6] of pass 2
+    stats = torch.stack([w[1] + w[5], w[2] + w[6]])
+    last_grid_modes_work[0] = torch.cat([work[:2], stats.view(torch.int32)])
+    return counts, iters
+
+
 def ms_brute_modes(points, n, seeds_soa, n_seeds, bandwidth, max_iter=300):
     """Climb every seed to convergence (brute-force n-body form); one accumulate + one update launch per
     iteration over the still-active seeds.  `seeds_soa` is updated in place.  Returns `(counts, iters)`."""

@@ -244,7 +244,8 @@ def cuda_ops(method: str = "auto") -> MeanShiftOps:
             use = "brute" if n * s <= MS._BRUTE_PAIR_LIMIT else "grid"
         if use == "grid":
             sorted_pts, cell_start, _ = K.grid_build(pts, n, grid)
-            counts, iters = K.ms_grid_modes(sorted_pts, n, grid, cell_start, sd, s, bandwidth)
+            # distinct trajectories only: the merged copies come back with count 0 and are dropped by `dedupe`
+            counts, iters = K.ms_grid_modes_distinct(sorted_pts, n, grid, cell_start, sd, s, bandwidth)
         else:
             counts, iters = K.ms_brute_modes(pts, n, sd, s, bandwidth)
         return sd[:, :s], counts[:s], iters[:s]

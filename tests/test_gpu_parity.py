@@ -775,6 +775,47 @@ def test_mean_shift_matches_oracle_larger_scene():
         assert np.array_equal(labels.cpu().numpy() > 0, ref > 0)
 
 
+@pytest.mark.parametrize("shape,objects,radius,bw,rp", [((160, 200), 40, 8.0, 5.0, 0.3), ((40, 96, 96), 30, 8.0, 6.0, 1.0),
+                                                        ((24, 40, 40), 3, 9.0, 2.5, 1.0), ((30, 30), 1, 4.0, 40.0, 1.0)])
+def test_distinct_trajectory_climb_equals_full_climb(shape, objects, radius, bw, rp):
+    """`cb200_ms_grid_modes_distinct` (one evaluation per seed, then one representative per distinct unfinished mean)
+    against `cb200_ms_grid_modes` (every seed to convergence): every seed it did not merge holds bit for bit the same
+    mode, count and iteration count; the merged copies are exactly seeds whose full climb ends in a mode another seed
+    reports; the distinct (mode, count) sets are equal, and so are the centres."""
+    dev = _dev()
+    emb_np, _, _ = synthetic.blob_scene(shape, objects, radius=radius, seed=13)
+    emb = torch.from_numpy(emb_np).to(dev)
+    pts, _, n, _ = K.fg_compact(emb, 0.5)
+    fit, n_fit = K.select_points(pts, n, K.bernoulli_flags(n, rp, 3, dev)) if rp < 1.0 else (pts, n)
+    lo, hi = K.bounding_box(fit, n_fit)
+    grid = K.plan_grid(lo, hi, bw)
+    sorted_pts, cell_start, _ = K.grid_build(fit, n_fit, grid)
+    full = fit.clone()
+    c_full, i_full = K.ms_grid_modes(sorted_pts, n_fit, grid, cell_start, full, n_fit, bw)
+    tests_full = K.grid_modes_distance_tests()
+    dist = fit.clone()
+    c_dist, i_dist = K.ms_grid_modes_distinct(sorted_pts, n_fit, grid, cell_start, dist, n_fit, bw)
+    tests_dist = K.grid_modes_distance_tests()
+    kept = (c_dist[:n_fit] > 0) | (c_full[:n_fit] == 0)
+    assert torch.equal(c_dist[:n_fit][kept], c_full[:n_fit][kept])
+    assert torch.equal(i_dist[:n_fit][kept], i_full[:n_fit][kept])
+    assert torch.equal(dist[:, :n_fit][:, kept].view(torch.int64), full[:, :n_fit][:, kept].view(torch.int64))
+    merged = ~kept
+    assert (i_dist[:n_fit][merged] < 0).all()
+    # same distinct (mode, count) pairs
+    def distinct(m, c):
+        u, cu, k = K.unique_modes(m, c, n_fit)
+        rows = torch.cat([u[:, :k].view(torch.int64), cu[:k].long()[None]], 0).T.cpu().numpy()
+        return np.unique(rows, axis=0)
+    assert np.array_equal(distinct(full, c_full), distinct(dist, c_dist))
+    a, ka = K.nms_centres(full, c_full, n_fit, bw, grid)
+    b, kb = K.nms_centres(dist, c_dist, n_fit, bw, grid)
+    assert ka == kb and torch.equal(a[:, :ka], b[:, :kb])
+    assert tests_dist <= tests_full
+    if n_fit > 5000:
+        assert int(merged.sum()) > n_fit // 4 and tests_dist < 0.8 * tests_full  # it actually saves work
+
+
 def test_unique_modes_keeps_the_copy_the_suppression_keeps():
     """`cb200_unique_modes`: one copy per bit-identical mode with count > 0 -- the one with the highest count, then
     the lowest index -- in input order; against numpy on crafted duplicates, and the suppression gives the same
