@@ -351,7 +351,11 @@ def bench_detect(dev, windows, with_cpu):
                                "seed, then the distinct unfinished means) incl. the merge pass between them",
                      "kernel_ms": k_ms,
                      "every_seed_to_convergence": {"kernel_ms": full_ms, "distance_tests": full_tests, "climb_steps": full_steps,
-                                                   "note": "cb200_ms_grid_modes: the work scikit-learn does per seed"},
+                                                   "achieved": full_tests * flop_per_test / (full_ms * 1e-3) / 1e12,
+                                                   "frac": full_tests * flop_per_test / (full_ms * 1e-3) / 1e12 / fp64_peak,
+                                                   "note": "cb200_ms_grid_modes, one launch: the work scikit-learn does per "
+                                                           "seed; the shipped form does 47 % fewer tests in 20 % less time "
+                                                           "(its second pass is a latency tail of a few long climbs)"},
                      "kernel_share_of_volume": k_ms / ms,
                      "distance_tests_per_launch": tests, "flop_per_test": flop_per_test,
                      "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
