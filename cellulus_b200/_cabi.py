@@ -98,8 +98,8 @@ PROTOTYPES = {
     "cb200_grid_build": (_i, [_p, _i64, _i64, C.POINTER(Grid), _p, _i64, _p, _p, _p, _i64, _p]),
     "cb200_ms_grid_modes": (_i, [_p, _i64, _i64, C.POINTER(Grid), _p, _p, _i64, _i64, _d, _i, _p, _p, _p, _p]),
     "cb200_ms_distinct_workspace_bytes": (_i64, [_i64]),
-    "cb200_ms_grid_modes_distinct": (_i, [_p, _i64, _i64, C.POINTER(Grid), _p, _p, _i64, _i64, _d, _i, _p, _p, _p, _p, _i64,
-                                          _p]),
+    "cb200_ms_grid_modes_distinct": (_i, [_p, _i64, _i64, C.POINTER(Grid), _p, _p, _i64, _i64, _d, _i, _i, _p, _p, _p, _p,
+                                          _i64, _p]),
     "cb200_bin_seeds_workspace_bytes": (_i64, [_i64]),
     "cb200_bin_seeds": (_i, [_p, _i64, _i64, _i, _d, _p, _i64, _p, _p, _p, _i64, _p]),
     "cb200_unique_modes_workspace_bytes": (_i64, [_i64]),

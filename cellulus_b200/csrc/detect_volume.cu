@@ -235,8 +235,11 @@ extern "C" int cb200_detect_volume(const void* emb, int dtype, int num_dims, con
     uint8_t* distinct_ws;
     const int64_t distinct_bytes = cb200_ms_distinct_workspace_bytes(n_fit);
     POOL_GET(&distinct_ws, (size_t)distinct_bytes);
+    // one merge for ordinary seed counts; millions of dense seeds keep meeting as they climb (CB200_MS_ROUNDS overrides)
+    static const int rounds_env = [] { const char* e = getenv("CB200_MS_ROUNDS"); return e ? atoi(e) : 0; }();
+    const int merge_rounds = rounds_env >= 1 && rounds_env <= 30 ? rounds_env : (n_fit < 1000000 ? 1 : 4);
     CB200_TRY_RC(cb200_ms_grid_modes_distinct(sorted, n_fit, fit_cap, &grid, cell_start, modes, fit_cap, n_fit, bandwidth,
-                                              max_iter > 0 ? max_iter : 300, counts, iters, work, distinct_ws,
+                                              max_iter > 0 ? max_iter : 300, merge_rounds, counts, iters, work, distinct_ws,
                                               distinct_bytes, st));
   }
   info->n_seeds = n_fit;

@@ -720,12 +720,28 @@ struct UniqueEmit {
 // centre holds the same points); cb200_ms_grid_modes_distinct climbs only one representative (the lowest seed index) of
 // every distinct unfinished mean and drops the copies (count = 0: they would end as copies of the representative's
 // mode, which the suppression merges anyway).
+constexpr int MS_DROPPED = INT_MIN;  // iters[] of a seed that was merged into its representative
+constexpr int MS_MAX_MERGE_ROUNDS = 30;
+
+// tests / window evaluations of the launches after the first, summed into the caller's second statistics block
+__global__ void ms_stats_sum_kernel(const int* __restrict__ blocks, int n_blocks, int* __restrict__ out8) {
+  if (threadIdx.x == 0) {
+    unsigned long long tests = 0, steps = 0;
+    for (int b = 0; b < n_blocks; ++b) {
+      tests += *reinterpret_cast<const unsigned long long*>(blocks + 8 * b + 2);
+      steps += *reinterpret_cast<const unsigned long long*>(blocks + 8 * b + 4);
+    }
+    *reinterpret_cast<unsigned long long*>(out8 + 2) = tests;
+    *reinterpret_cast<unsigned long long*>(out8 + 4) = steps;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 unfinished_insert_kernel(const double* __restrict__ means, int64_t stride, int D, const int* __restrict__ iters, int64_t n,
                          unsigned long long* __restrict__ table, uint64_t mask) {
   const int64_t gs = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
-    if (iters[i] >= 0) continue;  // finished within the first evaluation
+    if (iters[i] >= 0 || iters[i] == MS_DROPPED) continue;  // finished, or merged into another seed earlier
     const unsigned long long mine = (unsigned long long)i + 1ull;
     uint64_t slot = mode_hash(means, stride, D, i) & mask;
     while (true) {
@@ -748,12 +764,12 @@ struct RepresentativePred {
   const double* means;
   int64_t stride;
   int D;
-  const int* iters;
+  int* iters;
   int* counts;
   const unsigned long long* table;
   uint64_t mask;
   __device__ __forceinline__ bool operator()(int64_t i) const {
-    if (iters[i] >= 0) return false;
+    if (iters[i] >= 0 || iters[i] == MS_DROPPED) return false;
     uint64_t slot = mode_hash(means, stride, D, i) & mask;
     while (true) {
       const unsigned long long cur = table[slot];
@@ -762,6 +778,7 @@ struct RepresentativePred {
       if (j == i) return true;
       if (same_mode(means, stride, D, i, j)) {
         counts[i] = 0;
+        iters[i] = MS_DROPPED;
         return false;
       }
       slot = (slot + 1) & mask;
@@ -905,21 +922,18 @@ int cb200_unique_modes(const double* modes, int64_t seed_stride, int num_dims, c
 int64_t cb200_ms_distinct_workspace_bytes(int64_t n_seeds) {
   if (n_seeds < 0) return -1;
   return (int64_t)(unique_table_slots(n_seeds) * sizeof(unsigned long long)) + ((4 * n_seeds + 255) / 256 * 256) +
-         CompactWorkspace::bytes(n_seeds) + 1024;
+         CompactWorkspace::bytes(n_seeds) + 2048;
 }
 
 int cb200_ms_grid_modes_distinct(const double* points_sorted, int64_t n_points, int64_t sorted_stride, const cb200_grid* grid,
                                  const int* cell_start, double* means, int64_t seed_stride, int64_t n_seeds,
-                                 double bandwidth, int max_iter, int* counts, int* iters, int* work, void* workspace,
-                                 int64_t workspace_bytes, void* stream) {
+                                 double bandwidth, int max_iter, int merge_rounds, int* counts, int* iters, int* work,
+                                 void* workspace, int64_t workspace_bytes, void* stream) {
   if (!workspace || !work || n_seeds < 0 || workspace_bytes < cb200_ms_distinct_workspace_bytes(n_seeds)) return CB200_EINVAL;
+  if (merge_rounds < 1 || merge_rounds > MS_MAX_MERGE_ROUNDS) return CB200_EINVAL;
   if (n_seeds == 0) return CB200_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int D = grid ? grid->num_dims : 0;
-  // pass 1: ONE window evaluation per seed; unconverged seeds are left with iters = -2
-  int rc = ms_grid_modes_launch(points_sorted, n_points, sorted_stride, grid, cell_start, means, seed_stride, n_seeds, bandwidth,
-                                max_iter, counts, iters, work, nullptr, nullptr, 1, st);
-  if (rc != CB200_OK) return rc;
   char* w = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
   const uint64_t slots = unique_table_slots(n_seeds);
   auto* table = reinterpret_cast<unsigned long long*>(w);
@@ -928,16 +942,30 @@ int cb200_ms_grid_modes_distinct(const double* points_sorted, int64_t n_points, 
   w += (4 * n_seeds + 255) / 256 * 256;
   long long* n_work = reinterpret_cast<long long*>(w);
   w += 256;
-  CB200_CUDA_TRY(cudaMemsetAsync(table, 0, slots * sizeof(unsigned long long), st));
-  unfinished_insert_kernel<<<grid_for(n_seeds, 256, 1, 16), 256, 0, st>>>(means, seed_stride, D, iters, n_seeds, table, slots - 1);
-  CB200_LAUNCH_CHECK();
-  RepresentativePred pred{means, seed_stride, D, iters, counts, table, slots - 1};
-  WorklistEmit emit{worklist};
-  rc = run_compaction(pred, emit, n_seeds, n_seeds, n_work, w, st);
+  int* blocks = reinterpret_cast<int*>(w);  // claim counter + statistics of every launch after the first: 8 ints each
+  w += 1024;
+  CB200_CUDA_TRY(cudaMemsetAsync(blocks, 0, 1024, st));
+  // first evaluation of every seed; unconverged seeds are left with iters = -2
+  int rc = ms_grid_modes_launch(points_sorted, n_points, sorted_stride, grid, cell_start, means, seed_stride, n_seeds, bandwidth,
+                                max_iter, counts, iters, work, nullptr, nullptr, 1, st);
   if (rc != CB200_OK) return rc;
-  // pass 2: the representatives, to convergence
-  return ms_grid_modes_launch(points_sorted, n_points, sorted_stride, grid, cell_start, means, seed_stride, n_seeds, bandwidth,
-                              max_iter, counts, iters, work + 8, worklist, n_work, 0, st);
+  for (int r = 1; r <= merge_rounds; ++r) {
+    // merge the unfinished seeds by the bit pattern of their mean (all of them have done r iterations)
+    CB200_CUDA_TRY(cudaMemsetAsync(table, 0, slots * sizeof(unsigned long long), st));
+    unfinished_insert_kernel<<<grid_for(n_seeds, 256, 1, 16), 256, 0, st>>>(means, seed_stride, D, iters, n_seeds, table, slots - 1);
+    CB200_LAUNCH_CHECK();
+    RepresentativePred pred{means, seed_stride, D, iters, counts, table, slots - 1};
+    WorklistEmit emit{worklist};
+    rc = run_compaction(pred, emit, n_seeds, n_seeds, n_work, w, st);
+    if (rc != CB200_OK) return rc;
+    // the representatives: one more evaluation each, or -- after the last merge -- to convergence
+    rc = ms_grid_modes_launch(points_sorted, n_points, sorted_stride, grid, cell_start, means, seed_stride, n_seeds, bandwidth,
+                              max_iter, counts, iters, blocks + 8 * (r - 1), worklist, n_work, r < merge_rounds ? 1 : 0, st);
+    if (rc != CB200_OK) return rc;
+  }
+  ms_stats_sum_kernel<<<1, 32, 0, st>>>(blocks, merge_rounds, work + 8);
+  CB200_LAUNCH_CHECK();
+  return CB200_OK;
 }
 
 }  // extern "C"

@@ -8,6 +8,7 @@ is no CPU fallback (a CPU tensor raises).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import numpy as np
@@ -541,7 +542,16 @@ def ms_grid_modes(sorted_pts, n, grid, cell_start, seeds_soa, n_seeds, bandwidth
     return counts, iters
 
 
-def ms_grid_modes_distinct(sorted_pts, n, grid, cell_start, seeds_soa, n_seeds, bandwidth, max_iter=300):
+def default_merge_rounds(n_seeds: int) -> int:
+    """How often `ms_grid_modes_distinct` merges identical trajectories: once for ordinary seed counts (every further
+    round costs two small launches and a merge pass), more often for millions of dense seeds (CB200_MS_ROUNDS overrides)."""
+    env = os.environ.get("CB200_MS_ROUNDS")
+    if env:
+        return max(1, min(30, int(env)))
+    return 1 if n_seeds < 1_000_000 else 4
+
+
+def ms_grid_modes_distinct(sorted_pts, n, grid, cell_start, seeds_soa, n_seeds, bandwidth, max_iter=300, merge_rounds=None):
     """`cb200_ms_grid_modes_distinct`: one window evaluation for every seed, then only one representative of every
     distinct unfinished mean climbs on.  `seeds_soa` is updated in place; returns `(counts, iters)` where the merged
     copies have count 0 and a negative `iters` (they would end as copies of their representative's mode)."""
@@ -553,7 +563,8 @@ def ms_grid_modes_distinct(sorted_pts, n, grid, cell_start, seeds_soa, n_seeds, 
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     rc = _lib().cb200_ms_grid_modes_distinct(_ptr(sorted_pts), n, sorted_pts.stride(0), C.byref(grid), _ptr(cell_start),
                                              _ptr(seeds_soa), seeds_soa.stride(0), n_seeds, float(bandwidth),
-                                             int(max_iter), _ptr(counts), _ptr(iters), _ptr(work), _ptr(ws), nbytes,
+                                             int(max_iter), int(merge_rounds or default_merge_rounds(n_seeds)),
+                                             _ptr(counts), _ptr(iters), _ptr(work), _ptr(ws), nbytes,
                                              _stream(sorted_pts))
     check(rc, "cb200_ms_grid_modes_distinct")
     launch_counter["calls"] += 1

@@ -352,7 +352,9 @@ CB200_API int cb200_ms_grid_modes(const double* points_sorted, int64_t n_points,
  * The same climb over DISTINCT trajectories only.  Two seeds whose means are bit-identical after the same number of
  * iterations follow the same trajectory from there on, and after one window evaluation most seeds of an object already
  * share their mean.  Pass 1 gives every seed ONE evaluation; the unconverged seeds are merged by the bit pattern of their
- * mean; pass 2 climbs one representative (the lowest seed index) of every distinct mean to convergence.  On return
+ * mean; pass 2 climbs one representative (the lowest seed index) of every distinct mean to convergence.  With
+ * merge_rounds > 1 the representatives get ONE more evaluation per round and are merged again (trajectories keep
+ * meeting as they approach the same window; worth it for millions of dense seeds), to convergence after the last.  On return
  * every finished seed and every representative holds exactly what cb200_ms_grid_modes gives it (mean, count,
  * iterations); the merged copies have count 0 (they would end as copies of their representative's mode, which the
  * centre post-processing merges anyway), so cb200_unique_modes / cb200_nms_suppress see the same distinct modes.
@@ -364,7 +366,7 @@ CB200_API int64_t cb200_ms_distinct_workspace_bytes(int64_t n_seeds);
 CB200_API int cb200_ms_grid_modes_distinct(const double* points_sorted, int64_t n_points, int64_t sorted_stride,
                         const cb200_grid* grid, const int* cell_start,
                         double* means, int64_t seed_stride, int64_t n_seeds,
-                        double bandwidth, int max_iter, int* counts, int* iters, int* work,
+                        double bandwidth, int max_iter, int merge_rounds /* 1..30 */, int* counts, int* iters, int* work,
                         void* workspace, int64_t workspace_bytes, void* stream);
 
 /*

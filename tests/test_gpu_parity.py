@@ -793,27 +793,31 @@ def test_distinct_trajectory_climb_equals_full_climb(shape, objects, radius, bw,
     full = fit.clone()
     c_full, i_full = K.ms_grid_modes(sorted_pts, n_fit, grid, cell_start, full, n_fit, bw)
     tests_full = K.grid_modes_distance_tests()
-    dist = fit.clone()
-    c_dist, i_dist = K.ms_grid_modes_distinct(sorted_pts, n_fit, grid, cell_start, dist, n_fit, bw)
-    tests_dist = K.grid_modes_distance_tests()
-    kept = (c_dist[:n_fit] > 0) | (c_full[:n_fit] == 0)
-    assert torch.equal(c_dist[:n_fit][kept], c_full[:n_fit][kept])
-    assert torch.equal(i_dist[:n_fit][kept], i_full[:n_fit][kept])
-    assert torch.equal(dist[:, :n_fit][:, kept].view(torch.int64), full[:, :n_fit][:, kept].view(torch.int64))
-    merged = ~kept
-    assert (i_dist[:n_fit][merged] < 0).all()
-    # same distinct (mode, count) pairs
     def distinct(m, c):
         u, cu, k = K.unique_modes(m, c, n_fit)
         rows = torch.cat([u[:, :k].view(torch.int64), cu[:k].long()[None]], 0).T.cpu().numpy()
         return np.unique(rows, axis=0)
-    assert np.array_equal(distinct(full, c_full), distinct(dist, c_dist))
+
     a, ka = K.nms_centres(full, c_full, n_fit, bw, grid)
-    b, kb = K.nms_centres(dist, c_dist, n_fit, bw, grid)
-    assert ka == kb and torch.equal(a[:, :ka], b[:, :kb])
-    assert tests_dist <= tests_full
-    if n_fit > 5000:
-        assert int(merged.sum()) > n_fit // 4 and tests_dist < 0.8 * tests_full  # it actually saves work
+    tests_prev = tests_full
+    for merge_rounds in (1, 2, 6):  # merged once, or again after every further evaluation
+        dist = fit.clone()
+        c_dist, i_dist = K.ms_grid_modes_distinct(sorted_pts, n_fit, grid, cell_start, dist, n_fit, bw,
+                                                  merge_rounds=merge_rounds)
+        tests_dist = K.grid_modes_distance_tests()
+        kept = (c_dist[:n_fit] > 0) | (c_full[:n_fit] == 0)
+        assert torch.equal(c_dist[:n_fit][kept], c_full[:n_fit][kept])
+        assert torch.equal(i_dist[:n_fit][kept], i_full[:n_fit][kept])
+        assert torch.equal(dist[:, :n_fit][:, kept].view(torch.int64), full[:, :n_fit][:, kept].view(torch.int64))
+        merged = ~kept
+        assert (i_dist[:n_fit][merged] < 0).all()
+        assert np.array_equal(distinct(full, c_full), distinct(dist, c_dist))  # same distinct (mode, count) pairs
+        b, kb = K.nms_centres(dist, c_dist, n_fit, bw, grid)
+        assert ka == kb and torch.equal(a[:, :ka], b[:, :kb])
+        assert tests_dist <= tests_prev  # more merges never add work
+        tests_prev = tests_dist
+        if n_fit > 5000:
+            assert int(merged.sum()) > n_fit // 4 and tests_dist < 0.8 * tests_full  # it actually saves work
 
 
 def test_unique_modes_keeps_the_copy_the_suppression_keeps():
