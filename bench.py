@@ -1019,7 +1019,7 @@ def run_sweep(args):
                 bw = bw_factor * radius
                 for seeding in ("all_foreground", "grid_binned"):
                     kw = dict(reduction_probability=1.0, bin_seeding=(seeding == "grid_binned"), method="grid",
-                              label_dtype=torch.int32)
+                              label_dtype=torch.int32, distinct=True)
                     if seeding == "all_foreground" and n_m * bw_factor**D > 64:
                         # every point a seed with a wide window: > 1e12 distance tests -- tens of seconds here, weeks on
                         # the CPU reference; left out of the sweep

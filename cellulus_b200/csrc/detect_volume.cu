@@ -228,7 +228,7 @@ extern "C" int cb200_detect_volume(const void* emb, int dtype, int num_dims, con
   // per seed, then one representative of every distinct unfinished mean (cb200_ms_grid_modes_distinct) -- the centres
   // only need the distinct modes, and copies of a trajectory end in copies of its mode.
   static const bool climb_all = [] { const char* e = getenv("CB200_DETECT_CLIMB"); return e && e[0] == 'a'; }();
-  if (climb_all) {
+  if (climb_all || n_fit < 20000) {  // the merge pays from a few ten thousand seeds on
     CB200_TRY_RC(cb200_ms_grid_modes(sorted, n_fit, fit_cap, &grid, cell_start, modes, fit_cap, n_fit, bandwidth,
                                      max_iter > 0 ? max_iter : 300, counts, iters, work, st));
   } else {
@@ -254,7 +254,7 @@ extern "C" int cb200_detect_volume(const void* emb, int dtype, int num_dims, con
   const double* cand = modes;
   const int* cand_counts = counts;
   long long n_cand = n_fit;
-  if (dedupe) {
+  if (dedupe && n_fit >= 4096) {
     double* umodes;
     int* ucounts;
     long long* n_unique_dev;

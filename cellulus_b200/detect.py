@@ -80,7 +80,8 @@ def detect_embeddings(embeddings, bandwidth, threshold=None, num_bandwidths=1, r
     for k in range(num_bandwidths):
         labels, info = MS.segment_embeddings_device(
             embeddings, bandwidth / (2**k), threshold, reduction_probability, seeds=seeds, rng=rng, method=method,
-            label_dtype=label_dtype, want_mask=(k == 0), one_call=one_call, bin_seeding=bin_seeding)
+            label_dtype=label_dtype, want_mask=(k == 0), one_call=one_call, bin_seeding=bin_seeding,
+            distinct=not return_info)
         if k == 0:
             mask = info.pop("mask")
         if label_dtype == torch.uint16:

@@ -31,10 +31,12 @@ def _seeds_to_soa(seeds, D, device):
 
 
 def cluster_points_device(points, n, fit_points, n_fit, bandwidth, seeds=None, method="auto", max_iter=300,
-                          bin_seeding=False):
+                          bin_seeding=False, distinct=False):
     """sklearn `MeanShift(bandwidth, seeds).fit(fit_points)` centre finding on the device.
 
     points / fit_points: SoA (D, cap) float64.  Returns `(centres SoA (D, >=K), K, info)`.
+    `distinct`: climb distinct trajectories only (`cb200_ms_grid_modes_distinct`, grid method): same centres; the
+    per-seed `counts` / `iters` in `info` then mark the merged copies (count 0, negative iterations).
     """
     D = points.shape[0]
     dev = points.device
@@ -53,7 +55,9 @@ def cluster_points_device(points, n, fit_points, n_fit, bandwidth, seeds=None, m
         method = "brute" if n_seeds * n_fit <= _BRUTE_PAIR_LIMIT else "grid"
     if method == "grid":
         sorted_pts, cell_start, _ = K.grid_build(fit_points, n_fit, grid)
-        counts, iters = K.ms_grid_modes(sorted_pts, n_fit, grid, cell_start, seeds_soa, n_seeds, bandwidth, max_iter)
+        # the merge pays from a few ten thousand seeds on (two more launches, a hash pass and a compaction)
+        climb = K.ms_grid_modes_distinct if (distinct and n_seeds >= 20_000) else K.ms_grid_modes
+        counts, iters = climb(sorted_pts, n_fit, grid, cell_start, seeds_soa, n_seeds, bandwidth, max_iter)
     elif method == "brute":
         counts, iters = K.ms_brute_modes(fit_points, n_fit, seeds_soa, n_seeds, bandwidth, max_iter)
     else:
@@ -70,7 +74,7 @@ def cluster_points_device(points, n, fit_points, n_fit, bandwidth, seeds=None, m
 
 def segment_embeddings_device(emb, bandwidth, threshold, reduction_probability=1.0, seeds=None, rng="numpy",
                               fit_flags=None, method="auto", label_dtype=torch.int32, want_mask=False,
-                              philox_seed=0, assign="grid", one_call=False, bin_seeding=False):
+                              philox_seed=0, assign="grid", one_call=False, bin_seeding=False, distinct=False):
     """threshold -> foreground points -> fit subset -> modes -> centres -> labels, all on the device.
 
     emb: (D+1, *S) CUDA tensor (fp32/fp64), channel D = std.  Returns `(labels (*S), info)`;
@@ -82,6 +86,7 @@ def segment_embeddings_device(emb, bandwidth, threshold, reduction_probability=1
     `one_call`: run the identical sequence inside the library (`cb200_detect_volume`: one C-ABI call, no
     interpreter between the kernels); needs the device RNG (or no subsampling) and the grid kernels, and
     reports counts only (no per-seed modes / iterations in `info`).
+    `distinct`: see `cluster_points_device` (same labels, less climbing; per-seed info marks the merged seeds).
     """
     if one_call and seeds is None and not bin_seeding and fit_flags is None and method in ("auto", "grid") and assign == "grid" and (
             rng == "philox" or reduction_probability >= 1.0):
@@ -113,7 +118,7 @@ def segment_embeddings_device(emb, bandwidth, threshold, reduction_probability=1
     else:
         fit_pts, n_fit = pts, n
     centres, k, cinfo = cluster_points_device(pts, n, fit_pts, n_fit, bandwidth, seeds=seeds, method=method,
-                                              bin_seeding=bin_seeding)
+                                              bin_seeding=bin_seeding, distinct=distinct)
     # predict on ALL foreground (:74), scatter, +1; pruned nearest-centre search over the same cell grid
     K.assign_labels(pts, n, centres, k, pix, labels, grid=cinfo["grid"] if assign == "grid" else None)
     info.update(cinfo)
@@ -159,5 +164,6 @@ def mean_shift_segmentation(
         emb_np[0, ch] += np.arange(spatial[axis]).reshape(shape)
     with torch.cuda.device(dev):
         labels, _ = segment_embeddings_device(emb, float(bandwidth), float(threshold), float(reduction_probability),
-                                              seeds=seeds, rng="numpy", method=method, label_dtype=torch.int32)
+                                              seeds=seeds, rng="numpy", method=method, label_dtype=torch.int32,
+                                              distinct=True)
     return labels.cpu().numpy()
