@@ -248,15 +248,14 @@ def bench_detect(dev, windows, with_cpu):
         seeds = fit_pts.clone()
         fn(sorted_pts, n_fit2, grid, cell_start, seeds, n_fit2, DET_BW)  # warm-up outside the capture
         torch.cuda.synchronize(dev)
+        # two graphs: (seed reset + climb) and (seed reset) alone; the difference of their replay times is the climb
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             seeds.copy_(fit_pts)
-            mark0 = torch.zeros(1, device=dev)  # the copy above is outside the timed part: events go around replays of
-            fn(sorted_pts, n_fit2, grid, cell_start, seeds, n_fit2, DET_BW)  # the whole graph, its cost is subtracted below
+            fn(sorted_pts, n_fit2, grid, cell_start, seeds, n_fit2, DET_BW)
         copy_graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(copy_graph):
             seeds.copy_(fit_pts)
-            mark1 = torch.zeros(1, device=dev)
 
         def replay_ms(g):
             times = []
@@ -271,7 +270,6 @@ def bench_detect(dev, windows, with_cpu):
             return float(np.median(times[1:]))
 
         ms = replay_ms(graph) - replay_ms(copy_graph)
-        del mark0, mark1
         return ms, K.grid_modes_distance_tests(), K.grid_modes_climb_steps()
 
     # every seed to convergence (what scikit-learn does: the algorithmic work) ...
