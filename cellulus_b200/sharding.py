@@ -245,7 +245,8 @@ def cuda_ops(method: str = "auto") -> MeanShiftOps:
         if use == "grid":
             sorted_pts, cell_start, _ = K.grid_build(pts, n, grid)
             # distinct trajectories only: the merged copies come back with count 0 and are dropped by `dedupe`
-            counts, iters = K.ms_grid_modes_distinct(sorted_pts, n, grid, cell_start, sd, s, bandwidth)
+            counts, iters = K.ms_grid_modes_distinct(sorted_pts, n, grid, cell_start, sd, s, bandwidth,
+                                                     merge_rounds=K.default_merge_rounds(max(n, s)))
         else:
             counts, iters = K.ms_brute_modes(pts, n, sd, s, bandwidth)
         return sd[:, :s], counts[:s], iters[:s]
