@@ -339,3 +339,33 @@ def test_bin_seeding_oracle_matches_sklearn_golden(golden, case):
     assert np.array_equal(seeds, g[f"{case}_seeds"])  # same bins, same first-seen order, same float32 products
     labels, centres = oms.segment_points(X, None, bw, seeds=seeds)
     assert np.array_equal(centres, g[f"{case}_centres"]) and np.array_equal(labels, g[f"{case}_labels"])
+
+
+def test_identical_trajectories_premise_of_the_distinct_climb():
+    """The two exact shortcuts of the device hill climb, checked on the oracle's arithmetic (which is held to
+    scikit-learn's per-seed results above): (1) seeds whose means are bit-identical after the first window evaluation
+    share the rest of their trajectory -- same final mode, same count, same iteration count; (2) the converged modes
+    are few distinct values, and the centres computed from one copy of each equal the centres computed from all."""
+    from cellulus_b200 import synthetic
+
+    emb, _, _ = synthetic.blob_scene((72, 88), 7, radius=8.0, seed=3, dtype=np.float64)
+    X = oms.points_from_embedding(emb[:2], emb[2] < 0.5)
+    bw = 5.0
+    modes, counts, iters = oms.mean_shift_modes(X, X, bw)
+    first, _, _ = oms.mean_shift_modes(X, X, bw, max_iter=0)  # one evaluation per seed
+    going = iters >= 1  # not converged by that evaluation
+    groups = {}
+    for i in np.nonzero(going)[0]:
+        groups.setdefault(first[i].tobytes(), []).append(i)
+    assert len(groups) < going.sum() // 2  # the merge is worth something
+    for members in groups.values():
+        a = members[0]
+        for b in members[1:]:
+            assert modes[b].tobytes() == modes[a].tobytes() and counts[b] == counts[a] and iters[b] == iters[a]
+    distinct = {}
+    for m, c in zip(modes, counts):
+        if c and (m.tobytes() not in distinct or c > distinct[m.tobytes()][1]):
+            distinct[m.tobytes()] = (m, c)
+    assert len(distinct) < len(X) // 10
+    one_each = oms.nms_centres(np.array([v[0] for v in distinct.values()]), np.array([v[1] for v in distinct.values()]), bw)
+    assert np.array_equal(one_each, oms.nms_centres(modes, counts, bw))
